@@ -1,0 +1,111 @@
+/* snn_heads.h -- C ABI of the B200-native spiking detection heads (libsnn_heads_b200.so).
+ *
+ * The reference (aitor-martinez-seras/SNN-Automotive-Object-Detection) has no FFI: its hot path is two
+ * torch.nn.Module.forward methods built on Norse.  Each entry point below is what a binding for that
+ * path binds; the reference interface it replaces is cited as file:line into the reference repo.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory (torch tensors); the library never
+ *     allocates or frees device memory.  Scratch is a caller-provided workspace whose size the
+ *     matching *_workspace_bytes() call returns.
+ *   - kernels are enqueued on `stream` (a cudaStream_t) and the call returns without synchronising.
+ *   - return value 0 = success, negative SNN_E_* otherwise; snn_last_error() gives the message
+ *     (thread-local).  There is no CPU fallback: a non-sm_100 device is SNN_E_ARCH.
+ *   - `mode` selects how fp32 weights are fed to the bf16 tensor cores.  The other operand of every
+ *     contraction on this path is an exact {0,1} spike, so a weight kept as k bf16 pieces
+ *     (hi + mid + lo) gives exact products; only the fp32 accumulation order differs from the reference.
+ */
+#ifndef SNN_HEADS_H_
+#define SNN_HEADS_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNN_ABI_VERSION 1
+
+#define SNN_MODE_FP32_EXACT 0 /* 3 bf16 pieces per weight (24 mantissa bits): the parity mode          */
+#define SNN_MODE_BF16 1       /* 1 piece: weights rounded to bf16, the throughput mode                 */
+#define SNN_MODE_BF16X2 2     /* 2 pieces (16 mantissa bits)                                           */
+
+#define SNN_OK 0
+#define SNN_E_ARG (-1)       /* bad argument / unsupported shape                                        */
+#define SNN_E_ARCH (-2)      /* device is not sm_100 (B200)                                             */
+#define SNN_E_WORKSPACE (-3) /* workspace too small                                                     */
+#define SNN_E_CUDA (-4)      /* a CUDA runtime/driver call failed                                       */
+
+typedef void* snn_stream_t; /* cudaStream_t */
+
+int snn_version(void);
+const char* snn_last_error(void);
+
+/* Bytes per neuron of a time-packed spike train for T steps: 1 (T<=8), 2 (T<=16), 4 (T<=32). */
+int snn_train_word_bytes(int T);
+/* Number of bf16 pieces per weight for `mode`. */
+int snn_mode_pieces(int mode);
+
+/* ---- one-time weight preparation (re-run only when the fp32 weights change) ------------------------- */
+/* bytes of a prepared weight with `rows` outputs and `cols` inputs */
+size_t snn_prepared_weight_bytes(int rows, int cols, int mode);
+/* RPNHeadSNN.shared_conv.weight [O][C][3][3] fp32 (rpn.py:65-66) -> [pieces][O][9*C] bf16, k = (ky*3+kx)*C + c */
+int snn_prepare_conv3x3_weights(const float* w, int O, int C, int mode, void* out, snn_stream_t stream);
+/* nn.Linear weight [O][K] fp32 (fc6 / fc7, faster_rcnn.py:448,451) -> [pieces][O][K] bf16 */
+int snn_prepare_fc_weights(const float* w, int O, int K, int mode, void* out, snn_stream_t stream);
+
+/* ---- RPNHeadSNN.forward (rpn.py:84-121) ---------------------------------------------------------------
+ * feat_ptrs[l]   : level l features, fp32 NCHW [N][C_in][H[l]][W[l]]            (input `x`, rpn.py:84)
+ * w_shared_prep  : snn_prepare_conv3x3_weights() of shared_conv.weight           (rpn.py:105)
+ * w_cls, w_bbox  : conv_cls.weight [A][C_in], conv_bbox.weight [4A][C_in] fp32   (rpn.py:110,114)
+ * logits_out[l]  : fp32 NCHW [N][A][H][W]   = last-step membrane of lif_obj      (rpn.py:118)
+ * bbox_out[l]    : fp32 NCHW [N][4A][H][W]  = last-step membrane of lif_bbox     (rpn.py:119)
+ * spike_trains_out[l] (nullable array / entries): shared_lif spikes, NHWC [N][H][W][C_in] words of
+ *                  snn_train_word_bytes(T) bytes, bit t = spk_shared at step t   (rpn.py:106)
+ * spike_counts_out (nullable): [n_levels][N] total shared_lif spikes per level and image (must be zeroed
+ *                  by the caller; accumulated with integer atomics -> deterministic)
+ * T = num_steps (rpn.py:52, 1 <= T <= 32); C_in multiple of 128; every level processed independently
+ * with fresh state exactly as rpn.py:90-96. */
+size_t snn_rpn_head_workspace_bytes(const int* H, const int* W, int n_levels, int N, int C_in, int T, int mode);
+int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* W, int n_levels, int N, int C_in,
+                         int A, int T, int mode, const void* w_shared_prep, const float* w_cls, const float* w_bbox,
+                         void* const* logits_out, void* const* bbox_out, void* const* spike_trains_out,
+                         unsigned long long* spike_counts_out, void* workspace, size_t workspace_bytes,
+                         snn_stream_t stream);
+
+/* ---- FastRCNNPredictorSNNFull.forward (faster_rcnn.py:470-516) -----------------------------------------
+ * x          : RoI features fp32 [R][K] (= [R][256][7][7] flattened, k = c*49 + h*7 + w; faster_rcnn.py:474)
+ * w6_prep    : snn_prepare_fc_weights() of fc6.weight [Hdim][K];  w7_prep: of fc7.weight [Hdim][Hdim]
+ * w_cls      : cls_score.weight [C][Hdim] fp32; w_bbox: bbox_pred.weight [n_box_out][Hdim] fp32
+ *              (n_box_out = 4C, or 4 with only_one_bbox; faster_rcnn.py:455-467)
+ * cls_out    : fp32 [R][C] last-step membrane of lif_cls;  bbox_out: fp32 [R][n_box_out] (faster_rcnn.py:513-516)
+ * spk6_trains, spk7_trains (nullable): [R][Hdim] spike-train words of lif6 / lif7 (faster_rcnn.py:499,501)
+ * spike_counts_out (nullable): unsigned [2][R] spikes per RoI of lif6 and lif7 over all T steps.  When
+ *              given, fc6 is also evaluated for the step whose spikes only the statistics need.
+ * K multiple of 64, Hdim multiple of 256, 3 <= T <= 32, R >= 1 (ragged R is handled by TMA zero fill). */
+size_t snn_box_head_workspace_bytes(int R, int K, int Hdim, int T, int mode);
+int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box_out, int T, int mode,
+                         const void* w6_prep, const void* w7_prep, const float* w_cls, const float* w_bbox,
+                         float* cls_out, float* bbox_out, void* spk6_trains, void* spk7_trains,
+                         unsigned int* spike_counts_out, void* workspace, size_t workspace_bytes,
+                         snn_stream_t stream);
+
+/* ---- building block exposed for tests / profiling: one fully-connected spiking layer ------------------
+ * z [T_live][R][K] bf16 {0,1} input spike planes injected at steps t0 .. t0+T_live-1; w_prep [pieces][M][K];
+ * runs the LIF recurrence for steps 0..T-1 and writes trains [R][M]; optional bf16 planes
+ * spikes_out [t_hi-t_lo][R][M] and raw currents dump [T_live][R][M] fp32.  cta_group 1 or 2 (0 = auto). */
+int snn_fc_lif_layer(const void* z, int R, int K, int M, int T, int t0, int T_live, int mode, const void* w_prep,
+                     void* trains, void* spikes_out, int t_lo, int t_hi, float* dump, int cta_group,
+                     snn_stream_t stream);
+/* encoder only: x [R][K] fp32 -> z [T_live][R][K] bf16 {0,1} (Norse lif_current_encoder, faster_rcnn.py:494) */
+int snn_encode_rows(const float* x, int R, int K, int T_live, void* z, snn_stream_t stream);
+
+/* number of kernels the last forward call on this thread enqueued (for bench accounting) */
+int snn_last_launch_count(void);
+/* force cta_group (1 or 2; 0 = auto) for subsequent forward calls on this thread -- tests/profiling only */
+void snn_set_cta_group(int cta_group);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNN_HEADS_H_ */

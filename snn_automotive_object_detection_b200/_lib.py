@@ -1,0 +1,81 @@
+"""ctypes binding of libsnn_heads_b200.so (C ABI in include/snn_heads.h).
+
+The product path has no CPU or eager fallback: if the CUDA library cannot be
+loaded, or a call is made with non-CUDA tensors, a RuntimeError is raised.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsnn_heads_b200.so")
+
+MODE_FP32_EXACT, MODE_BF16, MODE_BF16X2 = 0, 1, 2
+MODES = {"fp32_exact": MODE_FP32_EXACT, "fp32": MODE_FP32_EXACT, "bf16": MODE_BF16, "bf16x2": MODE_BF16X2}
+
+# every symbol include/snn_heads.h declares
+EXPORTS = [
+    "snn_version", "snn_last_error", "snn_train_word_bytes", "snn_mode_pieces", "snn_prepared_weight_bytes",
+    "snn_prepare_conv3x3_weights", "snn_prepare_fc_weights", "snn_rpn_head_workspace_bytes", "snn_rpn_head_forward",
+    "snn_box_head_workspace_bytes", "snn_box_head_forward", "snn_fc_lif_layer", "snn_encode_rows",
+    "snn_last_launch_count", "snn_set_cta_group",
+]
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _declare(lib):
+    c = ctypes
+    vp, i, sz = c.c_void_p, c.c_int, c.c_size_t
+    pi = c.POINTER(c.c_int)
+    pvp = c.POINTER(c.c_void_p)
+    lib.snn_version.restype = i
+    lib.snn_last_error.restype = c.c_char_p
+    lib.snn_train_word_bytes.argtypes = [i]; lib.snn_train_word_bytes.restype = i
+    lib.snn_mode_pieces.argtypes = [i]; lib.snn_mode_pieces.restype = i
+    lib.snn_prepared_weight_bytes.argtypes = [i, i, i]; lib.snn_prepared_weight_bytes.restype = sz
+    lib.snn_prepare_conv3x3_weights.argtypes = [vp, i, i, i, vp, vp]; lib.snn_prepare_conv3x3_weights.restype = i
+    lib.snn_prepare_fc_weights.argtypes = [vp, i, i, i, vp, vp]; lib.snn_prepare_fc_weights.restype = i
+    lib.snn_rpn_head_workspace_bytes.argtypes = [pi, pi, i, i, i, i, i]; lib.snn_rpn_head_workspace_bytes.restype = sz
+    lib.snn_rpn_head_forward.argtypes = [pvp, pi, pi, i, i, i, i, i, i, vp, vp, vp, pvp, pvp, pvp, vp, vp, sz, vp]
+    lib.snn_rpn_head_forward.restype = i
+    lib.snn_box_head_workspace_bytes.argtypes = [i, i, i, i, i]; lib.snn_box_head_workspace_bytes.restype = sz
+    lib.snn_box_head_forward.argtypes = [vp, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.snn_box_head_forward.restype = i
+    lib.snn_fc_lif_layer.argtypes = [vp, i, i, i, i, i, i, i, vp, vp, vp, i, i, vp, i, vp]; lib.snn_fc_lif_layer.restype = i
+    lib.snn_encode_rows.argtypes = [vp, i, i, i, vp, vp]; lib.snn_encode_rows.restype = i
+    lib.snn_last_launch_count.restype = i
+    lib.snn_set_cta_group.argtypes = [i]; lib.snn_set_cta_group.restype = None
+
+
+def load():
+    """Load (once) and return the ctypes library.  Fails loudly when it is missing."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+                    "(nvcc, sm_100a).  There is no CPU / eager fallback for the spiking heads.")
+            lib = ctypes.CDLL(LIB_PATH)
+            _declare(lib)
+            _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().snn_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def mode_id(mode):
+    if isinstance(mode, int):
+        if mode not in (0, 1, 2):
+            raise ValueError(f"unknown mode {mode}")
+        return mode
+    try:
+        return MODES[str(mode).lower()]
+    except KeyError:
+        raise ValueError(f"unknown mode {mode!r}; expected one of {sorted(MODES)}") from None

@@ -1,0 +1,274 @@
+// HBM-bound companions of spike_gemm_lif: weight preparation, the constant-current
+// LIF encoder (Norse lif_current_encoder; rpn.py:101, faster_rcnn.py:494) and the
+// leaky-integrator readouts (Norse LICell; rpn.py:110-115, faster_rcnn.py:505-510).
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace snn {
+
+// ------------------------------------------------------------ weight prep
+// w = hi + mid + lo with each piece a bf16; residuals are exact in fp32.
+__device__ __forceinline__ void split_bf16(float w, int nsplit, __nv_bfloat16* out, size_t stride, size_t idx) {
+    float r = w;
+    for (int s = 0; s < nsplit; ++s) {
+        const __nv_bfloat16 b = __float2bfloat16_rn(r);
+        out[s * stride + idx] = b;
+        r = __fsub_rn(r, __bfloat162float(b));
+    }
+}
+
+// [O][C][3][3] fp32  ->  [nsplit][O][9*C] bf16 with k = (ky*3+kx)*C + c
+__global__ void prep_conv3x3_weights_kernel(const float* __restrict__ w, int O, int C, int nsplit,
+                                            __nv_bfloat16* __restrict__ out) {
+    const size_t total = static_cast<size_t>(O) * C * 9;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i % (9 * C));
+        const int o = static_cast<int>(i / (9 * C));
+        const int tap = k / C, c = k - tap * C;
+        split_bf16(w[(static_cast<size_t>(o) * C + c) * 9 + tap], nsplit, out, total, i);
+    }
+}
+
+// [O][K] fp32 -> [nsplit][O][K] bf16
+__global__ void prep_fc_weights_kernel(const float* __restrict__ w, size_t total, int nsplit,
+                                       __nv_bfloat16* __restrict__ out) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        split_bf16(w[i], nsplit, out, total, i);
+}
+
+// ---------------------------------------------------------------- encoder
+// Norse lif_current_encoder, op for op: v += 0.1f*((0-v)+x); z = (v-0.25f > 0); v -= z*v.
+// Returns the spike train of the first T steps as a bit word (bit t = z_t).
+__device__ __forceinline__ uint32_t encode_train(float x, int T) {
+    float v = 0.f;
+    uint32_t w = 0u;
+    for (int t = 0; t < T; ++t) {
+        v = __fadd_rn(v, __fmul_rn(0.1f, __fsub_rn(x, v)));
+        const bool z = __fsub_rn(v, 0.25f) > 0.f;
+        w |= (z ? 1u : 0u) << t;
+        v = z ? 0.f : v;
+    }
+    return w;
+}
+
+constexpr int kEncW = 32;   // pixels per block along W
+
+// x [N][C][H][W] fp32  ->  Z [T_box][N][H][W][C] bf16 {0,1}  (planes t >= T_live are zero)
+// One block = one (n, h, 32-pixel run): coalesced 128-B reads along W, smem transpose,
+// coalesced channel-contiguous bf16x2 writes.
+__global__ void __launch_bounds__(256) encode_nchw_kernel(const float* __restrict__ x, int N, int C, int H, int W,
+                                                          int T_live, int T_box, __nv_bfloat16* __restrict__ z) {
+    extern __shared__ uint32_t s_tr[];            // [kEncW][C+1]
+    const int w0 = blockIdx.x * kEncW, h = blockIdx.y, n = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = w0 + lane;
+    const int ld = C + 1;
+    for (int c = warp; c < C; c += 8) {
+        float xv = 0.f;
+        if (w < W) xv = __ldg(&x[((static_cast<size_t>(n) * C + c) * H + h) * W + w]);
+        s_tr[lane * ld + c] = encode_train(xv, T_live);
+    }
+    __syncthreads();
+    const int npx = min(kEncW, W - w0);
+    const int pairs = C >> 1;
+    const size_t plane = static_cast<size_t>(N) * H * W * C;
+    uint32_t* zo = reinterpret_cast<uint32_t*>(z);
+    for (int idx = threadIdx.x; idx < npx * pairs; idx += blockDim.x) {
+        const int px = idx / pairs, cp = idx - px * pairs;
+        const uint32_t t0 = s_tr[px * ld + 2 * cp], t1 = s_tr[px * ld + 2 * cp + 1];
+        const size_t base = ((static_cast<size_t>(n) * H + h) * W + (w0 + px)) * C + 2 * cp;
+        for (int t = 0; t < T_box; ++t) {
+            const uint32_t val = (((t0 >> t) & 1u) ? 0x3F80u : 0u) | (((t1 >> t) & 1u) ? 0x3F800000u : 0u);
+            zo[(static_cast<size_t>(t) * plane + base) >> 1] = (t < T_live) ? val : 0u;
+        }
+    }
+}
+
+// x [R][K] fp32 -> Z [T_box][R][K] bf16 {0,1}; 8 consecutive k per thread (2 x float4 in, 16 B out per step)
+__global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total8, size_t plane,
+                                                          int T_live, int T_box, __nv_bfloat16* __restrict__ z) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+        const float xs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t tr[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tr[q] = encode_train(xs[q], T_live);
+        for (int t = 0; t < T_box; ++t) {
+            uint4 o;
+            uint32_t wv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                wv[q] = (((tr[2 * q] >> t) & 1u) ? 0x3F80u : 0u) | (((tr[2 * q + 1] >> t) & 1u) ? 0x3F800000u : 0u);
+            o.x = wv[0]; o.y = wv[1]; o.z = wv[2]; o.w = wv[3];
+            if (t >= T_live) o = make_uint4(0, 0, 0, 0);
+            reinterpret_cast<uint4*>(z + static_cast<size_t>(t) * plane)[i] = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- readout
+// LICell is linear with zero initial state, so its last-step membrane is
+//   mem_{T-1} = W . s,   s[c] = sum_t kappa_{T-1-t} spk_t[c],  kappa_n = 0.9^{n+1} - 0.8^{n+1}
+// s[c] is a function of the neuron's spike-train word -> byte-indexed lookup tables
+// lut[b][256] (b = byte position in the word), built on the host in float64.
+constexpr int kMaxTrainBytes = 4;
+
+template <typename TrainT>
+__device__ __forceinline__ float lut_weight(const float* lut, TrainT tr) {
+    float s = lut[tr & 0xFFu];
+    if constexpr (sizeof(TrainT) >= 2) s += lut[256 + ((tr >> 8) & 0xFFu)];
+    if constexpr (sizeof(TrainT) == 4) { s += lut[512 + ((tr >> 16) & 0xFFu)]; s += lut[768 + ((tr >> 24) & 0xFFu)]; }
+    return s;
+}
+
+constexpr int kRpnRoPx = 128;      // pixels per block
+constexpr int kRpnMaxOut = 16;     // A + 4A <= 16 per pass (A = 3 -> 15)
+
+// trains [N][H*W][C] -> logits [N][A][H][W], bbox [N][4A][H][W]; one thread per pixel.
+// Also counts spikes per image (popc of the train words) into counts[n].
+template <typename TrainT>
+__global__ void __launch_bounds__(kRpnRoPx) readout_rpn_kernel(const TrainT* __restrict__ trains, int C, int HW,
+                                                               const float* __restrict__ w_cls,
+                                                               const float* __restrict__ w_bbox, int A,
+                                                               const float* __restrict__ lut_g,
+                                                               float* __restrict__ logits, float* __restrict__ bbox,
+                                                               unsigned long long* __restrict__ counts) {
+    extern __shared__ uint8_t s_raw[];
+    const int n_out = 5 * A;
+    const int row_words = (C * static_cast<int>(sizeof(TrainT))) / 4 + 1;   // +1 word: conflict-free row stride
+    float* s_w = reinterpret_cast<float*>(s_raw);                  // [n_out][C]
+    float* s_lut = s_w + n_out * C;                                // [sizeof(TrainT)][256]
+    uint32_t* s_tr = reinterpret_cast<uint32_t*>(s_lut + 256 * sizeof(TrainT));   // [kRpnRoPx][row_words]
+    __shared__ unsigned int s_cnt;
+
+    const int n = blockIdx.y;
+    const int p0 = blockIdx.x * kRpnRoPx;
+    const int npx = min(kRpnRoPx, HW - p0);
+    if (threadIdx.x == 0) s_cnt = 0;
+    for (int i = threadIdx.x; i < n_out * C; i += blockDim.x)
+        s_w[i] = (i < A * C) ? w_cls[i] : w_bbox[i - A * C];
+    for (int i = threadIdx.x; i < 256 * static_cast<int>(sizeof(TrainT)); i += blockDim.x) s_lut[i] = lut_g[i];
+    // coalesced tile load: npx rows of C*sizeof(TrainT) bytes are contiguous in global memory
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(trains + (static_cast<size_t>(n) * HW + p0) * C);
+    const int wpr = row_words - 1;
+    unsigned int cnt = 0;
+    for (int i = threadIdx.x; i < npx * wpr; i += blockDim.x) {
+        const int r = i / wpr, k = i - r * wpr;
+        const uint32_t wv = src[i];
+        cnt += __popc(wv);
+        s_tr[r * row_words + k] = wv;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+
+    const int px = threadIdx.x;
+    if (px < npx) {
+        constexpr int per_word = 4 / static_cast<int>(sizeof(TrainT));
+        const size_t pix = static_cast<size_t>(p0 + px);
+        for (int o0 = 0; o0 < n_out; o0 += kRpnMaxOut) {       // A = 3 -> a single pass of 15 outputs
+            float acc[kRpnMaxOut];
+#pragma unroll
+            for (int o = 0; o < kRpnMaxOut; ++o) acc[o] = 0.f;
+            for (int k = 0; k < wpr; ++k) {
+                const uint32_t wv = s_tr[px * row_words + k];
+#pragma unroll
+                for (int e = 0; e < per_word; ++e) {
+                    const TrainT tr = static_cast<TrainT>(wv >> (8 * static_cast<int>(sizeof(TrainT)) * e));
+                    const float s = lut_weight<TrainT>(s_lut, tr);
+                    const int c = k * per_word + e;
+#pragma unroll
+                    for (int o = 0; o < kRpnMaxOut; ++o)
+                        if (o0 + o < n_out) acc[o] = fmaf(s_w[(o0 + o) * C + c], s, acc[o]);
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < kRpnMaxOut; ++o) {
+                const int oo = o0 + o;
+                if (oo < A) logits[(static_cast<size_t>(n) * A + oo) * HW + pix] = acc[o];
+                else if (oo < n_out) bbox[(static_cast<size_t>(n) * 4 * A + (oo - A)) * HW + pix] = acc[o];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && counts != nullptr && s_cnt) atomicAdd(&counts[n], static_cast<unsigned long long>(s_cnt));
+}
+
+constexpr int kRowsPerWarp = 4;
+
+// trains [R][Hd] -> out_cls [R][n_cls], out_box [R][n_box]; one warp per 4 rows, lanes stride
+// the hidden units, warp-shuffle reduction per output.  Also per-row spike counts of this layer
+// (and of an optional second layer `trains_b`, e.g. fc6) into counts[0][R], counts[1][R].
+template <typename TrainT>
+__global__ void __launch_bounds__(256) readout_rows_kernel(const TrainT* __restrict__ trains,
+                                                           const TrainT* __restrict__ trains_b, int R, int Hd,
+                                                           const float* __restrict__ w_cls, int n_cls,
+                                                           const float* __restrict__ w_box, int n_box,
+                                                           const float* __restrict__ lut_g,
+                                                           float* __restrict__ out_cls, float* __restrict__ out_box,
+                                                           unsigned int* __restrict__ counts) {
+    __shared__ float s_lut[256 * sizeof(TrainT)];
+    extern __shared__ float s_s[];                 // [warps][kRowsPerWarp][Hd]
+    for (int i = threadIdx.x; i < 256 * static_cast<int>(sizeof(TrainT)); i += blockDim.x) s_lut[i] = lut_g[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = (blockIdx.x * (blockDim.x >> 5) + warp) * kRowsPerWarp;
+    if (r0 >= R) return;
+    float* s = s_s + static_cast<size_t>(warp) * kRowsPerWarp * Hd;
+    unsigned int cnt_a[kRowsPerWarp], cnt_b[kRowsPerWarp];
+#pragma unroll
+    for (int q = 0; q < kRowsPerWarp; ++q) {
+        cnt_a[q] = 0; cnt_b[q] = 0;
+        const int r = r0 + q;
+        for (int h = lane; h < Hd; h += 32) {
+            float sv = 0.f;
+            if (r < R) {
+                const TrainT tr = trains[static_cast<size_t>(r) * Hd + h];
+                cnt_a[q] += __popc(static_cast<unsigned int>(tr));
+                sv = lut_weight<TrainT>(s_lut, tr);
+                if (trains_b != nullptr) cnt_b[q] += __popc(static_cast<unsigned int>(trains_b[static_cast<size_t>(r) * Hd + h]));
+            }
+            s[q * Hd + h] = sv;
+        }
+    }
+    __syncwarp();
+    const int n_out = n_cls + n_box;
+    for (int o = 0; o < n_out; ++o) {
+        const float* wrow = (o < n_cls) ? (w_cls + static_cast<size_t>(o) * Hd) : (w_box + static_cast<size_t>(o - n_cls) * Hd);
+        float acc[kRowsPerWarp];
+#pragma unroll
+        for (int q = 0; q < kRowsPerWarp; ++q) acc[q] = 0.f;
+        for (int h = lane; h < Hd; h += 32) {
+            const float wv = __ldg(&wrow[h]);
+#pragma unroll
+            for (int q = 0; q < kRowsPerWarp; ++q) acc[q] = fmaf(wv, s[q * Hd + h], acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < kRowsPerWarp; ++q) {
+            for (int off = 16; off > 0; off >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
+            const int r = r0 + q;
+            if (lane == 0 && r < R) {
+                if (o < n_cls) out_cls[static_cast<size_t>(r) * n_cls + o] = acc[q];
+                else out_box[static_cast<size_t>(r) * n_box + (o - n_cls)] = acc[q];
+            }
+        }
+    }
+    if (counts != nullptr) {
+#pragma unroll
+        for (int q = 0; q < kRowsPerWarp; ++q) {
+            for (int off = 16; off > 0; off >>= 1) {
+                cnt_a[q] += __shfl_xor_sync(0xffffffffu, cnt_a[q], off);
+                cnt_b[q] += __shfl_xor_sync(0xffffffffu, cnt_b[q], off);
+            }
+            const int r = r0 + q;
+            if (lane == 0 && r < R) { counts[r] = cnt_b[q]; counts[R + r] = cnt_a[q]; }
+        }
+    }
+}
+
+}  // namespace snn

@@ -1,0 +1,517 @@
+// C ABI (include/snn_heads.h) over the sm_100a kernels: workspace carving, TMA tensor maps,
+// tile-shape selection and launches.  No device allocation, no synchronisation, no CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/snn_heads.h"
+#include "aux_kernels.cuh"
+#include "spike_gemm_lif.cuh"
+
+using namespace snn;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_launches = 0;
+thread_local int g_force_cg = 0;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) return fail(SNN_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// --------------------------------------------------------------------------- device / driver
+struct DeviceInfo { int sms = 0; int cc_major = 0; bool ok = false; };
+
+int device_info(DeviceInfo& di) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&di.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev));
+    if (di.cc_major != 10)
+        return fail(SNN_E_ARCH, "device compute capability %d.x is not sm_100 (B200); there is no fallback path",
+                    di.cc_major);
+    di.ok = true;
+    return SNN_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// bf16 tensor, innermost dim contiguous, 128-byte swizzle, zero fill out of bounds
+int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+              const cuuint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) return fail(SNN_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims,
+                    strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(SNN_E_CUDA, "cuTensorMapEncodeTiled failed (%d), rank %d dims %llu %llu box %u %u", (int)r, rank,
+                    (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return SNN_OK;
+}
+
+// --------------------------------------------------------------------------- tile selection
+struct TileCfg { int cg, T_box, J, Jh, TW, TH, TWh, THh, dw, dh, CW, n_mma; };
+
+// Fold time into the MMA N dimension: N = T_box * J <= 256, N % 16 == 0, J units per tile.
+bool pick_tile_cg(int T_live, bool conv, int cg, TileCfg& out) {
+    const int step = conv ? 8 * cg : 4 * cg;
+    int bestJ = 0, bestT = 0;
+    for (int J = step; J <= 256; J += step)
+        for (int Tb = T_live; Tb <= T_live + 1; ++Tb) {
+            const int n = Tb * J;
+            if (n > 256 || (n % 16) != 0 || n < 16) continue;
+            if (J > bestJ) { bestJ = J; bestT = Tb; }
+        }
+    if (bestJ == 0) return false;
+    out.cg = cg; out.T_box = bestT; out.J = bestJ; out.Jh = bestJ / cg; out.n_mma = bestT * bestJ;
+    if (conv) {
+        out.TW = 8; out.TH = bestJ / 8; out.TWh = 8; out.THh = out.TH / cg; out.dw = 0; out.dh = (cg == 2) ? out.THh : 0;
+    } else {
+        out.TW = out.TH = out.TWh = out.THh = 0; out.dw = out.dh = 0;
+    }
+    out.CW = (out.Jh % 16 == 0) ? 16 : (out.Jh % 8 == 0) ? 8 : 4;   // 32 would spill the LIF state
+    return true;
+}
+bool pick_tile(int T_live, bool conv, int m_total, int force_cg, TileCfg& out) {
+    if (force_cg != 1 && (m_total % 256) == 0 && pick_tile_cg(T_live, conv, 2, out)) return true;
+    if (force_cg == 2) return false;
+    return pick_tile_cg(T_live, conv, 1, out);
+}
+
+template <int kCG>
+cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = kGemmSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+#define SNN_LAUNCH(CWV)                                                                                        \
+    {                                                                                                          \
+        auto kern = spike_gemm_lif_kernel<kCG, CWV>;                                                           \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes); \
+        if (e != cudaSuccess) return e;                                                                        \
+        return cudaLaunchKernelEx(&cfg, kern, p);                                                              \
+    }
+    switch (CW) {
+        case 16: SNN_LAUNCH(16)
+        case 8: SNN_LAUNCH(8)
+        default: SNN_LAUNCH(4)
+    }
+#undef SNN_LAUNCH
+}
+
+int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, cudaStream_t st) {
+    p.J = tc.J; p.Jh = tc.Jh; p.TW = tc.TW; p.TH = tc.TH; p.TWh = tc.TWh; p.THh = tc.THh;
+    p.sub_dw = tc.dw; p.sub_dh = tc.dh; p.T_box = tc.T_box; p.n_mma = tc.n_mma;
+    p.idesc = umma_idesc_bf16(128 * tc.cg, tc.n_mma);
+    p.m_tiles = p.m_total / (128 * tc.cg);
+    p.total_tiles = p.unit_tiles * p.m_tiles;
+    if (p.total_tiles <= 0) return SNN_OK;
+    int groups = di.sms / tc.cg;
+    if (groups > p.total_tiles) groups = p.total_tiles;
+    const int grid = groups * tc.cg;
+    cudaError_t e = (tc.cg == 2) ? launch_gemm_cw<2>(p, tc.CW, grid, st) : launch_gemm_cw<1>(p, tc.CW, grid, st);
+    if (e != cudaSuccess) return fail(SNN_E_CUDA, "spike_gemm_lif launch failed: %s", cudaGetErrorString(e));
+    ++g_launches;
+    return SNN_OK;
+}
+
+// LUT of kappa-weighted spike trains: lut[b][v] = sum_{bit j of v} kappa_{T-1-(8b+j)}, kappa_n = .9^{n+1} - .8^{n+1}
+__global__ void build_lut_kernel(int T, int nbytes, float* lut) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbytes * 256) return;
+    const int b = i >> 8, v = i & 255;
+    double s = 0.0;
+    for (int j = 0; j < 8; ++j) {
+        const int t = 8 * b + j;
+        if (((v >> j) & 1) && t < T) {
+            const int n = T - 1 - t;
+            s += pow(0.9, n + 1) - pow(0.8, n + 1);
+        }
+    }
+    lut[i] = static_cast<float>(s);
+}
+
+int nsplit_of(int mode) { return mode == SNN_MODE_FP32_EXACT ? 3 : mode == SNN_MODE_BF16 ? 1 : mode == SNN_MODE_BF16X2 ? 2 : 0; }
+
+struct RpnWs { size_t z_off[kMaxLevels], tr_off[kMaxLevels], lut_off, total; };
+
+int rpn_ws_layout(const int* H, const int* W, int L, int N, int C, int T, int mode, RpnWs& ws, TileCfg& tc) {
+    if (L < 1 || L > kMaxLevels) return fail(SNN_E_ARG, "n_levels %d outside [1,%d]", L, kMaxLevels);
+    if (T < 1 || T > 32) return fail(SNN_E_ARG, "num_steps %d outside [1,32]", T);
+    if (C % 128 != 0 || C < 128) return fail(SNN_E_ARG, "in_channels %d must be a multiple of 128", C);
+    if (nsplit_of(mode) == 0) return fail(SNN_E_ARG, "unknown mode %d", mode);
+    if (N < 1) return fail(SNN_E_ARG, "batch size %d < 1", N);
+    const int T_live = T - 1;
+    tc = TileCfg{};
+    if (T_live > 0 && !pick_tile(T_live, true, C, g_force_cg, tc)) return fail(SNN_E_ARG, "no tile shape for T=%d", T);
+    const int tb = snn_train_word_bytes(T);
+    size_t off = 0;
+    for (int l = 0; l < L; ++l) {
+        if (H[l] < 1 || W[l] < 1) return fail(SNN_E_ARG, "level %d has empty spatial size", l);
+        ws.z_off[l] = off;
+        off = align_up(off + static_cast<size_t>(tc.T_box) * N * H[l] * W[l] * C * 2, 1024);
+    }
+    for (int l = 0; l < L; ++l) {
+        ws.tr_off[l] = off;
+        off = align_up(off + static_cast<size_t>(N) * H[l] * W[l] * C * tb, 1024);
+    }
+    ws.lut_off = off;
+    off += kMaxTrainBytes * 256 * sizeof(float);
+    ws.total = align_up(off, 1024);
+    return SNN_OK;
+}
+
+struct BoxWs { size_t z_off, s6_off, tr6_off, tr7_off, lut_off, total; };
+
+int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, TileCfg& t6, TileCfg& t7) {
+    if (T < 3 || T > 32) return fail(SNN_E_ARG, "num_steps %d outside [3,32]", T);
+    if (R < 1) return fail(SNN_E_ARG, "R %d < 1", R);
+    if (K % 64 != 0) return fail(SNN_E_ARG, "in_channels %d must be a multiple of 64", K);
+    if (Hd % 128 != 0) return fail(SNN_E_ARG, "representation_size %d must be a multiple of 128", Hd);
+    if (nsplit_of(mode) == 0) return fail(SNN_E_ARG, "unknown mode %d", mode);
+    // worst case over stats on/off so one workspace size serves both
+    TileCfg a{}, b{};
+    if (!pick_tile(T - 1, false, Hd, g_force_cg, a) || !pick_tile(T - 2, false, Hd, g_force_cg, b))
+        return fail(SNN_E_ARG, "no tile shape for T=%d", T);
+    t6 = stats ? a : b;
+    if (!pick_tile(T - 2, false, Hd, g_force_cg, t7)) return fail(SNN_E_ARG, "no tile shape for T=%d", T);
+    const int tbx = (a.T_box > b.T_box) ? a.T_box : b.T_box;
+    const int tb = snn_train_word_bytes(T);
+    size_t off = 0;
+    ws.z_off = off; off = align_up(off + static_cast<size_t>(tbx) * R * K * 2, 1024);
+    ws.s6_off = off; off = align_up(off + static_cast<size_t>(t7.T_box) * R * Hd * 2, 1024);
+    ws.tr6_off = off; off = align_up(off + static_cast<size_t>(R) * Hd * tb, 1024);
+    ws.tr7_off = off; off = align_up(off + static_cast<size_t>(R) * Hd * tb, 1024);
+    ws.lut_off = off; off += kMaxTrainBytes * 256 * sizeof(float);
+    ws.total = align_up(off, 1024);
+    return SNN_OK;
+}
+
+int fc_layer(const DeviceInfo& di, const void* z, int R, int K, int M, int T, int t0, int T_live, int nsplit,
+             const void* w_prep, void* trains, void* spikes_out, int t_lo, int t_hi, float* dump, const TileCfg& tc,
+             cudaStream_t st) {
+    GemmLifParams p;
+    memset(&p, 0, sizeof(p));
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)nsplit * M};
+        cuuint64_t str[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {64, 128};
+        int rc = make_tmap(&p.tmA, w_prep, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)R, (cuuint64_t)tc.T_box};
+        cuuint64_t str[2] = {(cuuint64_t)K * 2, (cuuint64_t)R * K * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)tc.Jh, (cuuint32_t)tc.T_box};
+        int rc = make_tmap(&p.tmB[0], z, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    p.n_levels = 1; p.conv = 0; p.n_images = 1;
+    p.m_total = M; p.nsplit = nsplit; p.kblocks = K / 64; p.cblocks = 1;
+    p.T_total = T; p.t0 = t0; p.T_live = T_live;
+    p.rows = R; p.unit_tiles = (R + tc.J - 1) / tc.J;
+    p.train_bytes = snn_train_word_bytes(T);
+    p.trains = trains;
+    p.spikes_out = reinterpret_cast<__nv_bfloat16*>(spikes_out); p.spk_t_lo = t_lo; p.spk_t_hi = t_hi;
+    p.dump = dump;
+    return launch_gemm(p, tc, di, st);
+}
+
+template <typename T>
+cudaError_t launch_readout_rpn(const void* trains, int C, int HW, int N, const float* wc, const float* wb, int A,
+                               const float* lut, float* lo, float* bo, unsigned long long* counts, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(5 * A) * C * 4 + 256 * sizeof(T) * 4 +
+                        static_cast<size_t>(kRpnRoPx) * ((C * sizeof(T)) / 4 + 1) * 4;
+    auto kern = readout_rpn_kernel<T>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((HW + kRpnRoPx - 1) / kRpnRoPx, N);
+    kern<<<grid, kRpnRoPx, smem, st>>>(reinterpret_cast<const T*>(trains), C, HW, wc, wb, A, lut, lo, bo, counts);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_readout_rows(const void* tr7, const void* tr6, int R, int Hd, const float* wc, int nc,
+                                const float* wb, int nb, const float* lut, float* oc, float* ob, unsigned int* counts,
+                                cudaStream_t st) {
+    const int warps = 4;
+    const size_t smem = static_cast<size_t>(warps) * kRowsPerWarp * Hd * 4;
+    auto kern = readout_rows_kernel<T>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int rows_per_block = warps * kRowsPerWarp;
+    kern<<<(R + rows_per_block - 1) / rows_per_block, warps * 32, smem, st>>>(
+        reinterpret_cast<const T*>(tr7), reinterpret_cast<const T*>(tr6), R, Hd, wc, nc, wb, nb, lut, oc, ob, counts);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int snn_version(void) { return SNN_ABI_VERSION; }
+const char* snn_last_error(void) { return g_err.c_str(); }
+int snn_last_launch_count(void) { return g_launches; }
+void snn_set_cta_group(int cg) { g_force_cg = (cg == 1 || cg == 2) ? cg : 0; }
+int snn_train_word_bytes(int T) { return T <= 8 ? 1 : T <= 16 ? 2 : 4; }
+int snn_mode_pieces(int mode) { return nsplit_of(mode); }
+
+size_t snn_prepared_weight_bytes(int rows, int cols, int mode) {
+    return static_cast<size_t>(nsplit_of(mode)) * rows * cols * 2;
+}
+
+int snn_prepare_conv3x3_weights(const float* w, int O, int C, int mode, void* out, snn_stream_t stream) {
+    const int ns = nsplit_of(mode);
+    if (ns == 0 || O < 1 || C < 1 || !w || !out) return fail(SNN_E_ARG, "prepare_conv3x3: bad argument");
+    const size_t total = static_cast<size_t>(O) * C * 9;
+    const int blocks = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+    prep_conv3x3_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, O, C, ns,
+                                                                           reinterpret_cast<__nv_bfloat16*>(out));
+    CUDA_TRY(cudaGetLastError());
+    return SNN_OK;
+}
+
+int snn_prepare_fc_weights(const float* w, int O, int K, int mode, void* out, snn_stream_t stream) {
+    const int ns = nsplit_of(mode);
+    if (ns == 0 || O < 1 || K < 1 || !w || !out) return fail(SNN_E_ARG, "prepare_fc: bad argument");
+    const size_t total = static_cast<size_t>(O) * K;
+    const int blocks = static_cast<int>((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256);
+    prep_fc_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, total, ns, reinterpret_cast<__nv_bfloat16*>(out));
+    CUDA_TRY(cudaGetLastError());
+    return SNN_OK;
+}
+
+size_t snn_rpn_head_workspace_bytes(const int* H, const int* W, int n_levels, int N, int C_in, int T, int mode) {
+    RpnWs ws; TileCfg tc;
+    if (rpn_ws_layout(H, W, n_levels, N, C_in, T, mode, ws, tc) != SNN_OK) return 0;
+    return ws.total;
+}
+
+int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* W, int n_levels, int N, int C_in,
+                         int A, int T, int mode, const void* w_shared_prep, const float* w_cls, const float* w_bbox,
+                         void* const* logits_out, void* const* bbox_out, void* const* spike_trains_out,
+                         unsigned long long* spike_counts_out, void* workspace, size_t workspace_bytes,
+                         snn_stream_t stream) {
+    g_launches = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!feat_ptrs || !H || !W || !w_shared_prep || !w_cls || !w_bbox || !logits_out || !bbox_out || !workspace)
+        return fail(SNN_E_ARG, "rpn_head_forward: null argument");
+    if (A < 1) return fail(SNN_E_ARG, "num_anchors %d < 1", A);
+    DeviceInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    RpnWs ws; TileCfg tc;
+    rc = rpn_ws_layout(H, W, n_levels, N, C_in, T, mode, ws, tc);
+    if (rc) return rc;
+    if (workspace_bytes < ws.total)
+        return fail(SNN_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, ws.total);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(SNN_E_ARG, "workspace must be 1024-B aligned");
+    uint8_t* wsp = reinterpret_cast<uint8_t*>(workspace);
+    const int tb = snn_train_word_bytes(T);
+    const int ns = nsplit_of(mode);
+    const int T_live = T - 1;
+    float* lut = reinterpret_cast<float*>(wsp + ws.lut_off);
+
+    build_lut_kernel<<<(tb * 256 + 255) / 256, 256, 0, st>>>(T, tb, lut);
+    CUDA_TRY(cudaGetLastError()); ++g_launches;
+
+    void* trains[kMaxLevels];
+    for (int l = 0; l < n_levels; ++l) {
+        trains[l] = (spike_trains_out && spike_trains_out[l]) ? spike_trains_out[l] : (wsp + ws.tr_off[l]);
+        if (!feat_ptrs[l] || !logits_out[l] || !bbox_out[l]) return fail(SNN_E_ARG, "level %d: null pointer", l);
+    }
+
+    if (T_live > 0) {
+        // 1) encoder: fp32 NCHW features -> bf16 {0,1} NHWC spike planes
+        for (int l = 0; l < n_levels; ++l) {
+            dim3 grid((W[l] + kEncW - 1) / kEncW, H[l], N);
+            const size_t smem = static_cast<size_t>(kEncW) * (C_in + 1) * 4;
+            if (smem > 48 * 1024)
+                CUDA_TRY(cudaFuncSetAttribute(encode_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            encode_nchw_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(feat_ptrs[l]), N, C_in, H[l],
+                                                        W[l], T_live, tc.T_box,
+                                                        reinterpret_cast<__nv_bfloat16*>(wsp + ws.z_off[l]));
+            CUDA_TRY(cudaGetLastError()); ++g_launches;
+        }
+        // 2) all levels, all images: implicit-GEMM 3x3 conv + LIF recurrence in one persistent launch
+        GemmLifParams p;
+        memset(&p, 0, sizeof(p));
+        {
+            cuuint64_t dims[2] = {(cuuint64_t)9 * C_in, (cuuint64_t)ns * C_in};
+            cuuint64_t str[1] = {(cuuint64_t)9 * C_in * 2};
+            cuuint32_t box[2] = {64, 128};
+            rc = make_tmap(&p.tmA, w_shared_prep, 2, dims, str, box);
+            if (rc) return rc;
+        }
+        int tiles = 0;
+        for (int l = 0; l < n_levels; ++l) {
+            cuuint64_t dims[5] = {(cuuint64_t)C_in, (cuuint64_t)W[l], (cuuint64_t)H[l], (cuuint64_t)N, (cuuint64_t)tc.T_box};
+            cuuint64_t str[4] = {(cuuint64_t)C_in * 2, (cuuint64_t)W[l] * C_in * 2, (cuuint64_t)H[l] * W[l] * C_in * 2,
+                                 (cuuint64_t)N * H[l] * W[l] * C_in * 2};
+            cuuint32_t box[5] = {64, (cuuint32_t)tc.TWh, (cuuint32_t)tc.THh, 1, (cuuint32_t)tc.T_box};
+            rc = make_tmap(&p.tmB[l], wsp + ws.z_off[l], 5, dims, str, box);
+            if (rc) return rc;
+            LevelDesc& L = p.lv[l];
+            L.H = H[l]; L.W = W[l];
+            L.tiles_w = (W[l] + tc.TW - 1) / tc.TW; L.tiles_h = (H[l] + tc.TH - 1) / tc.TH;
+            L.tile_begin = tiles; L.trains = trains[l];
+            tiles += L.tiles_w * L.tiles_h * N;
+        }
+        p.n_levels = n_levels; p.conv = 1; p.n_images = N;
+        p.m_total = C_in; p.nsplit = ns; p.cblocks = C_in / 64; p.kblocks = 9 * p.cblocks;
+        p.T_total = T; p.t0 = 0; p.T_live = T_live;
+        p.rows = 0; p.unit_tiles = tiles; p.train_bytes = tb;
+        rc = launch_gemm(p, tc, di, st);
+        if (rc) return rc;
+    } else {
+        for (int l = 0; l < n_levels; ++l)
+            CUDA_TRY(cudaMemsetAsync(trains[l], 0, static_cast<size_t>(N) * H[l] * W[l] * C_in * tb, st));
+    }
+    // 3) leaky-integrator readouts (objectness + box deltas) from the spike trains
+    for (int l = 0; l < n_levels; ++l) {
+        unsigned long long* cnt = spike_counts_out ? spike_counts_out + static_cast<size_t>(l) * N : nullptr;
+        cudaError_t e;
+        float* lo = reinterpret_cast<float*>(logits_out[l]);
+        float* bo = reinterpret_cast<float*>(bbox_out[l]);
+        if (tb == 1) e = launch_readout_rpn<uint8_t>(trains[l], C_in, H[l] * W[l], N, w_cls, w_bbox, A, lut, lo, bo, cnt, st);
+        else if (tb == 2) e = launch_readout_rpn<uint16_t>(trains[l], C_in, H[l] * W[l], N, w_cls, w_bbox, A, lut, lo, bo, cnt, st);
+        else e = launch_readout_rpn<uint32_t>(trains[l], C_in, H[l] * W[l], N, w_cls, w_bbox, A, lut, lo, bo, cnt, st);
+        if (e != cudaSuccess) return fail(SNN_E_CUDA, "readout_rpn launch failed: %s", cudaGetErrorString(e));
+        ++g_launches;
+    }
+    return SNN_OK;
+}
+
+size_t snn_box_head_workspace_bytes(int R, int K, int Hdim, int T, int mode) {
+    BoxWs ws; TileCfg a, b;
+    if (box_ws_layout(R, K, Hdim, T, mode, true, ws, a, b) != SNN_OK) return 0;
+    return ws.total;
+}
+
+int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box_out, int T, int mode,
+                         const void* w6_prep, const void* w7_prep, const float* w_cls, const float* w_bbox,
+                         float* cls_out, float* bbox_out, void* spk6_trains, void* spk7_trains,
+                         unsigned int* spike_counts_out, void* workspace, size_t workspace_bytes,
+                         snn_stream_t stream) {
+    g_launches = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x || !w6_prep || !w7_prep || !w_cls || !w_bbox || !cls_out || !bbox_out || !workspace)
+        return fail(SNN_E_ARG, "box_head_forward: null argument");
+    if (C < 1 || n_box_out < 1) return fail(SNN_E_ARG, "box_head_forward: bad output sizes");
+    DeviceInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    const bool stats = spike_counts_out != nullptr;
+    BoxWs ws; TileCfg t6, t7;
+    rc = box_ws_layout(R, K, Hdim, T, mode, stats, ws, t6, t7);
+    if (rc) return rc;
+    if (workspace_bytes < ws.total)
+        return fail(SNN_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, ws.total);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(SNN_E_ARG, "workspace must be 1024-B aligned");
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail(SNN_E_ARG, "x must be 16-B aligned");
+    uint8_t* wsp = reinterpret_cast<uint8_t*>(workspace);
+    const int tb = snn_train_word_bytes(T);
+    const int ns = nsplit_of(mode);
+    float* lut = reinterpret_cast<float*>(wsp + ws.lut_off);
+    void* tr6 = spk6_trains ? spk6_trains : (wsp + ws.tr6_off);
+    void* tr7 = spk7_trains ? spk7_trains : (wsp + ws.tr7_off);
+    void* z = wsp + ws.z_off;
+    void* s6 = wsp + ws.s6_off;
+
+    build_lut_kernel<<<(tb * 256 + 255) / 256, 256, 0, st>>>(T, tb, lut);
+    CUDA_TRY(cudaGetLastError()); ++g_launches;
+
+    // fc6 is live for steps 0..T-3 (its last two steps never reach the outputs); one more step when
+    // the fc6 spike statistics are wanted.  fc7 is live for steps 1..T-2.
+    const int T_live6 = stats ? T - 1 : T - 2;
+    const int T_live7 = T - 2;
+    {
+        const size_t total8 = static_cast<size_t>(R) * K / 8;
+        const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
+        encode_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), total8, static_cast<size_t>(R) * K,
+                                                   T_live6, t6.T_box, reinterpret_cast<__nv_bfloat16*>(z));
+        CUDA_TRY(cudaGetLastError()); ++g_launches;
+    }
+    rc = fc_layer(di, z, R, K, Hdim, T, 0, T_live6, ns, w6_prep, tr6, s6, 1, 1 + t7.T_box, nullptr, t6, st);
+    if (rc) return rc;
+    rc = fc_layer(di, s6, R, Hdim, Hdim, T, 1, T_live7, ns, w7_prep, tr7, nullptr, 0, 0, nullptr, t7, st);
+    if (rc) return rc;
+    cudaError_t e;
+    const void* tr6_for_counts = stats ? tr6 : nullptr;
+    if (tb == 1) e = launch_readout_rows<uint8_t>(tr7, tr6_for_counts, R, Hdim, w_cls, C, w_bbox, n_box_out, lut, cls_out, bbox_out, spike_counts_out, st);
+    else if (tb == 2) e = launch_readout_rows<uint16_t>(tr7, tr6_for_counts, R, Hdim, w_cls, C, w_bbox, n_box_out, lut, cls_out, bbox_out, spike_counts_out, st);
+    else e = launch_readout_rows<uint32_t>(tr7, tr6_for_counts, R, Hdim, w_cls, C, w_bbox, n_box_out, lut, cls_out, bbox_out, spike_counts_out, st);
+    if (e != cudaSuccess) return fail(SNN_E_CUDA, "readout_rows launch failed: %s", cudaGetErrorString(e));
+    ++g_launches;
+    return SNN_OK;
+}
+
+int snn_encode_rows(const float* x, int R, int K, int T_live, void* z, snn_stream_t stream) {
+    if (!x || !z || R < 1 || K % 8 != 0 || T_live < 1 || T_live > 32) return fail(SNN_E_ARG, "encode_rows: bad argument");
+    const size_t total8 = static_cast<size_t>(R) * K / 8;
+    const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
+    encode_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, total8, static_cast<size_t>(R) * K, T_live, T_live,
+                                                                 reinterpret_cast<__nv_bfloat16*>(z));
+    CUDA_TRY(cudaGetLastError());
+    return SNN_OK;
+}
+
+int snn_fc_lif_layer(const void* z, int R, int K, int M, int T, int t0, int T_live, int mode, const void* w_prep,
+                     void* trains, void* spikes_out, int t_lo, int t_hi, float* dump, int cta_group,
+                     snn_stream_t stream) {
+    g_launches = 0;
+    if (!z || !w_prep || !trains) return fail(SNN_E_ARG, "fc_lif_layer: null argument");
+    if (K % 64 != 0 || M % 128 != 0 || R < 1 || T < 1 || T > 32 || T_live < 1 || t0 < 0 || t0 + T_live > T)
+        return fail(SNN_E_ARG, "fc_lif_layer: unsupported shape R=%d K=%d M=%d T=%d t0=%d T_live=%d", R, K, M, T, t0, T_live);
+    const int ns = nsplit_of(mode);
+    if (ns == 0) return fail(SNN_E_ARG, "unknown mode %d", mode);
+    DeviceInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    TileCfg tc;
+    if (!pick_tile(T_live, false, M, cta_group, tc)) return fail(SNN_E_ARG, "no tile shape for T_live=%d cta_group=%d", T_live, cta_group);
+    if (tc.T_box != T_live) return fail(SNN_E_ARG, "fc_lif_layer needs T_live with an unpadded tile (got T_box %d)", tc.T_box);
+    return fc_layer(di, z, R, K, M, T, t0, T_live, ns, w_prep, trains, spikes_out, t_lo, t_hi, dump, tc, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+"""Shared helpers for the GPU parity tests (call the C ABI through ctypes)."""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from oracle import snn_oracle as O
+from snn_automotive_object_detection_b200 import _lib
+from snn_automotive_object_detection_b200.heads import _TRAIN_DTYPE, unpack_trains  # noqa: F401
+
+
+def vp(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def prepared_fc(w, mode):
+    lib = _lib.load()
+    O_, K = w.shape
+    buf = torch.empty(lib.snn_prepared_weight_bytes(O_, K, mode), dtype=torch.uint8, device=w.device)
+    _lib.check(lib.snn_prepare_fc_weights(vp(w), O_, K, mode, vp(buf), stream()), "prepare_fc")
+    return buf
+
+
+def split_reconstruct(w, pieces):
+    """fp32 value the tensor cores effectively see for `pieces` bf16 pieces (hi+mid+lo)."""
+    r = w.clone().float()
+    tot = torch.zeros_like(r)
+    for _ in range(pieces):
+        b = r.to(torch.bfloat16).float()
+        tot += b
+        r = r - b
+    return tot
+
+
+def spike_agreement(got_trains, ref_spk, ref_vdec, T, upstream_flip_rows=None, v_th=0.1, band=1e-5):
+    """got_trains: integer spike-train words [...]; ref_spk: [T, ...] uint8; ref_vdec: [T, ...] fp32.
+    Returns (agreement fraction over neuron-steps, number of unexplained flips).
+    A flipped neuron is 'explained' if at its FIRST differing step the oracle's pre-threshold
+    membrane sits within `band` of the threshold (north_star: flips confined to |v - v_th| < 1e-5),
+    or -- for a layer fed by another spiking layer -- if its row already had an upstream flip."""
+    got = unpack_trains(got_trains.cpu(), T)
+    ref = ref_spk.cpu()
+    diff = got != ref
+    agree = 1.0 - diff.float().mean().item()
+    if not diff.any():
+        return agree, 0
+    first = diff.to(torch.uint8).argmax(dim=0)            # first differing step per neuron
+    anyd = diff.any(dim=0)
+    vd = torch.gather(ref_vdec.cpu(), 0, first.unsqueeze(0)).squeeze(0)
+    near = (vd - v_th).abs() < band
+    explained = near
+    if upstream_flip_rows is not None:
+        rows = upstream_flip_rows.view(-1, *([1] * (anyd.dim() - 1))).expand_as(anyd)
+        explained = explained | rows
+    unexplained = int((anyd & ~explained).sum().item())
+    return agree, unexplained
+
+
+def logits_close(got, ref, rel=1e-3):
+    """north_star: logits within 1e-3 relative; SURVEY.md section 7 defines it per tensor as
+    |delta| <= 1e-3 * max|ref| (pure element-wise relative error is meaningless near zero)."""
+    ref = ref.cpu().float(); got = got.cpu().float()
+    scale = max(ref.abs().max().item(), 1e-6)
+    err = (got - ref).abs().max().item()
+    return err <= rel * scale, err, scale
