@@ -81,7 +81,7 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
  * cls_out    : fp32 [R][C] last-step membrane of lif_cls;  bbox_out: fp32 [R][n_box_out] (faster_rcnn.py:513-516)
  * spk6_trains, spk7_trains (nullable): [R][Hdim] spike-train words of lif6 / lif7 (faster_rcnn.py:499,501)
  * spike_counts_out (nullable): unsigned [2][R] spikes per RoI of lif6 and lif7 over all T steps.  When
- *              given, fc6 is also evaluated for the step whose spikes only the statistics need.
+ *              it or spk6_trains is given, fc6 is also evaluated for the one step whose spikes no output needs.
  * K multiple of 64, Hdim multiple of 256, 3 <= T <= 32, R >= 1 (ragged R is handled by TMA zero fill). */
 size_t snn_box_head_workspace_bytes(int R, int K, int Hdim, int T, int mode);
 int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box_out, int T, int mode,

@@ -345,7 +345,7 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
     if (rc) return rc;
     if (workspace_bytes < ws.total)
         return fail(SNN_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, ws.total);
-    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(SNN_E_ARG, "workspace must be 1024-B aligned");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(SNN_E_ARG, "workspace must be 256-B aligned");
     uint8_t* wsp = reinterpret_cast<uint8_t*>(workspace);
     const int tb = snn_train_word_bytes(T);
     const int ns = nsplit_of(mode);
@@ -441,13 +441,14 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
     DeviceInfo di;
     int rc = device_info(di);
     if (rc) return rc;
-    const bool stats = spike_counts_out != nullptr;
+    // the last lif6 step feeds no output; it is evaluated only when its spikes are asked for
+    const bool stats = spike_counts_out != nullptr || spk6_trains != nullptr;
     BoxWs ws; TileCfg t6, t7;
     rc = box_ws_layout(R, K, Hdim, T, mode, stats, ws, t6, t7);
     if (rc) return rc;
     if (workspace_bytes < ws.total)
         return fail(SNN_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, ws.total);
-    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(SNN_E_ARG, "workspace must be 1024-B aligned");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(SNN_E_ARG, "workspace must be 256-B aligned");
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail(SNN_E_ARG, "x must be 16-B aligned");
     uint8_t* wsp = reinterpret_cast<uint8_t*>(workspace);
     const int tb = snn_train_word_bytes(T);
@@ -477,7 +478,7 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
     rc = fc_layer(di, s6, R, Hdim, Hdim, T, 1, T_live7, ns, w7_prep, tr7, nullptr, 0, 0, nullptr, t7, st);
     if (rc) return rc;
     cudaError_t e;
-    const void* tr6_for_counts = stats ? tr6 : nullptr;
+    const void* tr6_for_counts = spike_counts_out ? tr6 : nullptr;
     if (tb == 1) e = launch_readout_rows<uint8_t>(tr7, tr6_for_counts, R, Hdim, w_cls, C, w_bbox, n_box_out, lut, cls_out, bbox_out, spike_counts_out, st);
     else if (tb == 2) e = launch_readout_rows<uint16_t>(tr7, tr6_for_counts, R, Hdim, w_cls, C, w_bbox, n_box_out, lut, cls_out, bbox_out, spike_counts_out, st);
     else e = launch_readout_rows<uint32_t>(tr7, tr6_for_counts, R, Hdim, w_cls, C, w_bbox, n_box_out, lut, cls_out, bbox_out, spike_counts_out, st);
