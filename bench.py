@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- SNN-head images/sec (BASELINE.json metric) on N B200s, one process per GPU.
+
+A "step" = one pass of both spiking heads over one batch of synthetic input:
+RPNHeadSNN.forward on the 5 Cityscapes-shaped FPN levels (768x1536 after the reference's
+transform: 192x384 ... 12x24, 256 channels) + FastRCNNPredictorSNNFull.forward on 1000 RoIs
+per image, T_rpn = 8 / T_det = 12, 9 classes, random-init weights (reference constructors).
+
+  value : whole-job images/s with the step's inputs already resident in HBM (CUDA events).
+  e2e   : same metric through the public modules with HOST (pinned) inputs: every step's features
+          and RoI features are copied host->device and its outputs device->host inside the timed
+          region (double-buffered on side streams so copies overlap the kernels).
+  roofline : the dominant kernel (rpn conv+LIF spike GEMM): executed tensor FLOPs per launch /
+          its CUDA-event duration (events recorded by the library on the launch stream) against
+          the measured bf16 peak in MEASURED_PEAKS.json.
+  cpu_baseline : the oracle port of the reference's torch+Norse path timed on the host cores,
+          on a bounded sample (N = 1, rank 0 only).
+
+`--impl reference` times that CPU port alone (the Norse package is not installable offline and
+/root/reference is absent on the GPU box, so the reference arm is the oracle port: kind "port").
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CITYSCAPES_LEVELS = [(192, 384), (96, 192), (48, 96), (24, 48), (12, 24)]
+BDD_LEVELS = [(192, 344), (96, 172), (48, 86), (24, 43), (12, 22)]
+WORKLOADS = {
+    "cityscapes": dict(levels=CITYSCAPES_LEVELS, classes=9, name="cityscapes-1024x2048(heads see 768x1536)"),
+    "bdd": dict(levels=BDD_LEVELS, classes=5, name="bdd-720x1280(heads see 768x1376)"),
+}
+T_RPN, T_DET, ROIS, CH, HID, KBOX = 8, 12, 1000, 256, 1024, 12544
+METRIC = "SNN-head images/sec (1024x2048, Trpn8/Tdet12)"
+PIECES = {"fp32_exact": 3, "bf16x2": 2, "bf16": 1}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="fp32_exact", choices=list(PIECES))
+    ap.add_argument("--workload", default="cityscapes", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=2, help="images per GPU per step (BASELINE configs[0]/[1]: 2)")
+    ap.add_argument("--t-rpn", type=int, default=T_RPN)
+    ap.add_argument("--t-det", type=int, default=T_DET)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cta-group", type=int, default=0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- CPU port (oracle) timing
+def cpu_port_step_fn(workload, t_rpn, t_det, frac_den=4):
+    """Returns (fn, images_per_call, description).  The sample is 1/frac_den of an image: every FPN
+    level cropped to H/frac_den rows and ROIS/frac_den RoIs (both heads are linear in these units)."""
+    import torch
+    from oracle import snn_oracle as O                       # CPU baseline leg only
+    torch.set_num_threads(os.cpu_count() or 1)
+    W = O.reference_weights(num_classes=WORKLOADS[workload]["classes"], seed=0)
+    g = torch.Generator().manual_seed(1234)
+    levels = [(max(h // frac_den, 1), w) for (h, w) in WORKLOADS[workload]["levels"]]
+    feats = [torch.randn(1, CH, h, w, generator=g) for (h, w) in levels]
+    rois = torch.randn(ROIS // frac_den, CH, 7, 7, generator=g)
+
+    def fn():
+        O.rpn_head_forward(feats, W["shared_conv"], W["conv_cls"], W["conv_bbox"], t_rpn)
+        O.box_head_forward(rois, W["fc6"], W["fc7"], W["cls_score"], W["bbox_pred"], t_det)
+
+    desc = (f"1/{frac_den} image per step: 5 FPN levels cropped to H/{frac_den} rows + {ROIS // frac_den} RoIs, "
+            f"T {t_rpn}/{t_det}, torch CPU fp32 port of the reference's torch+Norse path")
+    return fn, 1.0 / frac_den, desc
+
+
+def time_cpu_port(workload, t_rpn, t_det, steps, warmup):
+    fn, imgs, desc = cpu_port_step_fn(workload, t_rpn, t_det)
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return imgs / dt, dt * 1e3, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, ms, desc = time_cpu_port(args.workload, args.t_rpn, args.t_det, args.steps, args.warmup)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload]["name"], "T_rpn": args.t_rpn, "T_det": args.t_det,
+                   "rois_per_image": ROIS, "classes": WORKLOADS[args.workload]["classes"]},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from snn_automotive_object_detection_b200 import RPNHeadSNN, FastRCNNPredictorSNNFull, _lib, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the spiking heads have no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    levels, C = wl["levels"], wl["classes"]
+    B = args.batch
+    lib = _lib.load()
+    lib.snn_set_cta_group(args.cta_group)
+
+    # weights: the reference constructors' init (random init; there are no checkpoints offline)
+    torch.manual_seed(0)
+    rpn = RPNHeadSNN(CH, 3, args.t_rpn, mode=args.mode).to(dev)
+    box = FastRCNNPredictorSNNFull(KBOX, HID, C, args.t_det, mode=args.mode).to(dev)
+    rpn.record_rates = box.record_rates = world > 1          # spike statistics are what the ranks gather
+
+    # synthetic inputs, seeded per global image index so shards are reproducible
+    def make_inputs(pin):
+        feats = [torch.empty(B, CH, h, w, pin_memory=pin) for (h, w) in levels]
+        rois = torch.empty(B * ROIS, CH, 7, 7, pin_memory=pin)
+        for b in range(B):
+            g = torch.Generator().manual_seed(1234 + rank * B + b)
+            for l, (h, w) in enumerate(levels):
+                feats[l][b] = torch.randn(CH, h, w, generator=g)
+            rois[b * ROIS:(b + 1) * ROIS] = torch.randn(ROIS, CH, 7, 7, generator=g)
+        return feats, rois
+
+    h_feats, h_rois = make_inputs(pin=True)
+    d_feats = [f.to(dev) for f in h_feats]
+    d_rois = h_rois.to(dev)
+    in_bytes = sum(f.numel() for f in h_feats) * 4 + h_rois.numel() * 4
+
+    def step_resident():
+        lo, bb = rpn(d_feats)
+        cls, dl = box(d_rois)
+        if world > 1:
+            rec = parallel.spike_rate_records(rpn.last_spike_counts, levels, CH, args.t_rpn, box.last_spike_counts,
+                                              ROIS, HID, args.t_det)
+            parallel.gather_records(rec, [B] * world)
+        return lo, bb, cls, dl
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    launches_per_step = rpn.last_launch_count + box.last_launch_count
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _lib.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    phases = _lib.profile_read()
+    _lib.profile_enable(False)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---------------- end-to-end timing: host (pinned) inputs in, host outputs out, every step
+    e2e = None
+    if not args.no_e2e:
+        cs_in, cs_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        main = torch.cuda.current_stream(dev)
+        bufs = [([torch.empty_like(f, device=dev) for f in h_feats], torch.empty_like(h_rois, device=dev)) for _ in range(2)]
+        out_shapes = [(B, 3, h, w) for (h, w) in levels] + [(B, 12, h, w) for (h, w) in levels] + \
+                     [(B * ROIS, C), (B * ROIS, 4 * C)]
+        h_out = [[torch.empty(s, pin_memory=True) for s in out_shapes] for _ in range(2)]
+        out_bytes = sum(t_.numel() for t_ in h_out[0]) * 4
+        in_done = [torch.cuda.Event() for _ in range(2)]
+        comp_done = [torch.cuda.Event() for _ in range(2)]
+        out_done = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_step(s):
+            k = s & 1
+            with torch.cuda.stream(cs_in):
+                cs_in.wait_event(comp_done[k])               # device buffer k free again
+                for dst, src in zip(bufs[k][0], h_feats):
+                    dst.copy_(src, non_blocking=True)
+                bufs[k][1].copy_(h_rois, non_blocking=True)
+                in_done[k].record(cs_in)
+            main.wait_event(in_done[k])
+            lo, bb = rpn(bufs[k][0])
+            cls, dl = box(bufs[k][1])
+            if world > 1:
+                rec = parallel.spike_rate_records(rpn.last_spike_counts, levels, CH, args.t_rpn,
+                                                  box.last_spike_counts, ROIS, HID, args.t_det)
+                parallel.gather_records(rec, [B] * world)
+            comp_done[k].record(main)
+            with torch.cuda.stream(cs_out):
+                cs_out.wait_event(comp_done[k])
+                cs_out.wait_event(out_done[k])               # pinned output buffer k free again
+                for dst, src in zip(h_out[k], list(lo) + list(bb) + [cls, dl]):
+                    dst.copy_(src, non_blocking=True)
+                    src.record_stream(cs_out)
+                out_done[k].record(cs_out)
+
+        for s in range(max(args.warmup, 3)):
+            e2e_step(s)
+        sync_all()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(main)
+        for s in range(args.steps):
+            e2e_step(s)
+        main.wait_stream(cs_in); main.wait_stream(cs_out)
+        t1.record(main)
+        sync_all()
+        te = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B / (te.item() / args.steps * 1e-3), "unit": "images/s",
+               "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+               "ms_per_step": te.item() / args.steps, "overlap": "copies double-buffered on side streams"}
+
+    # ---------------- roofline of the dominant kernel (rpn conv + LIF spike GEMM)
+    peaks, peak_src = None, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+            peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+    except Exception:
+        pass
+    peak_tf = peaks["bf16_tflops_sustained"] if peaks else 1400.0
+    pieces = PIECES[args.mode]
+    pix = sum(h * w for (h, w) in levels) * B
+    conv_flops = 2.0 * pix * (9 * CH) * CH * (args.t_rpn - 1) * pieces        # executed (dead last step skipped)
+    g_ms, g_n = phases["rpn_conv_lif_gemm"]
+    roof = None
+    if g_n > 0:
+        ach = conv_flops / (g_ms / g_n * 1e-3) / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                traffic = json.load(f).get(f"rpn_conv_lif_gemm:{args.mode}:b{B}")
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "spike_gemm_lif_kernel (rpn 3x3 conv + LIF, all levels, one launch)",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                "peak_source": peak_src, "flops_per_launch": conv_flops, "ms_per_launch": g_ms / g_n}
+    phase_ms = {k: (v[0] / v[1] if v[1] else None) for k, v in phases.items()}
+    fc6_flops = 2.0 * B * ROIS * KBOX * HID * (args.t_det - 2) * pieces
+    fc7_flops = 2.0 * B * ROIS * HID * HID * (args.t_det - 2) * pieces
+    extra = {}
+    for name, fl in (("fc6_lif_gemm", fc6_flops), ("fc7_lif_gemm", fc7_flops)):
+        if phase_ms.get(name):
+            extra[name] = {"tflops": fl / (phase_ms[name] * 1e-3) / 1e12, "frac": fl / (phase_ms[name] * 1e-3) / 1e12 / peak_tf}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, ms, desc = time_cpu_port(args.workload, args.t_rpn, args.t_det, steps=3, warmup=1)
+        cpu = {"value": v, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc,
+               "ms_per_sample": ms}
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": wl["name"], "images_per_gpu_per_step": B, "global_batch": B * world,
+                   "T_rpn": args.t_rpn, "T_det": args.t_det, "rois_per_image": ROIS, "classes": C,
+                   "weight_mode": args.mode, "bf16_pieces_per_weight": pieces,
+                   "l2": f"inputs {in_bytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+                   "parallelism": f"image-sharded dp{world}, no hot-path collective"},
+        "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "phase_ms_per_step": phase_ms,
+        "other_kernels": extra,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -105,6 +105,14 @@ int snn_last_launch_count(void);
 /* force cta_group (1 or 2; 0 = auto) for subsequent forward calls on this thread -- tests/profiling only */
 void snn_set_cta_group(int cta_group);
 
+/* Per-phase device timing for bench.py: when enabled, every forward records CUDA events on its stream
+ * around each phase (up to 256 forwards).  snn_profile_read() waits for them, writes the summed
+ * milliseconds and the number of timed forwards per phase, and resets.  Phase order:
+ * 0 rpn encoder, 1 rpn conv+LIF GEMM, 2 rpn readout, 3 box encoder, 4 fc6+LIF GEMM, 5 fc7+LIF GEMM, 6 box readout. */
+#define SNN_PHASES 7
+void snn_profile_enable(int on);
+int snn_profile_read(float* ms_out, int* counts_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,8 +18,9 @@ EXPORTS = [
     "snn_version", "snn_last_error", "snn_train_word_bytes", "snn_mode_pieces", "snn_prepared_weight_bytes",
     "snn_prepare_conv3x3_weights", "snn_prepare_fc_weights", "snn_rpn_head_workspace_bytes", "snn_rpn_head_forward",
     "snn_box_head_workspace_bytes", "snn_box_head_forward", "snn_fc_lif_layer", "snn_encode_rows",
-    "snn_last_launch_count", "snn_set_cta_group",
+    "snn_last_launch_count", "snn_set_cta_group", "snn_profile_enable", "snn_profile_read",
 ]
+PHASES = ["rpn_encoder", "rpn_conv_lif_gemm", "rpn_readout", "box_encoder", "fc6_lif_gemm", "fc7_lif_gemm", "box_readout"]
 
 _lock = threading.Lock()
 _lib = None
@@ -47,6 +48,8 @@ def _declare(lib):
     lib.snn_encode_rows.argtypes = [vp, i, i, i, vp, vp]; lib.snn_encode_rows.restype = i
     lib.snn_last_launch_count.restype = i
     lib.snn_set_cta_group.argtypes = [i]; lib.snn_set_cta_group.restype = None
+    lib.snn_profile_enable.argtypes = [i]; lib.snn_profile_enable.restype = None
+    lib.snn_profile_read.argtypes = [c.POINTER(c.c_float), pi]; lib.snn_profile_read.restype = i
 
 
 def load():
@@ -79,3 +82,15 @@ def mode_id(mode):
         return MODES[str(mode).lower()]
     except KeyError:
         raise ValueError(f"unknown mode {mode!r}; expected one of {sorted(MODES)}") from None
+
+
+def profile_enable(on: bool):
+    load().snn_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{phase: (total_ms, n_forwards)} of the forwards since the last read."""
+    ms = (ctypes.c_float * len(PHASES))()
+    cnt = (ctypes.c_int * len(PHASES))()
+    check(load().snn_profile_read(ms, cnt), "snn_profile_read")
+    return {name: (float(ms[k]), int(cnt[k])) for k, name in enumerate(PHASES)}

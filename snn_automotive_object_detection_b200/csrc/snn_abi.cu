@@ -20,6 +20,31 @@ thread_local std::string g_err;
 thread_local int g_launches = 0;
 thread_local int g_force_cg = 0;
 
+// Optional per-phase device timing (CUDA events recorded on the launch stream around each phase).
+enum Phase { PH_ENC_RPN = 0, PH_GEMM_RPN, PH_RO_RPN, PH_ENC_BOX, PH_GEMM_FC6, PH_GEMM_FC7, PH_RO_BOX, PH_COUNT };
+constexpr int kMaxPairs = 256;
+struct PhaseEvents { cudaEvent_t start[kMaxPairs], stop[kMaxPairs]; int created = 0, used = 0; };
+PhaseEvents g_ph[PH_COUNT];
+bool g_profile = false;
+
+void phase_begin(int ph, cudaStream_t st) {
+    if (!g_profile) return;
+    PhaseEvents& e = g_ph[ph];
+    if (e.used >= kMaxPairs) return;
+    if (e.used >= e.created) {
+        if (cudaEventCreate(&e.start[e.created]) != cudaSuccess || cudaEventCreate(&e.stop[e.created]) != cudaSuccess) return;
+        ++e.created;
+    }
+    cudaEventRecord(e.start[e.used], st);
+}
+void phase_end(int ph, cudaStream_t st) {
+    if (!g_profile) return;
+    PhaseEvents& e = g_ph[ph];
+    if (e.used >= kMaxPairs || e.used >= e.created) return;
+    cudaEventRecord(e.stop[e.used], st);
+    ++e.used;
+}
+
 int fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -363,6 +388,7 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
 
     if (T_live > 0) {
         // 1) encoder: fp32 NCHW features -> bf16 {0,1} NHWC spike planes
+        phase_begin(PH_ENC_RPN, st);
         for (int l = 0; l < n_levels; ++l) {
             dim3 grid((W[l] + kEncW - 1) / kEncW, H[l], N);
             const size_t smem = static_cast<size_t>(kEncW) * (C_in + 1) * 4;
@@ -373,6 +399,7 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
                                                         reinterpret_cast<__nv_bfloat16*>(wsp + ws.z_off[l]));
             CUDA_TRY(cudaGetLastError()); ++g_launches;
         }
+        phase_end(PH_ENC_RPN, st);
         // 2) all levels, all images: implicit-GEMM 3x3 conv + LIF recurrence in one persistent launch
         GemmLifParams p;
         memset(&p, 0, sizeof(p));
@@ -401,13 +428,16 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
         p.m_total = C_in; p.nsplit = ns; p.cblocks = C_in / 64; p.kblocks = 9 * p.cblocks;
         p.T_total = T; p.t0 = 0; p.T_live = T_live;
         p.rows = 0; p.unit_tiles = tiles; p.train_bytes = tb;
+        phase_begin(PH_GEMM_RPN, st);
         rc = launch_gemm(p, tc, di, st);
+        phase_end(PH_GEMM_RPN, st);
         if (rc) return rc;
     } else {
         for (int l = 0; l < n_levels; ++l)
             CUDA_TRY(cudaMemsetAsync(trains[l], 0, static_cast<size_t>(N) * H[l] * W[l] * C_in * tb, st));
     }
     // 3) leaky-integrator readouts (objectness + box deltas) from the spike trains
+    phase_begin(PH_RO_RPN, st);
     for (int l = 0; l < n_levels; ++l) {
         unsigned long long* cnt = spike_counts_out ? spike_counts_out + static_cast<size_t>(l) * N : nullptr;
         cudaError_t e;
@@ -419,6 +449,7 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
         if (e != cudaSuccess) return fail(SNN_E_CUDA, "readout_rpn launch failed: %s", cudaGetErrorString(e));
         ++g_launches;
     }
+    phase_end(PH_RO_RPN, st);
     return SNN_OK;
 }
 
@@ -469,14 +500,21 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
     {
         const size_t total8 = static_cast<size_t>(R) * K / 8;
         const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
+        phase_begin(PH_ENC_BOX, st);
         encode_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), total8, static_cast<size_t>(R) * K,
                                                    T_live6, t6.T_box, reinterpret_cast<__nv_bfloat16*>(z));
+        phase_end(PH_ENC_BOX, st);
         CUDA_TRY(cudaGetLastError()); ++g_launches;
     }
+    phase_begin(PH_GEMM_FC6, st);
     rc = fc_layer(di, z, R, K, Hdim, T, 0, T_live6, ns, w6_prep, tr6, s6, 1, 1 + t7.T_box, nullptr, t6, st);
+    phase_end(PH_GEMM_FC6, st);
     if (rc) return rc;
+    phase_begin(PH_GEMM_FC7, st);
     rc = fc_layer(di, s6, R, Hdim, Hdim, T, 1, T_live7, ns, w7_prep, tr7, nullptr, 0, 0, nullptr, t7, st);
+    phase_end(PH_GEMM_FC7, st);
     if (rc) return rc;
+    phase_begin(PH_RO_BOX, st);
     cudaError_t e;
     const void* tr6_for_counts = spike_counts_out ? tr6 : nullptr;
     if (tb == 1) e = launch_readout_rows<uint8_t>(tr7, tr6_for_counts, R, Hdim, w_cls, C, w_bbox, n_box_out, lut, cls_out, bbox_out, spike_counts_out, st);
@@ -484,6 +522,29 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
     else e = launch_readout_rows<uint32_t>(tr7, tr6_for_counts, R, Hdim, w_cls, C, w_bbox, n_box_out, lut, cls_out, bbox_out, spike_counts_out, st);
     if (e != cudaSuccess) return fail(SNN_E_CUDA, "readout_rows launch failed: %s", cudaGetErrorString(e));
     ++g_launches;
+    phase_end(PH_RO_BOX, st);
+    return SNN_OK;
+}
+
+void snn_profile_enable(int on) {
+    g_profile = on != 0;
+    for (int k = 0; k < PH_COUNT; ++k) g_ph[k].used = 0;
+}
+
+int snn_profile_read(float* ms_out, int* counts_out) {
+    for (int k = 0; k < PH_COUNT; ++k) {
+        float tot = 0.f;
+        PhaseEvents& e = g_ph[k];
+        for (int i = 0; i < e.used; ++i) {
+            CUDA_TRY(cudaEventSynchronize(e.stop[i]));
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, e.start[i], e.stop[i]));
+            tot += ms;
+        }
+        if (ms_out) ms_out[k] = tot;
+        if (counts_out) counts_out[k] = e.used;
+        e.used = 0;
+    }
     return SNN_OK;
 }
 

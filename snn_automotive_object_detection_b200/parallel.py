@@ -1,0 +1,55 @@
+"""Multi-GPU plumbing for the spiking heads: images (and their RoIs) are sharded across ranks,
+one process per GPU, with NO collective on the hot path -- every image's RPN head and every
+RoI's box head is independent (the reference's own multi-GPU mode is DistributedSampler + DDP,
+train.py:594-601,708).  The only exchange is an end-of-batch all-gather of fixed-size per-image
+records (spike-rate statistics / detection summaries), replacing the reference's
+all_gather_object of pickled eval arrays (coco_eval.py:158-160, utils.py:78-91)."""
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of `n_items` owned by `rank`; sizes differ by at most one."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_images(n_images: int, rank: int, world: int) -> List[int]:
+    lo, hi = shard_range(n_images, rank, world)
+    return list(range(lo, hi))
+
+
+def gather_records(local: torch.Tensor, counts: Sequence[int]) -> torch.Tensor:
+    """All-gather per-image records.  `local` is [n_local, F] on this rank, counts[r] the number of
+    images rank r owns.  Returns [sum(counts), F] in global image order on every rank.  Ragged shards
+    are padded to max(counts) so a single fixed-size all_gather_into_tensor is used."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    assert len(counts) == world and local.shape[0] == counts[dist.get_rank()]
+    mx = max(counts)
+    F = local.shape[1:]
+    padded = local.new_zeros((mx,) + tuple(F))
+    padded[: local.shape[0]] = local
+    out = local.new_empty((world * mx,) + tuple(F))
+    dist.all_gather_into_tensor(out, padded.contiguous())
+    out = out.view(world, mx, *F)
+    return torch.cat([out[r, : counts[r]] for r in range(world)], dim=0)
+
+
+def spike_rate_records(rpn_counts: torch.Tensor, level_sizes: Sequence[Tuple[int, int]], channels: int, T_rpn: int,
+                       box_counts: torch.Tensor, rois_per_image: int, hidden: int, T_det: int) -> torch.Tensor:
+    """Per-image record [n_local, levels + 2] of mean spike rates: shared_lif per FPN level, then lif6
+    and lif7 averaged over the image's RoIs (the quantities train.py:482,491 reads from the reference's
+    spike-rate list, indices {0,3,6,9,12} and {15,16})."""
+    L, N = rpn_counts.shape
+    rec = torch.empty(N, L + 2, device=rpn_counts.device, dtype=torch.float64)
+    for l, (h, w) in enumerate(level_sizes):
+        rec[:, l] = rpn_counts[l].double() / float(h * w * channels * T_rpn)
+    per_img = box_counts.double().view(2, N, rois_per_image).sum(dim=2) / float(rois_per_image * hidden * T_det)
+    rec[:, L] = per_img[0]
+    rec[:, L + 1] = per_img[1]
+    return rec
