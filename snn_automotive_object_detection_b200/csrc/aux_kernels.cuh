@@ -54,35 +54,65 @@ __device__ __forceinline__ uint32_t encode_train(float x, int T) {
     return w;
 }
 
-constexpr int kEncW = 32;   // pixels per block along W
+constexpr int kEncW = 32;        // pixels per block along W
+constexpr int kEncMaxLevels = 8;
 
-// x [N][C][H][W] fp32  ->  Z [T_box][N][H][W][C] bf16 {0,1}  (planes t >= T_live are zero)
-// One block = one (n, h, 32-pixel run): coalesced 128-B reads along W, smem transpose,
-// coalesced channel-contiguous bf16x2 writes.
-__global__ void __launch_bounds__(256) encode_nchw_kernel(const float* __restrict__ x, int N, int C, int H, int W,
-                                                          int T_live, int T_box, __nv_bfloat16* __restrict__ z) {
-    extern __shared__ uint32_t s_tr[];            // [kEncW][C+1]
-    const int w0 = blockIdx.x * kEncW, h = blockIdx.y, n = blockIdx.z;
+struct EncLevel {
+    const float* x;             // [N][C][H][W] fp32
+    __nv_bfloat16* z;           // [T_box][N][H][W][C] bf16 {0,1}
+    int H, W, wchunks, block_begin;
+};
+struct EncParams {
+    EncLevel lv[kEncMaxLevels];
+    int n_levels, N, C, T_live, T_box, total_blocks;
+};
+
+// All FPN levels in one launch.  One block = one (level, n, h, 32-pixel run):
+//   phase 1: coalesced 128-B reads along W (one channel per warp instruction), the encoder's T_live
+//            steps in registers, spike-train words transposed through shared memory;
+//   phase 2: each lane owns 8 consecutive channels of a pixel -> one 16-B store per plane, a warp
+//            writes the pixel's 512 contiguous bytes (C = 256) of each time plane.
+// Planes t >= T_live (tile padding) are written as zeros.
+__global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant__ EncParams p) {
+    extern __shared__ uint32_t s_tr[];            // [kEncW][C + 4]
+    int lvl = 0;
+    const int bid = blockIdx.x;
+    while (lvl + 1 < p.n_levels && bid >= p.lv[lvl + 1].block_begin) ++lvl;
+    const EncLevel& L = p.lv[lvl];
+    int local = bid - L.block_begin;
+    const int per_img = L.H * L.wchunks;
+    const int n = local / per_img; local -= n * per_img;
+    const int h = local / L.wchunks;
+    const int w0 = (local - h * L.wchunks) * kEncW;
+    const int C = p.C, H = L.H, W = L.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = w0 + lane;
-    const int ld = C + 1;
+    const int ld = C + 4;
+    const float* xrow = L.x + (static_cast<size_t>(n) * C * H + h) * W + w;
+    const size_t cstride = static_cast<size_t>(H) * W;
+#pragma unroll 4
     for (int c = warp; c < C; c += 8) {
         float xv = 0.f;
-        if (w < W) xv = __ldg(&x[((static_cast<size_t>(n) * C + c) * H + h) * W + w]);
-        s_tr[lane * ld + c] = encode_train(xv, T_live);
+        if (w < W) xv = __ldg(xrow + c * cstride);
+        s_tr[lane * ld + c] = encode_train(xv, p.T_live);
     }
     __syncthreads();
     const int npx = min(kEncW, W - w0);
-    const int pairs = C >> 1;
-    const size_t plane = static_cast<size_t>(N) * H * W * C;
-    uint32_t* zo = reinterpret_cast<uint32_t*>(z);
-    for (int idx = threadIdx.x; idx < npx * pairs; idx += blockDim.x) {
-        const int px = idx / pairs, cp = idx - px * pairs;
-        const uint32_t t0 = s_tr[px * ld + 2 * cp], t1 = s_tr[px * ld + 2 * cp + 1];
-        const size_t base = ((static_cast<size_t>(n) * H + h) * W + (w0 + px)) * C + 2 * cp;
-        for (int t = 0; t < T_box; ++t) {
-            const uint32_t val = (((t0 >> t) & 1u) ? 0x3F80u : 0u) | (((t1 >> t) & 1u) ? 0x3F800000u : 0u);
-            zo[(static_cast<size_t>(t) * plane + base) >> 1] = (t < T_live) ? val : 0u;
+    const size_t plane = static_cast<size_t>(p.N) * H * W * C;
+    const int groups = C >> 3;                    // 8-channel groups per pixel
+    for (int idx = threadIdx.x; idx < npx * groups; idx += blockDim.x) {
+        const int px = idx / groups, g8 = idx - px * groups;
+        const uint4 a = *reinterpret_cast<const uint4*>(&s_tr[px * ld + 8 * g8]);
+        const uint4 b = *reinterpret_cast<const uint4*>(&s_tr[px * ld + 8 * g8 + 4]);
+        __nv_bfloat16* dst = L.z + ((static_cast<size_t>(n) * H + h) * W + (w0 + px)) * C + 8 * g8;
+        for (int t = 0; t < p.T_box; ++t) {
+            uint4 o;
+            o.x = (((a.x >> t) & 1u) ? 0x3F80u : 0u) | (((a.y >> t) & 1u) ? 0x3F800000u : 0u);
+            o.y = (((a.z >> t) & 1u) ? 0x3F80u : 0u) | (((a.w >> t) & 1u) ? 0x3F800000u : 0u);
+            o.z = (((b.x >> t) & 1u) ? 0x3F80u : 0u) | (((b.y >> t) & 1u) ? 0x3F800000u : 0u);
+            o.w = (((b.z >> t) & 1u) ? 0x3F80u : 0u) | (((b.w >> t) & 1u) ? 0x3F800000u : 0u);
+            if (t >= p.T_live) o = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(dst + static_cast<size_t>(t) * plane) = o;
         }
     }
 }
@@ -199,11 +229,13 @@ __global__ void __launch_bounds__(kRpnRoPx) readout_rpn_kernel(const TrainT* __r
     if (threadIdx.x == 0 && counts != nullptr && s_cnt) atomicAdd(&counts[n], static_cast<unsigned long long>(s_cnt));
 }
 
-constexpr int kRowsPerWarp = 4;
+constexpr int kRoRows = 8;         // RoIs per block
 
-// trains [R][Hd] -> out_cls [R][n_cls], out_box [R][n_box]; one warp per 4 rows, lanes stride
-// the hidden units, warp-shuffle reduction per output.  Also per-row spike counts of this layer
-// (and of an optional second layer `trains_b`, e.g. fc6) into counts[0][R], counts[1][R].
+// trains [R][Hd] -> out_cls [R][n_cls], out_box [R][n_box].  One block = 8 RoIs: their kappa-weighted
+// spike sums s[8][Hd] are staged in shared memory (LUT per spike-train byte); each warp then owns
+// every 8th output row of [w_cls; w_box], streams it once (coalesced) against all 8 RoIs and finishes
+// with a warp-shuffle reduction.  Also per-RoI spike counts of this layer and of an optional
+// second layer `trains_b` (fc6): counts[0][R] = layer b, counts[1][R] = this layer.
 template <typename TrainT>
 __global__ void __launch_bounds__(256) readout_rows_kernel(const TrainT* __restrict__ trains,
                                                            const TrainT* __restrict__ trains_b, int R, int Hd,
@@ -213,60 +245,54 @@ __global__ void __launch_bounds__(256) readout_rows_kernel(const TrainT* __restr
                                                            float* __restrict__ out_cls, float* __restrict__ out_box,
                                                            unsigned int* __restrict__ counts) {
     __shared__ float s_lut[256 * sizeof(TrainT)];
-    extern __shared__ float s_s[];                 // [warps][kRowsPerWarp][Hd]
+    extern __shared__ float s_s[];                 // [kRoRows][Hd]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = blockIdx.x * kRoRows;
     for (int i = threadIdx.x; i < 256 * static_cast<int>(sizeof(TrainT)); i += blockDim.x) s_lut[i] = lut_g[i];
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r0 = (blockIdx.x * (blockDim.x >> 5) + warp) * kRowsPerWarp;
-    if (r0 >= R) return;
-    float* s = s_s + static_cast<size_t>(warp) * kRowsPerWarp * Hd;
-    unsigned int cnt_a[kRowsPerWarp], cnt_b[kRowsPerWarp];
-#pragma unroll
-    for (int q = 0; q < kRowsPerWarp; ++q) {
-        cnt_a[q] = 0; cnt_b[q] = 0;
-        const int r = r0 + q;
+    {   // warp q stages row r0 + q (8 warps <-> 8 rows) and counts its spikes
+        const int r = r0 + warp;
+        unsigned int ca = 0, cb = 0;
         for (int h = lane; h < Hd; h += 32) {
             float sv = 0.f;
             if (r < R) {
                 const TrainT tr = trains[static_cast<size_t>(r) * Hd + h];
-                cnt_a[q] += __popc(static_cast<unsigned int>(tr));
+                ca += __popc(static_cast<unsigned int>(tr));
                 sv = lut_weight<TrainT>(s_lut, tr);
-                if (trains_b != nullptr) cnt_b[q] += __popc(static_cast<unsigned int>(trains_b[static_cast<size_t>(r) * Hd + h]));
+                if (trains_b != nullptr)
+                    cb += __popc(static_cast<unsigned int>(trains_b[static_cast<size_t>(r) * Hd + h]));
             }
-            s[q * Hd + h] = sv;
+            s_s[warp * Hd + h] = sv;
+        }
+        if (counts != nullptr) {
+            for (int off = 16; off > 0; off >>= 1) {
+                ca += __shfl_xor_sync(0xffffffffu, ca, off);
+                cb += __shfl_xor_sync(0xffffffffu, cb, off);
+            }
+            if (lane == 0 && r < R) { counts[r] = cb; counts[R + r] = ca; }
         }
     }
-    __syncwarp();
+    __syncthreads();
     const int n_out = n_cls + n_box;
-    for (int o = 0; o < n_out; ++o) {
+    for (int o = warp; o < n_out; o += 8) {
         const float* wrow = (o < n_cls) ? (w_cls + static_cast<size_t>(o) * Hd) : (w_box + static_cast<size_t>(o - n_cls) * Hd);
-        float acc[kRowsPerWarp];
+        float acc[kRoRows];
 #pragma unroll
-        for (int q = 0; q < kRowsPerWarp; ++q) acc[q] = 0.f;
+        for (int q = 0; q < kRoRows; ++q) acc[q] = 0.f;
+#pragma unroll 4
         for (int h = lane; h < Hd; h += 32) {
             const float wv = __ldg(&wrow[h]);
 #pragma unroll
-            for (int q = 0; q < kRowsPerWarp; ++q) acc[q] = fmaf(wv, s[q * Hd + h], acc[q]);
+            for (int q = 0; q < kRoRows; ++q) acc[q] = fmaf(wv, s_s[q * Hd + h], acc[q]);
         }
 #pragma unroll
-        for (int q = 0; q < kRowsPerWarp; ++q) {
+        for (int q = 0; q < kRoRows; ++q) {
             for (int off = 16; off > 0; off >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
             const int r = r0 + q;
             if (lane == 0 && r < R) {
                 if (o < n_cls) out_cls[static_cast<size_t>(r) * n_cls + o] = acc[q];
                 else out_box[static_cast<size_t>(r) * n_box + (o - n_cls)] = acc[q];
             }
-        }
-    }
-    if (counts != nullptr) {
-#pragma unroll
-        for (int q = 0; q < kRowsPerWarp; ++q) {
-            for (int off = 16; off > 0; off >>= 1) {
-                cnt_a[q] += __shfl_xor_sync(0xffffffffu, cnt_a[q], off);
-                cnt_b[q] += __shfl_xor_sync(0xffffffffu, cnt_b[q], off);
-            }
-            const int r = r0 + q;
-            if (lane == 0 && r < R) { counts[r] = cnt_b[q]; counts[R + r] = cnt_a[q]; }
         }
     }
 }

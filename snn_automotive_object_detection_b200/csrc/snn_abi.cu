@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -299,14 +300,14 @@ template <typename T>
 cudaError_t launch_readout_rows(const void* tr7, const void* tr6, int R, int Hd, const float* wc, int nc,
                                 const float* wb, int nb, const float* lut, float* oc, float* ob, unsigned int* counts,
                                 cudaStream_t st) {
-    const int warps = 4;
-    const size_t smem = static_cast<size_t>(warps) * kRowsPerWarp * Hd * 4;
+    const size_t smem = static_cast<size_t>(kRoRows) * Hd * 4;
     auto kern = readout_rows_kernel<T>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const int rows_per_block = warps * kRowsPerWarp;
-    kern<<<(R + rows_per_block - 1) / rows_per_block, warps * 32, smem, st>>>(
-        reinterpret_cast<const T*>(tr7), reinterpret_cast<const T*>(tr6), R, Hd, wc, nc, wb, nb, lut, oc, ob, counts);
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<(R + kRoRows - 1) / kRoRows, 256, smem, st>>>(reinterpret_cast<const T*>(tr7), reinterpret_cast<const T*>(tr6),
+                                                        R, Hd, wc, nc, wb, nb, lut, oc, ob, counts);
     return cudaGetLastError();
 }
 
@@ -380,6 +381,10 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
     build_lut_kernel<<<(tb * 256 + 255) / 256, 256, 0, st>>>(T, tb, lut);
     CUDA_TRY(cudaGetLastError()); ++g_launches;
 
+    // The LI readout (and the spike counts) are fused into the GEMM epilogue when a CTA pair covers all
+    // output channels (cta_group 2, C_in == 256) and the 5A outputs fit one pass; otherwise a separate
+    // readout kernel consumes the spike trains.
+    const bool fused = T_live > 0 && tc.cg == 2 && C_in == 256 && 5 * A <= kRoMaxOut;
     void* trains[kMaxLevels];
     for (int l = 0; l < n_levels; ++l) {
         trains[l] = (spike_trains_out && spike_trains_out[l]) ? spike_trains_out[l] : (wsp + ws.tr_off[l]);
@@ -389,14 +394,22 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
     if (T_live > 0) {
         // 1) encoder: fp32 NCHW features -> bf16 {0,1} NHWC spike planes
         phase_begin(PH_ENC_RPN, st);
-        for (int l = 0; l < n_levels; ++l) {
-            dim3 grid((W[l] + kEncW - 1) / kEncW, H[l], N);
-            const size_t smem = static_cast<size_t>(kEncW) * (C_in + 1) * 4;
+        {
+            EncParams ep;
+            memset(&ep, 0, sizeof(ep));
+            int blocks = 0;
+            for (int l = 0; l < n_levels; ++l) {
+                EncLevel& E = ep.lv[l];
+                E.x = reinterpret_cast<const float*>(feat_ptrs[l]);
+                E.z = reinterpret_cast<__nv_bfloat16*>(wsp + ws.z_off[l]);
+                E.H = H[l]; E.W = W[l]; E.wchunks = (W[l] + kEncW - 1) / kEncW; E.block_begin = blocks;
+                blocks += N * H[l] * E.wchunks;
+            }
+            ep.n_levels = n_levels; ep.N = N; ep.C = C_in; ep.T_live = T_live; ep.T_box = tc.T_box; ep.total_blocks = blocks;
+            const size_t smem = static_cast<size_t>(kEncW) * (C_in + 4) * 4;
             if (smem > 48 * 1024)
                 CUDA_TRY(cudaFuncSetAttribute(encode_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            encode_nchw_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(feat_ptrs[l]), N, C_in, H[l],
-                                                        W[l], T_live, tc.T_box,
-                                                        reinterpret_cast<__nv_bfloat16*>(wsp + ws.z_off[l]));
+            encode_nchw_kernel<<<blocks, 256, smem, st>>>(ep);
             CUDA_TRY(cudaGetLastError()); ++g_launches;
         }
         phase_end(PH_ENC_RPN, st);
@@ -422,8 +435,23 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
             L.H = H[l]; L.W = W[l];
             L.tiles_w = (W[l] + tc.TW - 1) / tc.TW; L.tiles_h = (H[l] + tc.TH - 1) / tc.TH;
             L.tile_begin = tiles; L.trains = trains[l];
+            L.logits = reinterpret_cast<float*>(logits_out[l]); L.bbox = reinterpret_cast<float*>(bbox_out[l]);
+            L.counts = spike_counts_out ? spike_counts_out + static_cast<size_t>(l) * N : nullptr;
             tiles += L.tiles_w * L.tiles_h * N;
         }
+        if (fused) {
+            p.fuse_readout = 1;
+            for (int l = 0; l < n_levels; ++l) {
+                if (!(spike_trains_out && spike_trains_out[l])) p.lv[l].trains = nullptr;   // nobody reads them
+                CUDA_TRY(cudaMemsetAsync(logits_out[l], 0, static_cast<size_t>(N) * A * H[l] * W[l] * 4, st));
+                CUDA_TRY(cudaMemsetAsync(bbox_out[l], 0, static_cast<size_t>(N) * 4 * A * H[l] * W[l] * 4, st));
+            }
+        } else {
+            for (int l = 0; l < n_levels; ++l) p.lv[l].counts = nullptr;   // the readout kernel counts instead
+        }
+        p.A = A; p.w_cls = w_cls; p.w_bbox = w_bbox;
+        for (int t = 0; t < 32; ++t)
+            p.kappa[t] = (t < T) ? static_cast<float>(pow(0.9, T - t) - pow(0.8, T - t)) : 0.f;
         p.n_levels = n_levels; p.conv = 1; p.n_images = N;
         p.m_total = C_in; p.nsplit = ns; p.cblocks = C_in / 64; p.kblocks = 9 * p.cblocks;
         p.T_total = T; p.t0 = 0; p.T_live = T_live;
@@ -436,9 +464,9 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
         for (int l = 0; l < n_levels; ++l)
             CUDA_TRY(cudaMemsetAsync(trains[l], 0, static_cast<size_t>(N) * H[l] * W[l] * C_in * tb, st));
     }
-    // 3) leaky-integrator readouts (objectness + box deltas) from the spike trains
+    // 3) leaky-integrator readouts (objectness + box deltas) from the spike trains (unless fused above)
     phase_begin(PH_RO_RPN, st);
-    for (int l = 0; l < n_levels; ++l) {
+    for (int l = 0; l < n_levels && !fused; ++l) {
         unsigned long long* cnt = spike_counts_out ? spike_counts_out + static_cast<size_t>(l) * N : nullptr;
         cudaError_t e;
         float* lo = reinterpret_cast<float*>(logits_out[l]);

@@ -36,13 +36,21 @@ constexpr int kStagesB = 3;                 // up to 32 KB each
 constexpr int kTileBytesA = 128 * 128;      // 128 rows x 64 bf16
 constexpr int kSlotBytesB = 256 * 128;      // up to 256 rows x 64 bf16
 constexpr int kGemmThreads = 256;
-constexpr size_t kGemmSmemBytes = 1024 /*align slack*/ + kStagesA * kTileBytesA + kStagesB * kSlotBytesB + 256;
+constexpr int kRoMaxOut = 16;               // fused readout: objectness + box deltas per pixel (5 * A <= 16)
+constexpr int kRoWStride = 132;             // floats per readout-weight row in smem (128 + pad, 16-B aligned)
+constexpr int kRoSStride = 20;              // floats per channel row of the kappa-weighted spike sums (16 + pad)
+constexpr int kRoSmemBytes = kRoMaxOut * kRoWStride * 4 + 2 * 128 * kRoSStride * 4;
+constexpr size_t kGemmSmemBytes =
+    1024 /*align slack*/ + kStagesA * kTileBytesA + kStagesB * kSlotBytesB + 256 + kRoSmemBytes;
 
 struct LevelDesc {
     int H, W, tiles_w, tiles_h;
     int tile_begin;           // first unit-tile index of this level
     int pad_;
-    void* trains;             // [N][H][W][m_total] spike-train words
+    void* trains;             // [N][H][W][m_total] spike-train words (nullable when the readout is fused)
+    float* logits;            // fused readout: [N][A][H][W]   (zero-initialised; 2 CTAs add their channel halves)
+    float* bbox;              // fused readout: [N][4A][H][W]
+    unsigned long long* counts;   // nullable: [N] spikes per image of this level
 };
 
 struct GemmLifParams {
@@ -63,6 +71,11 @@ struct GemmLifParams {
     __nv_bfloat16* spikes_out;  // optional: [spk_t_hi - spk_t_lo][rows][m_total] bf16 {0,1}
     int spk_t_lo, spk_t_hi;
     float* dump;              // debug (fc only): raw currents [T_live][rows][m_total]
+    // fused leaky-integrator readout (conv, cta_group 2, m_total == 256): mem_{T-1} = W . sum_t kappa_{T-1-t} spk_t
+    int fuse_readout, A;
+    const float* w_cls;       // [A][m_total]
+    const float* w_bbox;      // [4A][m_total]
+    float kappa[32];          // kappa[t] = 0.9^{T-t} - 0.8^{T-t}: weight of a spike at step t in the last membrane
 };
 
 // One LIF step of Norse's lif_feed_forward_step, op for op (no FMA contraction):
@@ -92,6 +105,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
     uint64_t* acc_full = b_empty + kStagesB;         // [2]
     uint64_t* acc_empty = acc_full + 2;              // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* ro_w = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);     // [kRoMaxOut][kRoWStride]
+    float* ro_s = ro_w + kRoMaxOut * kRoWStride;                                          // [2][128][kRoSStride]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -201,14 +216,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         // ============================================ LIF epilogue (4 warps)
         const int q = warp - 4;                        // TMEM lane quadrant of this warp
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const int te = q * 32 + lane;                  // 0..127: channel of this thread inside the CTA's 128
+        const int n_out = 5 * p.A;
+        if (p.fuse_readout) {                          // this CTA's 128-channel slice of the two 1x1 readout convs
+            const int c0 = static_cast<int>(rank) * 128;
+            for (int i = te; i < kRoMaxOut * 128; i += 128) {
+                const int o = i >> 7, cc = i & 127;
+                float wv = 0.f;
+                if (o < p.A) wv = p.w_cls[o * p.m_total + c0 + cc];
+                else if (o < n_out) wv = p.w_bbox[(o - p.A) * p.m_total + c0 + cc];
+                ro_w[o * kRoWStride + cc] = wv;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        uint32_t chunk_ctr = 0;
         uint32_t it = 0;
         for (int tile = group; tile < p.total_tiles; tile += n_groups, ++it) {
             const int ut = tile / p.m_tiles, mt = tile - ut * p.m_tiles;
             const int c = mt * 128 * kCG + static_cast<int>(rank) * 128 + q * 32 + lane;
-            int H = 1, W = 1, n = 0, h0 = 0, w0 = 0;
+            int H = 1, W = 1, n = 0, h0 = 0, w0 = 0, lvl = 0;
             uint8_t* trains = reinterpret_cast<uint8_t*>(p.trains);
+            unsigned int tile_spikes = 0;
             if (p.conv) {
-                int lvl = 0;
                 while (lvl + 1 < p.n_levels && ut >= p.lv[lvl + 1].tile_begin) ++lvl;
                 const LevelDesc& L = p.lv[lvl];
                 int local = ut - L.tile_begin;
@@ -227,10 +256,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             for (int sub = 0; sub < kCG; ++sub) {
                 for (int j0 = 0; j0 < p.Jh; j0 += CW) {
                     float v[CW], cu[CW];
-                    float ii[CW];
+                    float ii[CW], sk[CW];
                     uint32_t tr[CW];
 #pragma unroll
-                    for (int u = 0; u < CW; ++u) { v[u] = 0.f; ii[u] = 0.f; tr[u] = 0u; }
+                    for (int u = 0; u < CW; ++u) { v[u] = 0.f; ii[u] = 0.f; tr[u] = 0u; sk[u] = 0.f; }
                     for (int t = p.t0; t < p.T_total; ++t) {
                         const int tl = t - p.t0;
                         const bool live = tl < p.T_live;
@@ -239,10 +268,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                                         reinterpret_cast<uint32_t*>(cu));
                             tmem_ld_wait();
                         }
+                        const float kap = p.kappa[t];
 #pragma unroll
                         for (int u = 0; u < CW; ++u) {
                             const float cur = live ? cu[u] : 0.0f;
-                            tr[u] |= lif_update(v[u], ii[u], cur) << t;
+                            const uint32_t z = lif_update(v[u], ii[u], cur);
+                            tr[u] |= z << t;
+                            sk[u] = z ? __fadd_rn(sk[u], kap) : sk[u];
                         }
                         if (p.dump != nullptr && live && !p.conv) {
 #pragma unroll
@@ -270,6 +302,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                             r = static_cast<size_t>(rr);
                         }
                         if (!ok) continue;
+                        tile_spikes += __popc(tr[u]);
+                        if (trains == nullptr) continue;
                         const size_t e = r * p.m_total + c;
                         if (p.train_bytes == 1) trains[e] = static_cast<uint8_t>(tr[u]);
                         else if (p.train_bytes == 2) reinterpret_cast<uint16_t*>(trains)[e] = static_cast<uint16_t>(tr[u]);
@@ -280,7 +314,56 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                                     __ushort_as_bfloat16(((tr[u] >> t) & 1u) ? 0x3F80 : 0);
                         }
                     }
+                    // ---- fused LI readout: out[o][px] += sum_{c in this CTA} W[o][c] * sk[c][px]
+                    if (p.fuse_readout) {
+                        float* S = ro_s + (chunk_ctr & 1u) * (128 * kRoSStride);
+                        ++chunk_ctr;
+#pragma unroll
+                        for (int u = 0; u < CW; u += 4)
+                            *reinterpret_cast<float4*>(&S[te * kRoSStride + u]) = make_float4(sk[u], sk[u + 1], sk[u + 2], sk[u + 3]);
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        constexpr int kGroups = 128 / CW;              // thread = (pixel u, output group og)
+                        constexpr int kOPT = (kRoMaxOut + kGroups - 1) / kGroups;
+                        const int u = te % CW, og = te / CW;
+                        float acc[kOPT];
+#pragma unroll
+                        for (int k = 0; k < kOPT; ++k) acc[k] = 0.f;
+                        if (og < kRoMaxOut) {
+#pragma unroll 4
+                            for (int cc = 0; cc < 128; cc += 4) {
+                                const float s0 = S[(cc + 0) * kRoSStride + u], s1 = S[(cc + 1) * kRoSStride + u];
+                                const float s2 = S[(cc + 2) * kRoSStride + u], s3 = S[(cc + 3) * kRoSStride + u];
+#pragma unroll
+                                for (int k = 0; k < kOPT; ++k) {
+                                    const int o = og + k * kGroups;
+                                    if (o < kRoMaxOut) {
+                                        const float4 wv = *reinterpret_cast<const float4*>(&ro_w[o * kRoWStride + cc]);
+                                        acc[k] = fmaf(wv.x, s0, acc[k]); acc[k] = fmaf(wv.y, s1, acc[k]);
+                                        acc[k] = fmaf(wv.z, s2, acc[k]); acc[k] = fmaf(wv.w, s3, acc[k]);
+                                    }
+                                }
+                            }
+                            const int jh = j0 + u;
+                            const int ty = jh / p.TWh, tx = jh - ty * p.TWh;
+                            const int h = h0 + sub * p.sub_dh + ty, w = w0 + sub * p.sub_dw + tx;
+                            if (h < H && w < W) {
+                                const LevelDesc& L = p.lv[lvl];
+                                const size_t hw = static_cast<size_t>(H) * W, pix = static_cast<size_t>(h) * W + w;
+#pragma unroll
+                                for (int k = 0; k < kOPT; ++k) {
+                                    const int o = og + k * kGroups;
+                                    if (o < p.A) atomicAdd(&L.logits[(static_cast<size_t>(n) * p.A + o) * hw + pix], acc[k]);
+                                    else if (o < n_out)
+                                        atomicAdd(&L.bbox[(static_cast<size_t>(n) * 4 * p.A + (o - p.A)) * hw + pix], acc[k]);
+                                }
+                            }
+                        }
+                    }
                 }
+            }
+            if (p.conv && p.lv[lvl].counts != nullptr) {
+                for (int o = 16; o > 0; o >>= 1) tile_spikes += __shfl_xor_sync(0xffffffffu, tile_spikes, o);
+                if (lane == 0 && tile_spikes) atomicAdd(&p.lv[lvl].counts[n], static_cast<unsigned long long>(tile_spikes));
             }
             tcgen05_fence_before();
             __syncwarp();
