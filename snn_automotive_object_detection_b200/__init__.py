@@ -1,5 +1,8 @@
 """B200-native spiking detection heads (drop-in for the reference's Norse path)."""
 from .heads import RPNHeadSNN, FastRCNNPredictorSNNFull, EncoderParameters, unpack_trains  # noqa: F401
-from . import _lib  # noqa: F401
+from .plugin import attach_snn_heads  # noqa: F401
+from .rates import rpn_spike_rates_and_flops, box_spike_rates_and_flops, energy_ratio  # noqa: F401
+from . import _lib, parallel  # noqa: F401
 
-__all__ = ["RPNHeadSNN", "FastRCNNPredictorSNNFull", "EncoderParameters", "unpack_trains"]
+__all__ = ["RPNHeadSNN", "FastRCNNPredictorSNNFull", "EncoderParameters", "unpack_trains", "attach_snn_heads",
+           "rpn_spike_rates_and_flops", "box_spike_rates_and_flops", "energy_ratio", "parallel"]
