@@ -39,7 +39,7 @@ WORKLOADS = {
 }
 T_RPN, T_DET, ROIS, CH, HID, KBOX = 8, 12, 1000, 256, 1024, 12544
 METRIC = "SNN-head images/sec (1024x2048, Trpn8/Tdet12)"
-PIECES = {"fp32_exact": 3, "bf16x2": 2, "bf16": 1}
+PIECES = {"fp32_exact": 3, "bf16x2": 2, "bf16": 1, "fp16x2": 2, "fp16": 1}
 
 
 def parse():
@@ -340,7 +340,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl["name"], "images_per_gpu_per_step": B, "global_batch": B * world,
                    "T_rpn": args.t_rpn, "T_det": args.t_det, "rois_per_image": ROIS, "classes": C,
-                   "weight_mode": args.mode, "bf16_pieces_per_weight": pieces,
+                   "weight_mode": args.mode, "pieces_per_weight": pieces,
                    "l2": f"inputs {in_bytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                    "parallelism": f"image-sharded dp{world}, no hot-path collective"},
         "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,

@@ -11,9 +11,13 @@
  *   - kernels are enqueued on `stream` (a cudaStream_t) and the call returns without synchronising.
  *   - return value 0 = success, negative SNN_E_* otherwise; snn_last_error() gives the message
  *     (thread-local).  There is no CPU fallback: a non-sm_100 device is SNN_E_ARCH.
- *   - `mode` selects how fp32 weights are fed to the bf16 tensor cores.  The other operand of every
- *     contraction on this path is an exact {0,1} spike, so a weight kept as k bf16 pieces
+ *   - `mode` selects how fp32 weights are fed to the 16-bit tensor cores.  The other operand of every
+ *     contraction on this path is an exact {0,1} spike, so a weight kept as k 16-bit pieces
  *     (hi + mid + lo) gives exact products; only the fp32 accumulation order differs from the reference.
+ *     bf16 pieces carry 8 significant bits each (3 pieces = the fp32 weight exactly); fp16 pieces carry
+ *     11 bits each and are taken from the weight row scaled by a power of two (so no piece is subnormal),
+ *     the accumulator being scaled back in the epilogue: 2 fp16 pieces reproduce every weight to within
+ *     one fp32 ulp (>= 23 of its 24 significant bits) at 2/3 of the tensor work of 3 bf16 pieces.
  */
 #ifndef SNN_HEADS_H_
 #define SNN_HEADS_H_
@@ -24,11 +28,13 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 1
+#define SNN_ABI_VERSION 2
 
 #define SNN_MODE_FP32_EXACT 0 /* 3 bf16 pieces per weight (24 mantissa bits): the parity mode          */
 #define SNN_MODE_BF16 1       /* 1 piece: weights rounded to bf16, the throughput mode                 */
 #define SNN_MODE_BF16X2 2     /* 2 pieces (16 mantissa bits)                                           */
+#define SNN_MODE_FP16X2 3     /* 2 fp16 pieces of the row-scaled weight (>= 23 bits): fast fp32-grade mode */
+#define SNN_MODE_FP16 4       /* 1 fp16 piece of the row-scaled weight (11 bits)                        */
 
 #define SNN_OK 0
 #define SNN_E_ARG (-1)       /* bad argument / unsupported shape                                        */
@@ -43,11 +49,12 @@ const char* snn_last_error(void);
 
 /* Bytes per neuron of a time-packed spike train for T steps: 1 (T<=8), 2 (T<=16), 4 (T<=32). */
 int snn_train_word_bytes(int T);
-/* Number of bf16 pieces per weight for `mode`. */
+/* Number of 16-bit pieces per weight for `mode`. */
 int snn_mode_pieces(int mode);
 
 /* ---- one-time weight preparation (re-run only when the fp32 weights change) ------------------------- */
-/* bytes of a prepared weight with `rows` outputs and `cols` inputs */
+/* bytes of a prepared weight with `rows` outputs and `cols` inputs: [pieces][rows][cols] 16-bit pieces
+ * followed by float scale[rows] (the power of two the accumulator row is multiplied with; 1 for bf16 modes) */
 size_t snn_prepared_weight_bytes(int rows, int cols, int mode);
 /* RPNHeadSNN.shared_conv.weight [O][C][3][3] fp32 (rpn.py:65-66) -> [pieces][O][9*C] bf16, k = (ky*3+kx)*C + c */
 int snn_prepare_conv3x3_weights(const float* w, int O, int C, int mode, void* out, snn_stream_t stream);
@@ -97,8 +104,9 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
 int snn_fc_lif_layer(const void* z, int R, int K, int M, int T, int t0, int T_live, int mode, const void* w_prep,
                      void* trains, void* spikes_out, int t_lo, int t_hi, float* dump, int cta_group,
                      snn_stream_t stream);
-/* encoder only: x [R][K] fp32 -> z [T_live][R][K] bf16 {0,1} (Norse lif_current_encoder, faster_rcnn.py:494) */
-int snn_encode_rows(const float* x, int R, int K, int T_live, void* z, snn_stream_t stream);
+/* encoder only: x [R][K] fp32 -> z [T_live][R][K] {0,1} in the 16-bit format of `mode` (bf16 or fp16)
+ * (Norse lif_current_encoder, faster_rcnn.py:494) */
+int snn_encode_rows(const float* x, int R, int K, int T_live, int mode, void* z, snn_stream_t stream);
 
 /* number of kernels the last forward call on this thread enqueued (for bench accounting) */
 int snn_last_launch_count(void);

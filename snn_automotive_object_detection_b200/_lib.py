@@ -10,8 +10,12 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsnn_heads_b200.so")
 
-MODE_FP32_EXACT, MODE_BF16, MODE_BF16X2 = 0, 1, 2
-MODES = {"fp32_exact": MODE_FP32_EXACT, "fp32": MODE_FP32_EXACT, "bf16": MODE_BF16, "bf16x2": MODE_BF16X2}
+MODE_FP32_EXACT, MODE_BF16, MODE_BF16X2, MODE_FP16X2, MODE_FP16 = 0, 1, 2, 3, 4
+MODES = {"fp32_exact": MODE_FP32_EXACT, "fp32": MODE_FP32_EXACT, "bf16x3": MODE_FP32_EXACT, "bf16": MODE_BF16,
+         "bf16x2": MODE_BF16X2, "fp16x2": MODE_FP16X2, "fp16": MODE_FP16}
+# 16-bit pieces per weight and the torch dtype of the {0,1} spike planes each mode contracts
+PIECES = {MODE_FP32_EXACT: 3, MODE_BF16: 1, MODE_BF16X2: 2, MODE_FP16X2: 2, MODE_FP16: 1}
+FP16_MODES = (MODE_FP16X2, MODE_FP16)
 
 # every symbol include/snn_heads.h declares
 EXPORTS = [
@@ -45,7 +49,7 @@ def _declare(lib):
     lib.snn_box_head_forward.argtypes = [vp, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.snn_box_head_forward.restype = i
     lib.snn_fc_lif_layer.argtypes = [vp, i, i, i, i, i, i, i, vp, vp, vp, i, i, vp, i, vp]; lib.snn_fc_lif_layer.restype = i
-    lib.snn_encode_rows.argtypes = [vp, i, i, i, vp, vp]; lib.snn_encode_rows.restype = i
+    lib.snn_encode_rows.argtypes = [vp, i, i, i, i, vp, vp]; lib.snn_encode_rows.restype = i
     lib.snn_last_launch_count.restype = i
     lib.snn_set_cta_group.argtypes = [i]; lib.snn_set_cta_group.restype = None
     lib.snn_profile_enable.argtypes = [i]; lib.snn_profile_enable.restype = None
@@ -75,7 +79,7 @@ def check(rc, what):
 
 def mode_id(mode):
     if isinstance(mode, int):
-        if mode not in (0, 1, 2):
+        if mode not in PIECES:
             raise ValueError(f"unknown mode {mode}")
         return mode
     try:

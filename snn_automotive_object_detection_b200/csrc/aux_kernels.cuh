@@ -3,40 +3,67 @@
 // leaky-integrator readouts (Norse LICell; rpn.py:110-115, faster_rcnn.py:505-510).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace snn {
 
 // ------------------------------------------------------------ weight prep
-// w = hi + mid + lo with each piece a bf16; residuals are exact in fp32.
-__device__ __forceinline__ void split_bf16(float w, int nsplit, __nv_bfloat16* out, size_t stride, size_t idx) {
-    float r = w;
-    for (int s = 0; s < nsplit; ++s) {
-        const __nv_bfloat16 b = __float2bfloat16_rn(r);
-        out[s * stride + idx] = b;
-        r = __fsub_rn(r, __bfloat162float(b));
+// One block per output row.  bf16 modes: w = hi + mid + lo, each piece a bf16 (residuals are exact in
+// fp32), scale = 1.  fp16 modes: the row is first multiplied by 2^S with max|row| * 2^S in [2^14, 2^15)
+// (exact; keeps every low piece of a weight down to 2^-16 of the row maximum out of the fp16 subnormals),
+// then split into fp16 pieces; the epilogue multiplies the accumulator by scale = 2^-S (exact).
+// Output layout: [nsplit][O][K] 16-bit pieces, then float scale[O].
+// kConv: source is [O][C][3][3] and the prepared k index is (ky*3+kx)*C + c; else source is [O][K].
+template <bool kConv>
+__global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restrict__ w, int O, int K, int C,
+                                                           int nsplit, int fp16, uint16_t* __restrict__ out,
+                                                           float* __restrict__ scale) {
+    __shared__ float s_max[8];
+    const size_t plane = static_cast<size_t>(O) * K;
+    for (int o = blockIdx.x; o < O; o += gridDim.x) {
+        const float* wrow = w + static_cast<size_t>(o) * K;
+        int S = 0;
+        if (fp16) {
+            float m = 0.f;
+            for (int k = threadIdx.x; k < K; k += blockDim.x) m = fmaxf(m, fabsf(wrow[k]));
+            for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+            __syncthreads();
+            m = s_max[0];
+            for (int q = 1; q < 8; ++q) m = fmaxf(m, s_max[q]);
+            if (m > 0.f && m < 3.0e38f) {
+                int e;
+                frexpf(m, &e);                     // m = f * 2^e, f in [0.5, 1)
+                S = 15 - e;
+                S = S > 100 ? 100 : (S < -100 ? -100 : S);
+            }
+        }
+        if (threadIdx.x == 0) scale[o] = ldexpf(1.0f, -S);
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            float src;
+            if (kConv) {
+                const int tap = k / C, c = k - tap * C;
+                src = wrow[c * 9 + tap];
+            } else {
+                src = wrow[k];
+            }
+            float r = ldexpf(src, S);
+            const size_t idx = static_cast<size_t>(o) * K + k;
+            for (int s = 0; s < nsplit; ++s) {
+                if (fp16) {
+                    const __half h = __float2half_rn(r);
+                    out[s * plane + idx] = __half_as_ushort(h);
+                    r = __fsub_rn(r, __half2float(h));
+                } else {
+                    const __nv_bfloat16 b = __float2bfloat16_rn(r);
+                    out[s * plane + idx] = __bfloat16_as_ushort(b);
+                    r = __fsub_rn(r, __bfloat162float(b));
+                }
+            }
+        }
     }
-}
-
-// [O][C][3][3] fp32  ->  [nsplit][O][9*C] bf16 with k = (ky*3+kx)*C + c
-__global__ void prep_conv3x3_weights_kernel(const float* __restrict__ w, int O, int C, int nsplit,
-                                            __nv_bfloat16* __restrict__ out) {
-    const size_t total = static_cast<size_t>(O) * C * 9;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int k = static_cast<int>(i % (9 * C));
-        const int o = static_cast<int>(i / (9 * C));
-        const int tap = k / C, c = k - tap * C;
-        split_bf16(w[(static_cast<size_t>(o) * C + c) * 9 + tap], nsplit, out, total, i);
-    }
-}
-
-// [O][K] fp32 -> [nsplit][O][K] bf16
-__global__ void prep_fc_weights_kernel(const float* __restrict__ w, size_t total, int nsplit,
-                                       __nv_bfloat16* __restrict__ out) {
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x)
-        split_bf16(w[i], nsplit, out, total, i);
 }
 
 // ---------------------------------------------------------------- encoder
@@ -59,12 +86,13 @@ constexpr int kEncMaxLevels = 8;
 
 struct EncLevel {
     const float* x;             // [N][C][H][W] fp32
-    __nv_bfloat16* z;           // [T_box][N][H][W][C] bf16 {0,1}
+    uint16_t* z;                // [T_box][N][H][W][C] 16-bit {0,1} (bf16 or fp16 "one" pattern)
     int H, W, wchunks, block_begin;
 };
 struct EncParams {
     EncLevel lv[kEncMaxLevels];
     int n_levels, N, C, T_live, T_box, total_blocks;
+    uint32_t one;               // 16-bit pattern of 1.0: 0x3F80 (bf16) or 0x3C00 (fp16)
 };
 
 // All FPN levels in one launch.  One block = one (level, n, h, 32-pixel run):
@@ -104,22 +132,25 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
         const int px = idx / groups, g8 = idx - px * groups;
         const uint4 a = *reinterpret_cast<const uint4*>(&s_tr[px * ld + 8 * g8]);
         const uint4 b = *reinterpret_cast<const uint4*>(&s_tr[px * ld + 8 * g8 + 4]);
-        __nv_bfloat16* dst = L.z + ((static_cast<size_t>(n) * H + h) * W + (w0 + px)) * C + 8 * g8;
+        uint16_t* dst = L.z + ((static_cast<size_t>(n) * H + h) * W + (w0 + px)) * C + 8 * g8;
+        const uint32_t lo1 = p.one, hi1 = p.one << 16;
         for (int t = 0; t < p.T_box; ++t) {
             uint4 o;
-            o.x = (((a.x >> t) & 1u) ? 0x3F80u : 0u) | (((a.y >> t) & 1u) ? 0x3F800000u : 0u);
-            o.y = (((a.z >> t) & 1u) ? 0x3F80u : 0u) | (((a.w >> t) & 1u) ? 0x3F800000u : 0u);
-            o.z = (((b.x >> t) & 1u) ? 0x3F80u : 0u) | (((b.y >> t) & 1u) ? 0x3F800000u : 0u);
-            o.w = (((b.z >> t) & 1u) ? 0x3F80u : 0u) | (((b.w >> t) & 1u) ? 0x3F800000u : 0u);
+            o.x = (((a.x >> t) & 1u) ? lo1 : 0u) | (((a.y >> t) & 1u) ? hi1 : 0u);
+            o.y = (((a.z >> t) & 1u) ? lo1 : 0u) | (((a.w >> t) & 1u) ? hi1 : 0u);
+            o.z = (((b.x >> t) & 1u) ? lo1 : 0u) | (((b.y >> t) & 1u) ? hi1 : 0u);
+            o.w = (((b.z >> t) & 1u) ? lo1 : 0u) | (((b.w >> t) & 1u) ? hi1 : 0u);
             if (t >= p.T_live) o = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4*>(dst + static_cast<size_t>(t) * plane) = o;
         }
     }
 }
 
-// x [R][K] fp32 -> Z [T_box][R][K] bf16 {0,1}; 8 consecutive k per thread (2 x float4 in, 16 B out per step)
+// x [R][K] fp32 -> Z [T_box][R][K] 16-bit {0,1}; 8 consecutive k per thread (2 x float4 in, 16 B out per step)
 __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total8, size_t plane,
-                                                          int T_live, int T_box, __nv_bfloat16* __restrict__ z) {
+                                                          int T_live, int T_box, uint32_t one,
+                                                          uint16_t* __restrict__ z) {
+    const uint32_t lo1 = one, hi1 = one << 16;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
@@ -133,7 +164,7 @@ __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restric
             uint32_t wv[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                wv[q] = (((tr[2 * q] >> t) & 1u) ? 0x3F80u : 0u) | (((tr[2 * q + 1] >> t) & 1u) ? 0x3F800000u : 0u);
+                wv[q] = (((tr[2 * q] >> t) & 1u) ? lo1 : 0u) | (((tr[2 * q + 1] >> t) & 1u) ? hi1 : 0u);
             o.x = wv[0]; o.y = wv[1]; o.z = wv[2]; o.w = wv[3];
             if (t >= T_live) o = make_uint4(0, 0, 0, 0);
             reinterpret_cast<uint4*>(z + static_cast<size_t>(t) * plane)[i] = o;

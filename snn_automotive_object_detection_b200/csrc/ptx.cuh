@@ -136,9 +136,9 @@ __device__ __forceinline__ void tcgen05_fence_after() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread.
+// D[tmem] (+)= A[smem] * B[smem], 16-bit float operands (format in idesc) -> fp32, issued by ONE thread.
 template <int kCtaGroup>
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
     if constexpr (kCtaGroup == 1) {
         asm volatile(
@@ -185,9 +185,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= static_cast<uint64_t>(2) << 61;                       // [61,64) SWIZZLE_128B
     return d;
 }
-// instruction descriptor: dense, D=f32, A=B=bf16, both K-major
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+// instruction descriptor (kind::f16): dense, D=f32, A=B=bf16 (format 1) or fp16 (format 0), both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool bf16) {
+    const uint32_t fmt = bf16 ? 1u : 0u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
            (static_cast<uint32_t>(M >> 4) << 24);
 }
 

@@ -110,6 +110,25 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims
     return SNN_OK;
 }
 
+int nsplit_of(int mode) {
+    switch (mode) {
+        case SNN_MODE_FP32_EXACT: return 3;
+        case SNN_MODE_BF16: return 1;
+        case SNN_MODE_BF16X2: return 2;
+        case SNN_MODE_FP16X2: return 2;
+        case SNN_MODE_FP16: return 1;
+        default: return 0;
+    }
+}
+bool is_fp16(int mode) { return mode == SNN_MODE_FP16X2 || mode == SNN_MODE_FP16; }
+uint32_t one_of(int mode) { return is_fp16(mode) ? 0x3C00u : 0x3F80u; }
+// the per-row accumulator scales sit behind the 16-bit pieces of a prepared weight
+const float* scale_of(const void* w_prep, int rows, int cols, int mode) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(w_prep) +
+                                          static_cast<size_t>(nsplit_of(mode)) * rows * cols * 2);
+}
+
+
 // --------------------------------------------------------------------------- tile selection
 struct TileCfg { int cg, T_box, J, Jh, TW, TH, TWh, THh, dw, dh, CW, n_mma; };
 
@@ -165,10 +184,11 @@ cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_
 #undef SNN_LAUNCH
 }
 
-int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, cudaStream_t st) {
+int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int mode, cudaStream_t st) {
     p.J = tc.J; p.Jh = tc.Jh; p.TW = tc.TW; p.TH = tc.TH; p.TWh = tc.TWh; p.THh = tc.THh;
     p.sub_dw = tc.dw; p.sub_dh = tc.dh; p.T_box = tc.T_box; p.n_mma = tc.n_mma;
-    p.idesc = umma_idesc_bf16(128 * tc.cg, tc.n_mma);
+    p.idesc = umma_idesc_f16(128 * tc.cg, tc.n_mma, !is_fp16(mode));
+    p.spike_one = one_of(mode);
     p.m_tiles = p.m_total / (128 * tc.cg);
     p.total_tiles = p.unit_tiles * p.m_tiles;
     if (p.total_tiles <= 0) return SNN_OK;
@@ -196,8 +216,6 @@ __global__ void build_lut_kernel(int T, int nbytes, float* lut) {
     }
     lut[i] = static_cast<float>(s);
 }
-
-int nsplit_of(int mode) { return mode == SNN_MODE_FP32_EXACT ? 3 : mode == SNN_MODE_BF16 ? 1 : mode == SNN_MODE_BF16X2 ? 2 : 0; }
 
 struct RpnWs { size_t z_off[kMaxLevels], tr_off[kMaxLevels], lut_off, total; };
 
@@ -253,11 +271,13 @@ int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, 
     return SNN_OK;
 }
 
-int fc_layer(const DeviceInfo& di, const void* z, int R, int K, int M, int T, int t0, int T_live, int nsplit,
+int fc_layer(const DeviceInfo& di, const void* z, int R, int K, int M, int T, int t0, int T_live, int mode,
              const void* w_prep, void* trains, void* spikes_out, int t_lo, int t_hi, float* dump, const TileCfg& tc,
              cudaStream_t st) {
     GemmLifParams p;
     memset(&p, 0, sizeof(p));
+    const int nsplit = nsplit_of(mode);
+    p.w_scale = scale_of(w_prep, M, K, mode);
     {
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)nsplit * M};
         cuuint64_t str[1] = {(cuuint64_t)K * 2};
@@ -278,9 +298,9 @@ int fc_layer(const DeviceInfo& di, const void* z, int R, int K, int M, int T, in
     p.rows = R; p.unit_tiles = (R + tc.J - 1) / tc.J;
     p.train_bytes = snn_train_word_bytes(T);
     p.trains = trains;
-    p.spikes_out = reinterpret_cast<__nv_bfloat16*>(spikes_out); p.spk_t_lo = t_lo; p.spk_t_hi = t_hi;
+    p.spikes_out = reinterpret_cast<uint16_t*>(spikes_out); p.spk_t_lo = t_lo; p.spk_t_hi = t_hi;
     p.dump = dump;
-    return launch_gemm(p, tc, di, st);
+    return launch_gemm(p, tc, di, mode, st);
 }
 
 template <typename T>
@@ -323,16 +343,16 @@ int snn_train_word_bytes(int T) { return T <= 8 ? 1 : T <= 16 ? 2 : 4; }
 int snn_mode_pieces(int mode) { return nsplit_of(mode); }
 
 size_t snn_prepared_weight_bytes(int rows, int cols, int mode) {
-    return static_cast<size_t>(nsplit_of(mode)) * rows * cols * 2;
+    return static_cast<size_t>(nsplit_of(mode)) * rows * cols * 2 + static_cast<size_t>(rows) * sizeof(float);
 }
 
 int snn_prepare_conv3x3_weights(const float* w, int O, int C, int mode, void* out, snn_stream_t stream) {
     const int ns = nsplit_of(mode);
     if (ns == 0 || O < 1 || C < 1 || !w || !out) return fail(SNN_E_ARG, "prepare_conv3x3: bad argument");
-    const size_t total = static_cast<size_t>(O) * C * 9;
-    const int blocks = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
-    prep_conv3x3_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, O, C, ns,
-                                                                           reinterpret_cast<__nv_bfloat16*>(out));
+    if ((C * 9) % 8 != 0) return fail(SNN_E_ARG, "prepare_conv3x3: 9*C must be a multiple of 8");
+    float* scale = const_cast<float*>(scale_of(out, O, 9 * C, mode));
+    prep_weights_kernel<true><<<O < 2048 ? O : 2048, 256, 0, (cudaStream_t)stream>>>(
+        w, O, 9 * C, C, ns, is_fp16(mode) ? 1 : 0, reinterpret_cast<uint16_t*>(out), scale);
     CUDA_TRY(cudaGetLastError());
     return SNN_OK;
 }
@@ -340,9 +360,10 @@ int snn_prepare_conv3x3_weights(const float* w, int O, int C, int mode, void* ou
 int snn_prepare_fc_weights(const float* w, int O, int K, int mode, void* out, snn_stream_t stream) {
     const int ns = nsplit_of(mode);
     if (ns == 0 || O < 1 || K < 1 || !w || !out) return fail(SNN_E_ARG, "prepare_fc: bad argument");
-    const size_t total = static_cast<size_t>(O) * K;
-    const int blocks = static_cast<int>((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256);
-    prep_fc_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, total, ns, reinterpret_cast<__nv_bfloat16*>(out));
+    if (K % 2 != 0) return fail(SNN_E_ARG, "prepare_fc: K must be even");
+    float* scale = const_cast<float*>(scale_of(out, O, K, mode));
+    prep_weights_kernel<false><<<O < 2048 ? O : 2048, 256, 0, (cudaStream_t)stream>>>(
+        w, O, K, 0, ns, is_fp16(mode) ? 1 : 0, reinterpret_cast<uint16_t*>(out), scale);
     CUDA_TRY(cudaGetLastError());
     return SNN_OK;
 }
@@ -401,11 +422,12 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
             for (int l = 0; l < n_levels; ++l) {
                 EncLevel& E = ep.lv[l];
                 E.x = reinterpret_cast<const float*>(feat_ptrs[l]);
-                E.z = reinterpret_cast<__nv_bfloat16*>(wsp + ws.z_off[l]);
+                E.z = reinterpret_cast<uint16_t*>(wsp + ws.z_off[l]);
                 E.H = H[l]; E.W = W[l]; E.wchunks = (W[l] + kEncW - 1) / kEncW; E.block_begin = blocks;
                 blocks += N * H[l] * E.wchunks;
             }
             ep.n_levels = n_levels; ep.N = N; ep.C = C_in; ep.T_live = T_live; ep.T_box = tc.T_box; ep.total_blocks = blocks;
+            ep.one = one_of(mode);
             const size_t smem = static_cast<size_t>(kEncW) * (C_in + 4) * 4;
             if (smem > 48 * 1024)
                 CUDA_TRY(cudaFuncSetAttribute(encode_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -456,8 +478,9 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
         p.m_total = C_in; p.nsplit = ns; p.cblocks = C_in / 64; p.kblocks = 9 * p.cblocks;
         p.T_total = T; p.t0 = 0; p.T_live = T_live;
         p.rows = 0; p.unit_tiles = tiles; p.train_bytes = tb;
+        p.w_scale = scale_of(w_shared_prep, C_in, 9 * C_in, mode);
         phase_begin(PH_GEMM_RPN, st);
-        rc = launch_gemm(p, tc, di, st);
+        rc = launch_gemm(p, tc, di, mode, st);
         phase_end(PH_GEMM_RPN, st);
         if (rc) return rc;
     } else {
@@ -530,16 +553,16 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
         const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
         phase_begin(PH_ENC_BOX, st);
         encode_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), total8, static_cast<size_t>(R) * K,
-                                                   T_live6, t6.T_box, reinterpret_cast<__nv_bfloat16*>(z));
+                                                   T_live6, t6.T_box, one_of(mode), reinterpret_cast<uint16_t*>(z));
         phase_end(PH_ENC_BOX, st);
         CUDA_TRY(cudaGetLastError()); ++g_launches;
     }
     phase_begin(PH_GEMM_FC6, st);
-    rc = fc_layer(di, z, R, K, Hdim, T, 0, T_live6, ns, w6_prep, tr6, s6, 1, 1 + t7.T_box, nullptr, t6, st);
+    rc = fc_layer(di, z, R, K, Hdim, T, 0, T_live6, mode, w6_prep, tr6, s6, 1, 1 + t7.T_box, nullptr, t6, st);
     phase_end(PH_GEMM_FC6, st);
     if (rc) return rc;
     phase_begin(PH_GEMM_FC7, st);
-    rc = fc_layer(di, s6, R, Hdim, Hdim, T, 1, T_live7, ns, w7_prep, tr7, nullptr, 0, 0, nullptr, t7, st);
+    rc = fc_layer(di, s6, R, Hdim, Hdim, T, 1, T_live7, mode, w7_prep, tr7, nullptr, 0, 0, nullptr, t7, st);
     phase_end(PH_GEMM_FC7, st);
     if (rc) return rc;
     phase_begin(PH_RO_BOX, st);
@@ -576,12 +599,13 @@ int snn_profile_read(float* ms_out, int* counts_out) {
     return SNN_OK;
 }
 
-int snn_encode_rows(const float* x, int R, int K, int T_live, void* z, snn_stream_t stream) {
-    if (!x || !z || R < 1 || K % 8 != 0 || T_live < 1 || T_live > 32) return fail(SNN_E_ARG, "encode_rows: bad argument");
+int snn_encode_rows(const float* x, int R, int K, int T_live, int mode, void* z, snn_stream_t stream) {
+    if (!x || !z || R < 1 || K % 8 != 0 || T_live < 1 || T_live > 32 || nsplit_of(mode) == 0)
+        return fail(SNN_E_ARG, "encode_rows: bad argument");
     const size_t total8 = static_cast<size_t>(R) * K / 8;
     const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
     encode_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, total8, static_cast<size_t>(R) * K, T_live, T_live,
-                                                                 reinterpret_cast<__nv_bfloat16*>(z));
+                                                                 one_of(mode), reinterpret_cast<uint16_t*>(z));
     CUDA_TRY(cudaGetLastError());
     return SNN_OK;
 }
@@ -601,7 +625,7 @@ int snn_fc_lif_layer(const void* z, int R, int K, int M, int T, int t0, int T_li
     TileCfg tc;
     if (!pick_tile(T_live, false, M, cta_group, tc)) return fail(SNN_E_ARG, "no tile shape for T_live=%d cta_group=%d", T_live, cta_group);
     if (tc.T_box != T_live) return fail(SNN_E_ARG, "fc_lif_layer needs T_live with an unpadded tile (got T_box %d)", tc.T_box);
-    return fc_layer(di, z, R, K, M, T, t0, T_live, ns, w_prep, trains, spikes_out, t_lo, t_hi, dump, tc, (cudaStream_t)stream);
+    return fc_layer(di, z, R, K, M, T, t0, T_live, mode, w_prep, trains, spikes_out, t_lo, t_hi, dump, tc, (cudaStream_t)stream);
 }
 
 }  // extern "C"

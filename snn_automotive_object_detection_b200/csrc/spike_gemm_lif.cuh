@@ -5,12 +5,14 @@
 //     cur = conv/linear(z_t) ; spk_t, state = LIFCell(cur, state)
 // (rpn.py:105-106, faster_rcnn.py:498-501) by ONE launch:
 //
-//   D[c, (t, u)] = sum_k  Wsplit[c, k] * Z[t, u, k]         (tcgen05.mma, bf16 x {0,1} -> fp32 in TMEM)
+//   D[c, (t, u)] = sum_k  Wsplit[c, k] * Z[t, u, k]         (tcgen05.mma, bf16|fp16 x {0,1} -> fp32 in TMEM)
 //   for every neuron (u, c):  run the LIF recurrence over t in registers, emit its spike train
 //
 //  * A operand  = weights [M rows = output channels][K] bf16, K-major, TMA 2-D tiles 128 x 64.
 //    "fp32-exact" mode keeps 2 or 3 bf16 pieces of every weight (hi/mid/lo); because the other
 //    operand is exactly {0,1} every product is exact and the pieces are simply extra k-steps.
+//    fp16 modes keep 1 or 2 fp16 pieces of the power-of-two row-scaled weight (11 bits each) and
+//    the epilogue multiplies the accumulator row by the inverse scale (exact).
 //  * B operand  = input spikes, rows ordered (t, unit) so that ALL timesteps of a unit sit in
 //    the same accumulator tile (time folded into the MMA N dimension, N = T_box * J <= 256):
 //      fc   : 3-D tensor map  [T][R][K]          box (64, Jh, T_box)
@@ -68,8 +70,10 @@ struct GemmLifParams {
     int n_mma;                // T_box * J
     uint32_t idesc;
     void* trains;             // fc: [rows][m_total]
-    __nv_bfloat16* spikes_out;  // optional: [spk_t_hi - spk_t_lo][rows][m_total] bf16 {0,1}
+    uint16_t* spikes_out;     // optional: [spk_t_hi - spk_t_lo][rows][m_total] 16-bit {0,1} (pattern spike_one)
     int spk_t_lo, spk_t_hi;
+    uint32_t spike_one;       // 1.0 as bf16 (0x3F80) or fp16 (0x3C00)
+    const float* w_scale;     // [m_total] power of two each accumulator row is multiplied with (1 for bf16 pieces)
     float* dump;              // debug (fc only): raw currents [T_live][rows][m_total]
     // fused leaky-integrator readout (conv, cta_group 2, m_total == 256): mem_{T-1} = W . sum_t kappa_{T-1-t} spk_t
     int fuse_readout, A;
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                         const uint64_t a_desc = umma_desc_sw128(smem_u32(a_ring + sa * kTileBytesA));
 #pragma unroll
                         for (int k = 0; k < 4; ++k)     // 4 x (K = 16 bf16 = 32 B) inside the 128-B swizzle span
-                            umma_bf16<kCG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, p.idesc,
+                            umma_f16<kCG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, p.idesc,
                                            (kb | s | k) != 0 ? 1u : 0u);
                         if constexpr (kCG == 1) umma_commit<1>(&a_empty[sa]);
                         else umma_commit_2sm_mcast(&a_empty[sa], 0b11);
@@ -248,6 +252,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 H = L.H; W = L.W;
                 trains = reinterpret_cast<uint8_t*>(L.trains);
             }
+            const float wscale = __ldg(&p.w_scale[c]);
             const uint32_t buf = it & 1u;
             mbar_wait(&acc_full[buf], (it >> 1) & 1u);
             tcgen05_fence_after();
@@ -267,6 +272,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                             tmem_ld<CW>(acc + static_cast<uint32_t>(sub * n_half + tl * p.Jh + j0),
                                         reinterpret_cast<uint32_t*>(cu));
                             tmem_ld_wait();
+#pragma unroll
+                            for (int u = 0; u < CW; ++u) cu[u] = __fmul_rn(cu[u], wscale);   // exact: power of two
                         }
                         const float kap = p.kappa[t];
 #pragma unroll
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                         if (p.spikes_out != nullptr) {
                             for (int t = p.spk_t_lo; t < p.spk_t_hi; ++t)
                                 p.spikes_out[(static_cast<size_t>(t - p.spk_t_lo) * p.rows + r) * p.m_total + c] =
-                                    __ushort_as_bfloat16(((tr[u] >> t) & 1u) ? 0x3F80 : 0);
+                                    static_cast<uint16_t>(((tr[u] >> t) & 1u) ? p.spike_one : 0u);
                         }
                     }
                     // ---- fused LI readout: out[o][px] += sum_{c in this CTA} W[o][c] * sk[c][px]

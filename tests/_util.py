@@ -8,6 +8,7 @@ import torch
 from oracle import snn_oracle as O
 from snn_automotive_object_detection_b200 import _lib
 from snn_automotive_object_detection_b200.heads import _TRAIN_DTYPE, unpack_trains  # noqa: F401
+from tests._util_cpu import split_reconstruct  # noqa: F401
 
 
 def vp(t):
@@ -24,17 +25,6 @@ def prepared_fc(w, mode):
     buf = torch.empty(lib.snn_prepared_weight_bytes(O_, K, mode), dtype=torch.uint8, device=w.device)
     _lib.check(lib.snn_prepare_fc_weights(vp(w), O_, K, mode, vp(buf), stream()), "prepare_fc")
     return buf
-
-
-def split_reconstruct(w, pieces):
-    """fp32 value the tensor cores effectively see for `pieces` bf16 pieces (hi+mid+lo)."""
-    r = w.clone().float()
-    tot = torch.zeros_like(r)
-    for _ in range(pieces):
-        b = r.to(torch.bfloat16).float()
-        tot += b
-        r = r - b
-    return tot
 
 
 def spike_agreement(got_trains, ref_spk, ref_vdec, T, upstream_flip_rows=None, v_th=0.1, band=1e-5):

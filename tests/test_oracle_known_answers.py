@@ -128,3 +128,19 @@ def test_rate_variants_are_consistent_with_forward():
     assert torch.allclose(rates[0][:, 0], want, atol=1e-7)
     assert rates[0][0, 1].item() == 9 * 36 * 16 * 16
     assert rates[1][0, 1].item() == 36 * 16 * 3 * 4 and rates[2][0, 1].item() == 36 * 16 * 3   # swapped, as in the reference
+
+
+def test_two_fp16_pieces_of_the_row_scaled_weight_are_within_one_fp32_ulp():
+    # the split the fp16x2 mode feeds the tensor cores with (csrc/aux_kernels.cuh prep_weights_kernel)
+    from tests._util_cpu import split_reconstruct
+    g = torch.Generator().manual_seed(3)
+    for w in (torch.randn(64, 2304, generator=g) * 0.01,                       # rpn.py:78-82 init
+              (torch.rand(32, 12544, generator=g) * 2 - 1) / 12544 ** 0.5):    # nn.Linear default init (fc6)
+        eff = split_reconstruct(w, 2, fp16=True)
+        # one fp32 ulp of the weight, or (weights below 2^-16 of the row maximum, whose pieces reach the
+        # fp16 subnormals) 2^-39 of the row maximum -- far below the fp32 rounding of the row's sum
+        bound = torch.maximum(w.abs().double() * 2.0 ** -23, w.abs().amax(dim=1, keepdim=True).double() * 2.0 ** -39)
+        assert ((eff - w.double()).abs() <= bound).all()
+        assert (eff == w.double()).float().mean() > 0.4                          # about half are exact
+        eff3 = split_reconstruct(w, 3, fp16=False)
+        assert torch.equal(eff3, w.double())                                     # 3 bf16 pieces: exact
