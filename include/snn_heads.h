@@ -97,16 +97,20 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
                          unsigned int* spike_counts_out, void* workspace, size_t workspace_bytes,
                          snn_stream_t stream);
 
-/* ---- building block exposed for tests / profiling: one fully-connected spiking layer ------------------
- * z [T_live][R][K] bf16 {0,1} input spike planes injected at steps t0 .. t0+T_live-1; w_prep [pieces][M][K];
- * runs the LIF recurrence for steps 0..T-1 and writes trains [R][M]; optional bf16 planes
- * spikes_out [t_hi-t_lo][R][M] and raw currents dump [T_live][R][M] fp32.  cta_group 1 or 2 (0 = auto). */
-int snn_fc_lif_layer(const void* z, int R, int K, int M, int T, int t0, int T_live, int mode, const void* w_prep,
-                     void* trains, void* spikes_out, int t_lo, int t_hi, float* dump, int cta_group,
+/* ---- building blocks exposed for tests / profiling ---------------------------------------------------
+ * Spikes travel between kernels only as time-packed spike-train WORDS: one word per neuron, bit t = spike
+ * at step t, 1 / 2 / 4 bytes for up to 8 / 16 / 32 steps.
+ *
+ * encoder only: x [R][K] fp32 -> z_words [R][K], words of 1/2/4 bytes for T_live <= 8/16/32, bit t = z_t
+ * (Norse lif_current_encoder, faster_rcnn.py:494). */
+int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_words, snn_stream_t stream);
+/* one fully-connected spiking layer: z_words [R][K] input spike-train words of `in_word_bytes` bytes whose
+ * bit (in_bit0 + i) is the input spike injected at step t0 + i (i < T_live); w_prep [pieces][M][K] + scales;
+ * runs the LIF recurrence for steps 0..T-1 and writes trains [R][M] (words of snn_train_word_bytes(T));
+ * optional raw currents dump [T_live][R][M] fp32.  cta_group 1 or 2 (0 = auto). */
+int snn_fc_lif_layer(const void* z_words, int in_word_bytes, int in_bit0, int R, int K, int M, int T, int t0,
+                     int T_live, int mode, const void* w_prep, void* trains, float* dump, int cta_group,
                      snn_stream_t stream);
-/* encoder only: x [R][K] fp32 -> z [T_live][R][K] {0,1} in the 16-bit format of `mode` (bf16 or fp16)
- * (Norse lif_current_encoder, faster_rcnn.py:494) */
-int snn_encode_rows(const float* x, int R, int K, int T_live, int mode, void* z, snn_stream_t stream);
 
 /* number of kernels the last forward call on this thread enqueued (for bench accounting) */
 int snn_last_launch_count(void);

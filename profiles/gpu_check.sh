@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/${TAG}_gpu.txt
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
-tail -5 gpurun_out/${TAG}_pytest.log
+tail -40 gpurun_out/${TAG}_pytest.log
 for MODE in fp32_exact fp16x2 bf16 fp16; do
   timeout 600 python bench.py --mode $MODE --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench_${MODE}.json 2> gpurun_out/${TAG}_bench_${MODE}.err
   python - <<PY

@@ -86,21 +86,20 @@ constexpr int kEncMaxLevels = 8;
 
 struct EncLevel {
     const float* x;             // [N][C][H][W] fp32
-    uint16_t* z;                // [T_box][N][H][W][C] 16-bit {0,1} (bf16 or fp16 "one" pattern)
+    uint8_t* z;                 // [N][H][W][C] spike-train words of `wb` bytes (bit t = z_t, t < T_live)
     int H, W, wchunks, block_begin;
 };
 struct EncParams {
     EncLevel lv[kEncMaxLevels];
-    int n_levels, N, C, T_live, T_box, total_blocks;
-    uint32_t one;               // 16-bit pattern of 1.0: 0x3F80 (bf16) or 0x3C00 (fp16)
+    int n_levels, N, C, T_live, wb, total_blocks;
 };
 
 // All FPN levels in one launch.  One block = one (level, n, h, 32-pixel run):
 //   phase 1: coalesced 128-B reads along W (one channel per warp instruction), the encoder's T_live
 //            steps in registers, spike-train words transposed through shared memory;
-//   phase 2: each lane owns 8 consecutive channels of a pixel -> one 16-B store per plane, a warp
-//            writes the pixel's 512 contiguous bytes (C = 256) of each time plane.
-// Planes t >= T_live (tile padding) are written as zeros.
+//   phase 2: NHWC words out, 16 bytes per thread (16 / 8 / 4 channels for 1- / 2- / 4-byte words): a
+//            pixel's C words are contiguous, so the block writes one contiguous run of 32 * C words.
+// HBM traffic: 4 B read + wb B written per input neuron (the per-timestep planes never exist).
 __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant__ EncParams p) {
     extern __shared__ uint32_t s_tr[];            // [kEncW][C + 4]
     int lvl = 0;
@@ -126,31 +125,35 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
     }
     __syncthreads();
     const int npx = min(kEncW, W - w0);
-    const size_t plane = static_cast<size_t>(p.N) * H * W * C;
-    const int groups = C >> 3;                    // 8-channel groups per pixel
+    const int per16 = 16 / p.wb;                  // channels per 16-byte store
+    const int groups = C / per16;
+    uint8_t* dst0 = L.z + ((static_cast<size_t>(n) * H + h) * W + w0) * C * p.wb;
     for (int idx = threadIdx.x; idx < npx * groups; idx += blockDim.x) {
-        const int px = idx / groups, g8 = idx - px * groups;
-        const uint4 a = *reinterpret_cast<const uint4*>(&s_tr[px * ld + 8 * g8]);
-        const uint4 b = *reinterpret_cast<const uint4*>(&s_tr[px * ld + 8 * g8 + 4]);
-        uint16_t* dst = L.z + ((static_cast<size_t>(n) * H + h) * W + (w0 + px)) * C + 8 * g8;
-        const uint32_t lo1 = p.one, hi1 = p.one << 16;
-        for (int t = 0; t < p.T_box; ++t) {
-            uint4 o;
-            o.x = (((a.x >> t) & 1u) ? lo1 : 0u) | (((a.y >> t) & 1u) ? hi1 : 0u);
-            o.y = (((a.z >> t) & 1u) ? lo1 : 0u) | (((a.w >> t) & 1u) ? hi1 : 0u);
-            o.z = (((b.x >> t) & 1u) ? lo1 : 0u) | (((b.y >> t) & 1u) ? hi1 : 0u);
-            o.w = (((b.z >> t) & 1u) ? lo1 : 0u) | (((b.w >> t) & 1u) ? hi1 : 0u);
-            if (t >= p.T_live) o = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(dst + static_cast<size_t>(t) * plane) = o;
+        const int px = idx / groups, g = idx - px * groups;
+        const uint32_t* src = &s_tr[px * ld + g * per16];
+        uint4 o;
+        if (p.wb == 1) {
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint4 a = *reinterpret_cast<const uint4*>(src + 4 * k);
+                v[k] = (a.x & 0xFFu) | ((a.y & 0xFFu) << 8) | ((a.z & 0xFFu) << 16) | (a.w << 24);
+            }
+            o = make_uint4(v[0], v[1], v[2], v[3]);
+        } else if (p.wb == 2) {
+            const uint4 a = *reinterpret_cast<const uint4*>(src), b = *reinterpret_cast<const uint4*>(src + 4);
+            o = make_uint4((a.x & 0xFFFFu) | (a.y << 16), (a.z & 0xFFFFu) | (a.w << 16),
+                           (b.x & 0xFFFFu) | (b.y << 16), (b.z & 0xFFFFu) | (b.w << 16));
+        } else {
+            o = *reinterpret_cast<const uint4*>(src);
         }
+        *reinterpret_cast<uint4*>(dst0 + static_cast<size_t>(idx) * 16) = o;
     }
 }
 
-// x [R][K] fp32 -> Z [T_box][R][K] 16-bit {0,1}; 8 consecutive k per thread (2 x float4 in, 16 B out per step)
-__global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total8, size_t plane,
-                                                          int T_live, int T_box, uint32_t one,
-                                                          uint16_t* __restrict__ z) {
-    const uint32_t lo1 = one, hi1 = one << 16;
+// x [R][K] fp32 -> words [R][K] of `wb` bytes; 8 consecutive k per thread (2 x float4 in, 8 words out)
+__global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total8, int T_live,
+                                                          int wb, uint8_t* __restrict__ z) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
@@ -159,15 +162,17 @@ __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restric
         uint32_t tr[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) tr[q] = encode_train(xs[q], T_live);
-        for (int t = 0; t < T_box; ++t) {
-            uint4 o;
-            uint32_t wv[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                wv[q] = (((tr[2 * q] >> t) & 1u) ? lo1 : 0u) | (((tr[2 * q + 1] >> t) & 1u) ? hi1 : 0u);
-            o.x = wv[0]; o.y = wv[1]; o.z = wv[2]; o.w = wv[3];
-            if (t >= T_live) o = make_uint4(0, 0, 0, 0);
-            reinterpret_cast<uint4*>(z + static_cast<size_t>(t) * plane)[i] = o;
+        if (wb == 1) {
+            uint2 o;
+            o.x = tr[0] | (tr[1] << 8) | (tr[2] << 16) | (tr[3] << 24);
+            o.y = tr[4] | (tr[5] << 8) | (tr[6] << 16) | (tr[7] << 24);
+            reinterpret_cast<uint2*>(z)[i] = o;
+        } else if (wb == 2) {
+            reinterpret_cast<uint4*>(z)[i] =
+                make_uint4(tr[0] | (tr[1] << 16), tr[2] | (tr[3] << 16), tr[4] | (tr[5] << 16), tr[6] | (tr[7] << 16));
+        } else {
+            reinterpret_cast<uint4*>(z)[2 * i] = make_uint4(tr[0], tr[1], tr[2], tr[3]);
+            reinterpret_cast<uint4*>(z)[2 * i + 1] = make_uint4(tr[4], tr[5], tr[6], tr[7]);
         }
     }
 }

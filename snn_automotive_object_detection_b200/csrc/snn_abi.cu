@@ -23,15 +23,15 @@ thread_local int g_force_cg = 0;
 
 // Optional per-phase device timing (CUDA events recorded on the launch stream around each phase).
 enum Phase { PH_ENC_RPN = 0, PH_GEMM_RPN, PH_RO_RPN, PH_ENC_BOX, PH_GEMM_FC6, PH_GEMM_FC7, PH_RO_BOX, PH_COUNT };
-constexpr int kMaxPairs = 256;
-struct PhaseEvents { cudaEvent_t start[kMaxPairs], stop[kMaxPairs]; int created = 0, used = 0; };
+constexpr int kMaxTimed = 256;
+struct PhaseEvents { cudaEvent_t start[kMaxTimed], stop[kMaxTimed]; int created = 0, used = 0; };
 PhaseEvents g_ph[PH_COUNT];
 bool g_profile = false;
 
 void phase_begin(int ph, cudaStream_t st) {
     if (!g_profile) return;
     PhaseEvents& e = g_ph[ph];
-    if (e.used >= kMaxPairs) return;
+    if (e.used >= kMaxTimed) return;
     if (e.used >= e.created) {
         if (cudaEventCreate(&e.start[e.created]) != cudaSuccess || cudaEventCreate(&e.stop[e.created]) != cudaSuccess) return;
         ++e.created;
@@ -41,7 +41,7 @@ void phase_begin(int ph, cudaStream_t st) {
 void phase_end(int ph, cudaStream_t st) {
     if (!g_profile) return;
     PhaseEvents& e = g_ph[ph];
-    if (e.used >= kMaxPairs || e.used >= e.created) return;
+    if (e.used >= kMaxTimed || e.used >= e.created) return;
     cudaEventRecord(e.stop[e.used], st);
     ++e.used;
 }
@@ -95,14 +95,16 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// bf16 tensor, innermost dim contiguous, 128-byte swizzle, zero fill out of bounds
+// innermost dim contiguous, zero fill out of bounds.  words = false: 16-bit weight tensor, 128-byte swizzle
+// (tensor-core operand tiles); words = true: byte tensor of spike-train words, no swizzle (dense box).
 int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-              const cuuint32_t* box) {
+              const cuuint32_t* box, bool words = false) {
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) return fail(SNN_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims,
-                    strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = fn(m, words ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                    static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, words ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return fail(SNN_E_CUDA, "cuTensorMapEncodeTiled failed (%d), rank %d dims %llu %llu box %u %u", (int)r, rank,
@@ -135,8 +137,9 @@ struct TileCfg { int cg, T_box, J, Jh, TW, TH, TWh, THh, dw, dh, CW, n_mma; };
 // Fold time into the MMA N dimension: N = T_box * J <= 256, N % 16 == 0, J units per tile.
 bool pick_tile_cg(int T_live, bool conv, int cg, TileCfg& out) {
     const int step = conv ? 8 * cg : 4 * cg;
+    const int maxJ = (kMaxPairs * kProducerThreads / 8) * cg;     // producers: Jh * 8 pairs <= kMaxPairs * 128
     int bestJ = 0, bestT = 0;
-    for (int J = step; J <= 256; J += step)
+    for (int J = step; J <= maxJ; J += step)
         for (int Tb = T_live; Tb <= T_live + 1; ++Tb) {
             const int n = Tb * J;
             if (n > 256 || (n % 16) != 0 || n < 16) continue;
@@ -149,7 +152,7 @@ bool pick_tile_cg(int T_live, bool conv, int cg, TileCfg& out) {
     } else {
         out.TW = out.TH = out.TWh = out.THh = 0; out.dw = out.dh = 0;
     }
-    out.CW = (out.Jh % 16 == 0) ? 16 : (out.Jh % 8 == 0) ? 8 : 4;   // 32 would spill the LIF state
+    out.CW = (out.Jh % 8 == 0) ? 8 : 4;   // wider chunks do not fit the 384-thread register budget
     return true;
 }
 bool pick_tile(int T_live, bool conv, int m_total, int force_cg, TileCfg& out) {
@@ -169,17 +172,17 @@ cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kCG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-#define SNN_LAUNCH(CWV)                                                                                        \
+#define SNN_LAUNCH(CWV, CONV)                                                                                  \
     {                                                                                                          \
-        auto kern = spike_gemm_lif_kernel<kCG, CWV>;                                                           \
+        auto kern = spike_gemm_lif_kernel<kCG, CWV, CONV>;                                                     \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes); \
         if (e != cudaSuccess) return e;                                                                        \
         return cudaLaunchKernelEx(&cfg, kern, p);                                                              \
     }
-    switch (CW) {
-        case 16: SNN_LAUNCH(16)
-        case 8: SNN_LAUNCH(8)
-        default: SNN_LAUNCH(4)
+    if (p.conv) {
+        if (CW == 8) SNN_LAUNCH(8, true) else SNN_LAUNCH(4, true)
+    } else {
+        if (CW == 8) SNN_LAUNCH(8, false) else SNN_LAUNCH(4, false)
     }
 #undef SNN_LAUNCH
 }
@@ -189,6 +192,12 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
     p.sub_dw = tc.dw; p.sub_dh = tc.dh; p.T_box = tc.T_box; p.n_mma = tc.n_mma;
     p.idesc = umma_idesc_f16(128 * tc.cg, tc.n_mma, !is_fp16(mode));
     p.spike_one = one_of(mode);
+    p.slot_b = static_cast<int>(align_up(static_cast<size_t>(tc.n_mma / tc.cg) * 128, 1024));
+    p.stages_b = kRingBytesB / p.slot_b;
+    if (p.stages_b > kMaxStagesB) p.stages_b = kMaxStagesB;
+    p.slot_w = static_cast<int>(align_up(static_cast<size_t>(tc.Jh) * 64 * p.in_wb, 128));
+    p.stages_w = kRingBytesW / p.slot_w;
+    if (p.stages_w > kMaxStagesW) p.stages_w = kMaxStagesW;
     p.m_tiles = p.m_total / (128 * tc.cg);
     p.total_tiles = p.unit_tiles * p.m_tiles;
     if (p.total_tiles <= 0) return SNN_OK;
@@ -217,6 +226,8 @@ __global__ void build_lut_kernel(int T, int nbytes, float* lut) {
     lut[i] = static_cast<float>(s);
 }
 
+int word_bytes(int nbits) { return nbits <= 8 ? 1 : nbits <= 16 ? 2 : 4; }
+
 struct RpnWs { size_t z_off[kMaxLevels], tr_off[kMaxLevels], lut_off, total; };
 
 int rpn_ws_layout(const int* H, const int* W, int L, int N, int C, int T, int mode, RpnWs& ws, TileCfg& tc) {
@@ -233,7 +244,7 @@ int rpn_ws_layout(const int* H, const int* W, int L, int N, int C, int T, int mo
     for (int l = 0; l < L; ++l) {
         if (H[l] < 1 || W[l] < 1) return fail(SNN_E_ARG, "level %d has empty spatial size", l);
         ws.z_off[l] = off;
-        off = align_up(off + static_cast<size_t>(tc.T_box) * N * H[l] * W[l] * C * 2, 1024);
+        off = align_up(off + static_cast<size_t>(N) * H[l] * W[l] * C * word_bytes(T_live), 1024);   // encoder words
     }
     for (int l = 0; l < L; ++l) {
         ws.tr_off[l] = off;
@@ -245,7 +256,7 @@ int rpn_ws_layout(const int* H, const int* W, int L, int N, int C, int T, int mo
     return SNN_OK;
 }
 
-struct BoxWs { size_t z_off, s6_off, tr6_off, tr7_off, lut_off, total; };
+struct BoxWs { size_t z_off, tr6_off, tr7_off, lut_off, total; };
 
 int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, TileCfg& t6, TileCfg& t7) {
     if (T < 3 || T > 32) return fail(SNN_E_ARG, "num_steps %d outside [3,32]", T);
@@ -259,11 +270,9 @@ int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, 
         return fail(SNN_E_ARG, "no tile shape for T=%d", T);
     t6 = stats ? a : b;
     if (!pick_tile(T - 2, false, Hd, g_force_cg, t7)) return fail(SNN_E_ARG, "no tile shape for T=%d", T);
-    const int tbx = (a.T_box > b.T_box) ? a.T_box : b.T_box;
     const int tb = snn_train_word_bytes(T);
     size_t off = 0;
-    ws.z_off = off; off = align_up(off + static_cast<size_t>(tbx) * R * K * 2, 1024);
-    ws.s6_off = off; off = align_up(off + static_cast<size_t>(t7.T_box) * R * Hd * 2, 1024);
+    ws.z_off = off; off = align_up(off + static_cast<size_t>(R) * K * word_bytes(T - 1), 1024);   // encoder words
     ws.tr6_off = off; off = align_up(off + static_cast<size_t>(R) * Hd * tb, 1024);
     ws.tr7_off = off; off = align_up(off + static_cast<size_t>(R) * Hd * tb, 1024);
     ws.lut_off = off; off += kMaxTrainBytes * 256 * sizeof(float);
@@ -271,9 +280,8 @@ int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, 
     return SNN_OK;
 }
 
-int fc_layer(const DeviceInfo& di, const void* z, int R, int K, int M, int T, int t0, int T_live, int mode,
-             const void* w_prep, void* trains, void* spikes_out, int t_lo, int t_hi, float* dump, const TileCfg& tc,
-             cudaStream_t st) {
+int fc_layer(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, int R, int K, int M, int T, int t0,
+             int T_live, int mode, const void* w_prep, void* trains, float* dump, const TileCfg& tc, cudaStream_t st) {
     GemmLifParams p;
     memset(&p, 0, sizeof(p));
     const int nsplit = nsplit_of(mode);
@@ -285,20 +293,20 @@ int fc_layer(const DeviceInfo& di, const void* z, int R, int K, int M, int T, in
         int rc = make_tmap(&p.tmA, w_prep, 2, dims, str, box);
         if (rc) return rc;
     }
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)R, (cuuint64_t)tc.T_box};
-        cuuint64_t str[2] = {(cuuint64_t)K * 2, (cuuint64_t)R * K * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)tc.Jh, (cuuint32_t)tc.T_box};
-        int rc = make_tmap(&p.tmB[0], z, 3, dims, str, box);
-        if (rc) return rc;
-    }
     p.n_levels = 1; p.conv = 0; p.n_images = 1;
-    p.m_total = M; p.nsplit = nsplit; p.kblocks = K / 64; p.cblocks = 1;
+    p.m_total = M; p.nsplit = nsplit; p.kblocks = K / 64; p.cblocks = 1; p.k_in = K;
     p.T_total = T; p.t0 = t0; p.T_live = T_live;
     p.rows = R; p.unit_tiles = (R + tc.J - 1) / tc.J;
     p.train_bytes = snn_train_word_bytes(T);
+    p.in_wb = in_wb; p.in_bit0 = in_bit0;
+    {   // input words [R][K] as a byte tensor
+        cuuint64_t dims[2] = {(cuuint64_t)K * in_wb, (cuuint64_t)R};
+        cuuint64_t str[1] = {(cuuint64_t)K * in_wb};
+        cuuint32_t box[2] = {(cuuint32_t)(64 * in_wb), (cuuint32_t)tc.Jh};
+        int rc = make_tmap(&p.tmW[0], z_words, 2, dims, str, box, true);
+        if (rc) return rc;
+    }
     p.trains = trains;
-    p.spikes_out = reinterpret_cast<uint16_t*>(spikes_out); p.spk_t_lo = t_lo; p.spk_t_hi = t_hi;
     p.dump = dump;
     return launch_gemm(p, tc, di, mode, st);
 }
@@ -413,7 +421,7 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
     }
 
     if (T_live > 0) {
-        // 1) encoder: fp32 NCHW features -> bf16 {0,1} NHWC spike planes
+        // 1) encoder: fp32 NCHW features -> NHWC spike-train words (bit t = z_t)
         phase_begin(PH_ENC_RPN, st);
         {
             EncParams ep;
@@ -422,12 +430,11 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
             for (int l = 0; l < n_levels; ++l) {
                 EncLevel& E = ep.lv[l];
                 E.x = reinterpret_cast<const float*>(feat_ptrs[l]);
-                E.z = reinterpret_cast<uint16_t*>(wsp + ws.z_off[l]);
+                E.z = wsp + ws.z_off[l];
                 E.H = H[l]; E.W = W[l]; E.wchunks = (W[l] + kEncW - 1) / kEncW; E.block_begin = blocks;
                 blocks += N * H[l] * E.wchunks;
             }
-            ep.n_levels = n_levels; ep.N = N; ep.C = C_in; ep.T_live = T_live; ep.T_box = tc.T_box; ep.total_blocks = blocks;
-            ep.one = one_of(mode);
+            ep.n_levels = n_levels; ep.N = N; ep.C = C_in; ep.T_live = T_live; ep.wb = word_bytes(T_live); ep.total_blocks = blocks;
             const size_t smem = static_cast<size_t>(kEncW) * (C_in + 4) * 4;
             if (smem > 48 * 1024)
                 CUDA_TRY(cudaFuncSetAttribute(encode_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -447,16 +454,18 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
         }
         int tiles = 0;
         for (int l = 0; l < n_levels; ++l) {
-            cuuint64_t dims[5] = {(cuuint64_t)C_in, (cuuint64_t)W[l], (cuuint64_t)H[l], (cuuint64_t)N, (cuuint64_t)tc.T_box};
-            cuuint64_t str[4] = {(cuuint64_t)C_in * 2, (cuuint64_t)W[l] * C_in * 2, (cuuint64_t)H[l] * W[l] * C_in * 2,
-                                 (cuuint64_t)N * H[l] * W[l] * C_in * 2};
-            cuuint32_t box[5] = {64, (cuuint32_t)tc.TWh, (cuuint32_t)tc.THh, 1, (cuuint32_t)tc.T_box};
-            rc = make_tmap(&p.tmB[l], wsp + ws.z_off[l], 5, dims, str, box);
-            if (rc) return rc;
             LevelDesc& L = p.lv[l];
             L.H = H[l]; L.W = W[l];
             L.tiles_w = (W[l] + tc.TW - 1) / tc.TW; L.tiles_h = (H[l] + tc.TH - 1) / tc.TH;
             L.tile_begin = tiles; L.trains = trains[l];
+            {   // encoder words [N][H][W][C] as a byte tensor; one box = (64 words, TWh, THh) of one image
+                const cuuint64_t wbz = (cuuint64_t)word_bytes(T_live);
+                cuuint64_t dims[4] = {(cuuint64_t)C_in * wbz, (cuuint64_t)W[l], (cuuint64_t)H[l], (cuuint64_t)N};
+                cuuint64_t str[3] = {(cuuint64_t)C_in * wbz, (cuuint64_t)W[l] * C_in * wbz, (cuuint64_t)H[l] * W[l] * C_in * wbz};
+                cuuint32_t box[4] = {(cuuint32_t)(64 * wbz), (cuuint32_t)tc.TWh, (cuuint32_t)tc.THh, 1};
+                rc = make_tmap(&p.tmW[l], wsp + ws.z_off[l], 4, dims, str, box, true);
+                if (rc) return rc;
+            }
             L.logits = reinterpret_cast<float*>(logits_out[l]); L.bbox = reinterpret_cast<float*>(bbox_out[l]);
             L.counts = spike_counts_out ? spike_counts_out + static_cast<size_t>(l) * N : nullptr;
             tiles += L.tiles_w * L.tiles_h * N;
@@ -475,7 +484,8 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
         for (int t = 0; t < 32; ++t)
             p.kappa[t] = (t < T) ? static_cast<float>(pow(0.9, T - t) - pow(0.8, T - t)) : 0.f;
         p.n_levels = n_levels; p.conv = 1; p.n_images = N;
-        p.m_total = C_in; p.nsplit = ns; p.cblocks = C_in / 64; p.kblocks = 9 * p.cblocks;
+        p.m_total = C_in; p.nsplit = ns; p.cblocks = C_in / 64; p.kblocks = 9 * p.cblocks; p.k_in = C_in;
+        p.in_wb = word_bytes(T_live); p.in_bit0 = 0;
         p.T_total = T; p.t0 = 0; p.T_live = T_live;
         p.rows = 0; p.unit_tiles = tiles; p.train_bytes = tb;
         p.w_scale = scale_of(w_shared_prep, C_in, 9 * C_in, mode);
@@ -539,7 +549,6 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
     void* tr6 = spk6_trains ? spk6_trains : (wsp + ws.tr6_off);
     void* tr7 = spk7_trains ? spk7_trains : (wsp + ws.tr7_off);
     void* z = wsp + ws.z_off;
-    void* s6 = wsp + ws.s6_off;
 
     build_lut_kernel<<<(tb * 256 + 255) / 256, 256, 0, st>>>(T, tb, lut);
     CUDA_TRY(cudaGetLastError()); ++g_launches;
@@ -552,17 +561,18 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
         const size_t total8 = static_cast<size_t>(R) * K / 8;
         const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
         phase_begin(PH_ENC_BOX, st);
-        encode_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), total8, static_cast<size_t>(R) * K,
-                                                   T_live6, t6.T_box, one_of(mode), reinterpret_cast<uint16_t*>(z));
+        encode_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), total8, T_live6, word_bytes(T - 1),
+                                                   reinterpret_cast<uint8_t*>(z));
         phase_end(PH_ENC_BOX, st);
         CUDA_TRY(cudaGetLastError()); ++g_launches;
     }
     phase_begin(PH_GEMM_FC6, st);
-    rc = fc_layer(di, z, R, K, Hdim, T, 0, T_live6, mode, w6_prep, tr6, s6, 1, 1 + t7.T_box, nullptr, t6, st);
+    rc = fc_layer(di, z, word_bytes(T - 1), 0, R, K, Hdim, T, 0, T_live6, mode, w6_prep, tr6, nullptr, t6, st);
     phase_end(PH_GEMM_FC6, st);
     if (rc) return rc;
     phase_begin(PH_GEMM_FC7, st);
-    rc = fc_layer(di, s6, R, Hdim, Hdim, T, 1, T_live7, mode, w7_prep, tr7, nullptr, 0, 0, nullptr, t7, st);
+    // fc7 contracts lif6's spike-train words directly: its step t0 = 1 is bit 1 of the word
+    rc = fc_layer(di, tr6, tb, 1, R, Hdim, Hdim, T, 1, T_live7, mode, w7_prep, tr7, nullptr, t7, st);
     phase_end(PH_GEMM_FC7, st);
     if (rc) return rc;
     phase_begin(PH_RO_BOX, st);
@@ -599,33 +609,35 @@ int snn_profile_read(float* ms_out, int* counts_out) {
     return SNN_OK;
 }
 
-int snn_encode_rows(const float* x, int R, int K, int T_live, int mode, void* z, snn_stream_t stream) {
-    if (!x || !z || R < 1 || K % 8 != 0 || T_live < 1 || T_live > 32 || nsplit_of(mode) == 0)
+int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_words, snn_stream_t stream) {
+    if (!x || !z_words || R < 1 || K % 8 != 0 || T_live < 1 || T_live > 32)
         return fail(SNN_E_ARG, "encode_rows: bad argument");
     const size_t total8 = static_cast<size_t>(R) * K / 8;
     const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
-    encode_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, total8, static_cast<size_t>(R) * K, T_live, T_live,
-                                                                 one_of(mode), reinterpret_cast<uint16_t*>(z));
+    encode_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, total8, T_live, word_bytes(T_live),
+                                                                 reinterpret_cast<uint8_t*>(z_words));
     CUDA_TRY(cudaGetLastError());
     return SNN_OK;
 }
 
-int snn_fc_lif_layer(const void* z, int R, int K, int M, int T, int t0, int T_live, int mode, const void* w_prep,
-                     void* trains, void* spikes_out, int t_lo, int t_hi, float* dump, int cta_group,
+int snn_fc_lif_layer(const void* z_words, int in_word_bytes, int in_bit0, int R, int K, int M, int T, int t0,
+                     int T_live, int mode, const void* w_prep, void* trains, float* dump, int cta_group,
                      snn_stream_t stream) {
     g_launches = 0;
-    if (!z || !w_prep || !trains) return fail(SNN_E_ARG, "fc_lif_layer: null argument");
+    if (!z_words || !w_prep || !trains) return fail(SNN_E_ARG, "fc_lif_layer: null argument");
     if (K % 64 != 0 || M % 128 != 0 || R < 1 || T < 1 || T > 32 || T_live < 1 || t0 < 0 || t0 + T_live > T)
         return fail(SNN_E_ARG, "fc_lif_layer: unsupported shape R=%d K=%d M=%d T=%d t0=%d T_live=%d", R, K, M, T, t0, T_live);
-    const int ns = nsplit_of(mode);
-    if (ns == 0) return fail(SNN_E_ARG, "unknown mode %d", mode);
+    if ((in_word_bytes != 1 && in_word_bytes != 2 && in_word_bytes != 4) || in_bit0 < 0 ||
+        in_bit0 + T_live > 8 * in_word_bytes)
+        return fail(SNN_E_ARG, "fc_lif_layer: %d steps from bit %d do not fit %d-byte words", T_live, in_bit0, in_word_bytes);
+    if (nsplit_of(mode) == 0) return fail(SNN_E_ARG, "unknown mode %d", mode);
     DeviceInfo di;
     int rc = device_info(di);
     if (rc) return rc;
     TileCfg tc;
     if (!pick_tile(T_live, false, M, cta_group, tc)) return fail(SNN_E_ARG, "no tile shape for T_live=%d cta_group=%d", T_live, cta_group);
-    if (tc.T_box != T_live) return fail(SNN_E_ARG, "fc_lif_layer needs T_live with an unpadded tile (got T_box %d)", tc.T_box);
-    return fc_layer(di, z, R, K, M, T, t0, T_live, mode, w_prep, trains, spikes_out, t_lo, t_hi, dump, tc, (cudaStream_t)stream);
+    return fc_layer(di, z_words, in_word_bytes, in_bit0, R, K, M, T, t0, T_live, mode, w_prep, trains, dump, tc,
+                    (cudaStream_t)stream);
 }
 
 }  // extern "C"

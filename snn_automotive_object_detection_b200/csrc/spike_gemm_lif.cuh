@@ -8,23 +8,28 @@
 //   D[c, (t, u)] = sum_k  Wsplit[c, k] * Z[t, u, k]         (tcgen05.mma, bf16|fp16 x {0,1} -> fp32 in TMEM)
 //   for every neuron (u, c):  run the LIF recurrence over t in registers, emit its spike train
 //
-//  * A operand  = weights [M rows = output channels][K] bf16, K-major, TMA 2-D tiles 128 x 64.
+//  * A operand  = weights [M rows = output channels][K] 16-bit, K-major, TMA 2-D tiles 128 x 64.
 //    "fp32-exact" mode keeps 2 or 3 bf16 pieces of every weight (hi/mid/lo); because the other
 //    operand is exactly {0,1} every product is exact and the pieces are simply extra k-steps.
 //    fp16 modes keep 1 or 2 fp16 pieces of the power-of-two row-scaled weight (11 bits each) and
 //    the epilogue multiplies the accumulator row by the inverse scale (exact).
-//  * B operand  = input spikes, rows ordered (t, unit) so that ALL timesteps of a unit sit in
-//    the same accumulator tile (time folded into the MMA N dimension, N = T_box * J <= 256):
-//      fc   : 3-D tensor map  [T][R][K]          box (64, Jh, T_box)
-//      conv : 5-D tensor map  [T][N][H][W][C]    box (64, TWh, THh, 1, T_box), one box per
-//             (tap, 64-channel block); the 3x3 halo and image border are TMA out-of-bounds zero fill.
+//  * B operand  = input spikes.  They live in HBM ONLY as time-packed spike-train words (one word
+//    per input neuron, bit t = spike at step t: the encoder's output, or the previous layer's
+//    epilogue output) -- 1-2 bytes per neuron instead of one 16-bit plane per timestep.  Four
+//    producer warps expand the words of a k-block into the 128-byte-swizzled K-major tile the
+//    tensor core reads (rows ordered (t, unit): ALL timesteps of a unit sit in the same
+//    accumulator tile, time folded into the MMA N dimension, N = T_box * J <= 256):
+//      fc   : words [R][K]            TMA box (64 words, Jh rows)
+//      conv : words [N][H][W][C]      TMA box (64 words, TWh, THh, 1) per (tap, 64-channel block) at the
+//             shifted pixel; the 3x3 halo and the image border are TMA out-of-bounds zero fill.
+//    The word tile of a k-block is 1-2 KB per CTA (vs 14-16 KB for expanded planes), so the
+//    L2->SM feed of the kernel is essentially the weight tiles alone.
 //  * accumulators: 2 x 256 TMEM columns (double buffered) -> the MMA of tile i+1 overlaps the
 //    LIF epilogue of tile i.  The LIF state (v, i) never leaves registers; nothing of size
 //    T x state is ever written to HBM.  Output per neuron: one time-packed spike-train word
-//    (bit t = spike at step t; popc = spike count) and, optionally, bf16 {0,1} planes that feed
-//    the next layer's contraction.
+//    (bit t = spike at step t; popc = spike count), which is also the next layer's B operand.
 //  * kCG = 2 pairs two SMs (cta_group::2, UMMA M = 256): each CTA owns 128 output channels and
-//    loads half of the unit tile, halving B traffic per SM.
+//    produces half of the unit tile.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -34,16 +39,20 @@ namespace snn {
 
 constexpr int kMaxLevels = 8;
 constexpr int kStagesA = 6;                 // 16 KB each
-constexpr int kStagesB = 3;                 // up to 32 KB each
-constexpr int kTileBytesA = 128 * 128;      // 128 rows x 64 bf16
-constexpr int kSlotBytesB = 256 * 128;      // up to 256 rows x 64 bf16
-constexpr int kGemmThreads = 256;
+constexpr int kMaxStagesB = 6;              // ring of p.stages_b slots of p.slot_b bytes, 80 KB in total
+constexpr int kMaxStagesW = 8;              // ring of p.stages_w slots of p.slot_w bytes, 16 KB in total
+constexpr int kTileBytesA = 128 * 128;      // 128 rows x 64 16-bit
+constexpr int kRingBytesB = 80 * 1024;
+constexpr int kRingBytesW = 16 * 1024;
+constexpr int kBarBytes = 512;
+constexpr int kGemmThreads = 512;           // warps 0-3 control, 4-7 LIF epilogue, 8-15 spike-tile producers (2 groups)
+constexpr int kProducerThreads = 128;       // per producer group
+constexpr int kMaxPairs = 2;                // (unit, 8-channel chunk) pairs a producer thread expands per k-block
 constexpr int kRoMaxOut = 16;               // fused readout: objectness + box deltas per pixel (5 * A <= 16)
 constexpr int kRoWStride = 132;             // floats per readout-weight row in smem (128 + pad, 16-B aligned)
-constexpr int kRoSStride = 20;              // floats per channel row of the kappa-weighted spike sums (16 + pad)
-constexpr int kRoSmemBytes = kRoMaxOut * kRoWStride * 4 + 2 * 128 * kRoSStride * 4;
+constexpr int kRoSmemBytes = kRoMaxOut * kRoWStride * 4 + 2 * 8 * kRoWStride * 4;   // weights + 2 x [8 px][128 ch] sums
 constexpr size_t kGemmSmemBytes =
-    1024 /*align slack*/ + kStagesA * kTileBytesA + kStagesB * kSlotBytesB + 256 + kRoSmemBytes;
+    1024 /*align slack*/ + kStagesA * kTileBytesA + kRingBytesB + kRingBytesW + kBarBytes + kRoSmemBytes;
 
 struct LevelDesc {
     int H, W, tiles_w, tiles_h;
@@ -57,21 +66,23 @@ struct LevelDesc {
 
 struct GemmLifParams {
     CUtensorMap tmA;
-    CUtensorMap tmB[kMaxLevels];
+    CUtensorMap tmW[kMaxLevels];   // input spike-train words as byte tensors: conv [N][H][W][k_in*in_wb], fc [rows][k_in*in_wb]
     LevelDesc lv[kMaxLevels];
     int n_levels, conv, n_images;
     int m_total, m_tiles, nsplit;
     int kblocks, cblocks;
+    int k_in;                 // input neurons per unit (conv: channels; fc: K)
     int T_total, t0, T_live, T_box;
     int J, Jh, TWh, THh, TW, TH, sub_dw, sub_dh;
     int rows;                 // fc: number of units (RoIs)
     int total_tiles, unit_tiles;
-    int train_bytes;          // 1, 2 or 4
+    int train_bytes;          // output word size: 1, 2 or 4
+    int in_wb, in_bit0;       // input word size; bit of the input word that is step t0 of this layer
+    int stages_b, slot_b;     // B ring geometry
+    int stages_w, slot_w;     // word ring geometry (slot = Jh units x 64 words)
     int n_mma;                // T_box * J
     uint32_t idesc;
     void* trains;             // fc: [rows][m_total]
-    uint16_t* spikes_out;     // optional: [spk_t_hi - spk_t_lo][rows][m_total] 16-bit {0,1} (pattern spike_one)
-    int spk_t_lo, spk_t_hi;
     uint32_t spike_one;       // 1.0 as bf16 (0x3F80) or fp16 (0x3C00)
     const float* w_scale;     // [m_total] power of two each accumulator row is multiplied with (1 for bf16 pieces)
     float* dump;              // debug (fc only): raw currents [T_live][rows][m_total]
@@ -85,46 +96,72 @@ struct GemmLifParams {
 // One LIF step of Norse's lif_feed_forward_step, op for op (no FMA contraction):
 //   v_dec = v + 0.1f*((0 - v) + i);  i_dec = i + (-0.2f)*i;  z = (v_dec - 0.1f > 0);
 //   v' = (1-z)*v_dec + z*0;  i' = i_dec + cur
-__device__ __forceinline__ uint32_t lif_update(float& v, float& i, float cur) {
+__device__ __forceinline__ bool lif_update(float& v, float& i, float cur) {
     const float dv = __fmul_rn(0.1f, __fsub_rn(i, v));
     const float v_dec = __fadd_rn(v, dv);
     const float i_dec = __fadd_rn(i, __fmul_rn(-0.2f, i));
     const bool z = __fsub_rn(v_dec, 0.1f) > 0.0f;
     v = z ? 0.0f : v_dec;
     i = __fadd_rn(i_dec, cur);
-    return z ? 1u : 0u;
+    return z;
 }
 
-template <int kCG, int CW>
+// Decoded position of a unit tile.
+struct TilePos { int lvl, n, h0, w0; };
+
+__device__ __forceinline__ TilePos decode_tile(const GemmLifParams& p, int ut) {
+    TilePos tp{0, 0, 0, 0};
+    if (p.conv) {
+        while (tp.lvl + 1 < p.n_levels && ut >= p.lv[tp.lvl + 1].tile_begin) ++tp.lvl;
+        const LevelDesc& L = p.lv[tp.lvl];
+        int local = ut - L.tile_begin;
+        const int per_img = L.tiles_w * L.tiles_h;
+        tp.n = local / per_img; local -= tp.n * per_img;
+        const int ty = local / L.tiles_w;
+        tp.h0 = ty * p.TH; tp.w0 = (local - ty * L.tiles_w) * p.TW;
+    }
+    return tp;
+}
+
+// Raw spike-train words of 8 consecutive input neurons (8, 16 or 32 bytes).
+struct RawWords { uint4 a, b; };
+
+template <int kCG, int CW, bool kConv>
 __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const __grid_constant__ GemmLifParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + kStagesA * kTileBytesA;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + kStagesB * kSlotBytesB);
-    uint64_t* a_full = bars;                         // [kStagesA]
-    uint64_t* a_empty = a_full + kStagesA;           // [kStagesA]
-    uint64_t* b_full = a_empty + kStagesA;           // [kStagesB]
-    uint64_t* b_empty = b_full + kStagesB;           // [kStagesB]
-    uint64_t* acc_full = b_empty + kStagesB;         // [2]
+    uint8_t* w_ring = b_ring + kRingBytesB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + kRingBytesW);
+    uint64_t* a_full = bars;                         // [kStagesA]   weight tile landed (TMA tx, leader CTA)
+    uint64_t* a_empty = a_full + kStagesA;           // [kStagesA]   MMAs reading it retired
+    uint64_t* b_ready = a_empty + kStagesA;          // [kMaxStagesB] this CTA's half of the spike tile written
+    uint64_t* b_peer = b_ready + kMaxStagesB;        // [kMaxStagesB] leader only: the peer CTA's half written
+    uint64_t* b_empty = b_peer + kMaxStagesB;        // [kMaxStagesB] MMAs reading the spike tile retired
+    uint64_t* w_full = b_empty + kMaxStagesB;        // [kMaxStagesW] input words landed (TMA tx)
+    uint64_t* w_empty = w_full + kMaxStagesW;        // [kMaxStagesW] producers have read them
+    uint64_t* acc_full = w_empty + kMaxStagesW;      // [2]
     uint64_t* acc_empty = acc_full + 2;              // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* ro_w = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);     // [kRoMaxOut][kRoWStride]
-    float* ro_s = ro_w + kRoMaxOut * kRoWStride;                                          // [2][128][kRoSStride]
+    float* ro_w = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);   // [kRoMaxOut][kRoWStride]
+    float* ro_s = ro_w + kRoMaxOut * kRoWStride;                                              // [2][CW][kRoWStride]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = (kCG == 2) ? cluster_ctarank() : 0u;
     const int n_groups = gridDim.x / kCG;
     const int group = blockIdx.x / kCG;
+    const int stages_b = p.stages_b;
+    const int stages_w = p.stages_w;
 
-    if (warp == 0 && elect_one()) {
-        tma_prefetch_desc(&p.tmA);
-        for (int l = 0; l < p.n_levels; ++l) tma_prefetch_desc(&p.tmB[l]);
-    }
+    if (warp == 0 && elect_one()) tma_prefetch_desc(&p.tmA);
+    if (warp == 3 && elect_one())
+        for (int l = 0; l < p.n_levels; ++l) tma_prefetch_desc(&p.tmW[l]);
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < kStagesA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < kStagesB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < kMaxStagesB; ++s) { mbar_init(&b_ready[s], 4); mbar_init(&b_peer[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < kMaxStagesW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 4); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * kCG); }
         fence_barrier_init();
     }
@@ -134,46 +171,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int n_half = p.n_mma / kCG;                 // B rows (= accumulator columns) loaded per CTA
-    const uint32_t b_bytes = static_cast<uint32_t>(p.n_mma) * 128u;   // per k-block, both CTAs together
+    const int n_half = p.n_mma / kCG;                 // B rows (= accumulator columns) produced per CTA
 
     if (warp == 0) {
-        // ===================================================== TMA producer
+        // ===================================================== TMA producer (weight tiles)
         if (elect_one()) {
-            uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+            uint32_t sa = 0, pa = 0;
             for (int tile = group; tile < p.total_tiles; tile += n_groups) {
                 const int ut = tile / p.m_tiles, mt = tile - ut * p.m_tiles;
                 const int m0 = mt * 128 * kCG + static_cast<int>(rank) * 128;
-                int lvl = 0, n = 0, h0 = 0, w0 = 0;
-                if (p.conv) {
-                    while (lvl + 1 < p.n_levels && ut >= p.lv[lvl + 1].tile_begin) ++lvl;
-                    const LevelDesc& L = p.lv[lvl];
-                    int local = ut - L.tile_begin;
-                    const int per_img = L.tiles_w * L.tiles_h;
-                    n = local / per_img; local -= n * per_img;
-                    const int ty = local / L.tiles_w;
-                    h0 = ty * p.TH + static_cast<int>(rank) * p.sub_dh;
-                    w0 = (local - ty * L.tiles_w) * p.TW + static_cast<int>(rank) * p.sub_dw;
-                }
-                const int r0 = ut * p.J + static_cast<int>(rank) * p.Jh;
                 for (int kb = 0; kb < p.kblocks; ++kb) {
-                    mbar_wait(&b_empty[sb], pb ^ 1u);
-                    if (rank == 0) mbar_expect_tx(&b_full[sb], b_bytes);
-                    uint8_t* bdst = b_ring + sb * kSlotBytesB;
-                    if (p.conv) {
-                        const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-                        const int dy = tap / 3, dx = tap - dy * 3;
-                        if constexpr (kCG == 1)
-                            tma_load_5d(bdst, &p.tmB[lvl], &b_full[sb], cb * 64, w0 + dx - 1, h0 + dy - 1, n, 0);
-                        else
-                            tma_load_5d_2sm(bdst, &p.tmB[lvl], &b_full[sb], cb * 64, w0 + dx - 1, h0 + dy - 1, n, 0);
-                    } else {
-                        if constexpr (kCG == 1) tma_load_3d(bdst, &p.tmB[0], &b_full[sb], kb * 64, r0, 0);
-                        else tma_load_3d_2sm(bdst, &p.tmB[0], &b_full[sb], kb * 64, r0, 0);
-                    }
-                    if (++sb == kStagesB) { sb = 0; pb ^= 1u; }
                     for (int s = 0; s < p.nsplit; ++s) {
-                        mbar_wait(&a_empty[sa], pa ^ 1u);
+                        mbar_wait_parked(&a_empty[sa], pa ^ 1u);
                         if (rank == 0) mbar_expect_tx(&a_full[sa], kTileBytesA * kCG);
                         uint8_t* adst = a_ring + sa * kTileBytesA;
                         if constexpr (kCG == 1) tma_load_2d(adst, &p.tmA, &a_full[sa], kb * 64, s * p.m_total + m0);
@@ -193,27 +202,162 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 256u;
                 for (int kb = 0; kb < p.kblocks; ++kb) {
-                    mbar_wait(&b_full[sb], pb);
+                    mbar_wait(&b_ready[sb], pb);
+                    if constexpr (kCG == 2) mbar_wait_cluster(&b_peer[sb], pb);
                     tcgen05_fence_after();
-                    const uint64_t b_desc = umma_desc_sw128(smem_u32(b_ring + sb * kSlotBytesB));
+                    const uint64_t b_desc = umma_desc_sw128(smem_u32(b_ring + sb * p.slot_b));
                     for (int s = 0; s < p.nsplit; ++s) {
                         mbar_wait(&a_full[sa], pa);
                         tcgen05_fence_after();
                         const uint64_t a_desc = umma_desc_sw128(smem_u32(a_ring + sa * kTileBytesA));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)     // 4 x (K = 16 bf16 = 32 B) inside the 128-B swizzle span
+                        for (int k = 0; k < 4; ++k)     // 4 x (K = 16 x 16-bit = 32 B) inside the 128-B swizzle span
                             umma_f16<kCG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, p.idesc,
-                                           (kb | s | k) != 0 ? 1u : 0u);
+                                          (kb | s | k) != 0 ? 1u : 0u);
                         if constexpr (kCG == 1) umma_commit<1>(&a_empty[sa]);
                         else umma_commit_2sm_mcast(&a_empty[sa], 0b11);
                         if (++sa == kStagesA) { sa = 0; pa ^= 1u; }
                     }
                     if constexpr (kCG == 1) umma_commit<1>(&b_empty[sb]);
                     else umma_commit_2sm_mcast(&b_empty[sb], 0b11);
-                    if (++sb == kStagesB) { sb = 0; pb ^= 1u; }
+                    if (++sb == static_cast<uint32_t>(stages_b)) { sb = 0; pb ^= 1u; }
                 }
                 if constexpr (kCG == 1) umma_commit<1>(&acc_full[buf]);
                 else umma_commit_2sm_mcast(&acc_full[buf], 0b11);
+            }
+        } else if (kCG == 2 && rank == 1 && lane < stages_b) {
+            // relay (one lane per spike-tile ring stage): tell the leader's MMA thread that this CTA's half
+            // of the stage is written.  The cluster-scope release costs about a microsecond; one lane per
+            // stage keeps stages_b of them in flight, and none of them sits in a producer warp.
+            const int my_tiles = (group < p.total_tiles) ? (p.total_tiles - group + n_groups - 1) / n_groups : 0;
+            const long long total_kb = static_cast<long long>(my_tiles) * p.kblocks;
+            uint32_t pb = 0;
+            for (long long i = lane; i < total_kb; i += stages_b, pb ^= 1u) {
+                mbar_wait_parked(&b_ready[lane], pb);
+                mbar_arrive_cluster(&b_peer[lane], 0);
+            }
+        }
+    } else if (warp == 3) {
+        // ===================================================== TMA producer (input spike-train words)
+        if (elect_one()) {
+            uint32_t sw = 0, pw = 0;
+            const uint32_t w_bytes = static_cast<uint32_t>(p.Jh) * 64u * static_cast<uint32_t>(p.in_wb);
+            for (int tile = group; tile < p.total_tiles; tile += n_groups) {
+                const int ut = tile / p.m_tiles;
+                const TilePos tp = decode_tile(p, ut);
+                const int h0 = tp.h0 + static_cast<int>(rank) * p.sub_dh, w0 = tp.w0 + static_cast<int>(rank) * p.sub_dw;
+                const int r0 = ut * p.J + static_cast<int>(rank) * p.Jh;
+                int tap = 0, cb = 0;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait_parked(&w_empty[sw], pw ^ 1u);
+                    mbar_expect_tx(&w_full[sw], w_bytes);
+                    uint8_t* wdst = w_ring + sw * p.slot_w;
+                    if (p.conv) {
+                        const int dy = tap / 3, dx = tap - dy * 3;
+                        tma_load_4d(wdst, &p.tmW[tp.lvl], &w_full[sw], cb * 64 * p.in_wb, w0 + dx - 1, h0 + dy - 1, tp.n);
+                        if (++cb == p.cblocks) { cb = 0; ++tap; }
+                    } else {
+                        tma_load_2d(wdst, &p.tmW[0], &w_full[sw], kb * 64 * p.in_wb, r0);
+                    }
+                    if (++sw == static_cast<uint32_t>(stages_w)) { sw = 0; pw ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ============================== spike-tile producers (2 groups x 4 warps): words -> swizzled {0,1} tile
+        // The k-blocks of this CTA's tile sequence are numbered i = 0, 1, 2, ...; producer group g expands
+        // the k-blocks i = g (mod 2): word-ring stage i % stages_w -> spike-tile ring stage i % stages_b.
+        // A thread owns up to kMaxPairs (unit j, 16-byte chunk q) pairs of the CTA's half tile; per k-block
+        // it reads the pair's 8 input words and writes T_box 16-byte chunks: row r = t * Jh + j,
+        // chunk q ^ (r & 7) -- the 128-byte swizzle TMA would have produced for a K-major bf16 tile.
+        const int grp = (warp - 8) >> 2;
+        const int pt = static_cast<int>(threadIdx.x) - 256 - grp * kProducerThreads;
+        const int n_pairs = p.Jh * 8;
+        const int wb = p.in_wb;
+        const uint32_t tmask = (p.T_live >= 32) ? 0xFFFFFFFFu : ((1u << p.T_live) - 1u);
+        const uint32_t pmask = tmask | (tmask << 16);
+        const uint32_t one = p.spike_one;
+        const bool packed = p.T_box <= 16;             // both neurons of a 32-bit output fit one register
+        const int my_tiles = (group < p.total_tiles) ? (p.total_tiles - group + n_groups - 1) / n_groups : 0;
+        const long long total_kb = static_cast<long long>(my_tiles) * p.kblocks;
+        const uint32_t b_base = smem_u32(b_ring), w_base = smem_u32(w_ring);
+        const uint32_t row_step = static_cast<uint32_t>(p.Jh) * 128u;
+
+        uint32_t sb = static_cast<uint32_t>(grp % stages_b), pb = static_cast<uint32_t>((grp / stages_b) & 1);
+        uint32_t sw = static_cast<uint32_t>(grp % stages_w), pw = static_cast<uint32_t>((grp / stages_w) & 1);
+        for (long long i_kb = grp; i_kb < total_kb; i_kb += 2) {
+            // ---- the pair's 8 input words from the word ring
+            mbar_wait_parked(&w_full[sw], pw);
+            const uint32_t wslot = w_base + sw * p.slot_w;
+            RawWords cur[kMaxPairs];
+#pragma unroll
+            for (int i = 0; i < kMaxPairs; ++i) {
+                const int pr = pt + i * kProducerThreads;
+                cur[i].a = make_uint4(0u, 0u, 0u, 0u); cur[i].b = cur[i].a;
+                if (pr < n_pairs) {
+                    const uint32_t src = wslot + static_cast<uint32_t>(pr) * 8u * wb;
+                    if (wb == 1) { const uint2 v = lds_v2(src); cur[i].a.x = v.x; cur[i].a.y = v.y; }
+                    else if (wb == 2) cur[i].a = lds_v4(src);
+                    else { cur[i].a = lds_v4(src); cur[i].b = lds_v4(src + 16u); }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&w_empty[sw]);
+            // ---- expand into the spike-tile ring
+            mbar_wait_parked(&b_empty[sb], pb ^ 1u);
+            const uint32_t slot = b_base + sb * p.slot_b;
+#pragma unroll
+            for (int i = 0; i < kMaxPairs; ++i) {
+                const int pr = pt + i * kProducerThreads;
+                if (pr >= n_pairs) continue;
+                const uint32_t j = pr >> 3, q = pr & 7;
+                uint32_t r = j, addr = slot + j * 128u;
+                if (packed) {
+                    uint32_t P[4];
+                    if (wb == 1) {
+                        P[0] = __byte_perm(cur[i].a.x, 0u, 0x4140); P[1] = __byte_perm(cur[i].a.x, 0u, 0x4342);
+                        P[2] = __byte_perm(cur[i].a.y, 0u, 0x4140); P[3] = __byte_perm(cur[i].a.y, 0u, 0x4342);
+                    } else if (wb == 2) {
+                        P[0] = cur[i].a.x; P[1] = cur[i].a.y; P[2] = cur[i].a.z; P[3] = cur[i].a.w;
+                    } else {
+                        P[0] = ((cur[i].a.x >> p.in_bit0) & tmask) | (((cur[i].a.y >> p.in_bit0) & tmask) << 16);
+                        P[1] = ((cur[i].a.z >> p.in_bit0) & tmask) | (((cur[i].a.w >> p.in_bit0) & tmask) << 16);
+                        P[2] = ((cur[i].b.x >> p.in_bit0) & tmask) | (((cur[i].b.y >> p.in_bit0) & tmask) << 16);
+                        P[3] = ((cur[i].b.z >> p.in_bit0) & tmask) | (((cur[i].b.w >> p.in_bit0) & tmask) << 16);
+                    }
+                    if (wb != 4) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) P[e] = (P[e] >> p.in_bit0) & pmask;
+                    }
+                    for (int t = 0; t < p.T_box; ++t, r += p.Jh, addr += row_step) {
+                        uint4 o;
+                        o.x = ((P[0] >> t) & 0x00010001u) * one; o.y = ((P[1] >> t) & 0x00010001u) * one;
+                        o.z = ((P[2] >> t) & 0x00010001u) * one; o.w = ((P[3] >> t) & 0x00010001u) * one;
+                        sts_v4(addr + ((q ^ (r & 7u)) << 4), o);
+                    }
+                } else {                           // T_box > 16: 32-bit words, one neuron per register
+                    uint32_t wv[8] = {cur[i].a.x, cur[i].a.y, cur[i].a.z, cur[i].a.w,
+                                      cur[i].b.x, cur[i].b.y, cur[i].b.z, cur[i].b.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) wv[e] = (wv[e] >> p.in_bit0) & tmask;
+                    for (int t = 0; t < p.T_box; ++t, r += p.Jh, addr += row_step) {
+                        uint4 o;
+                        o.x = (((wv[0] >> t) & 1u) | (((wv[1] >> t) & 1u) << 16)) * one;
+                        o.y = (((wv[2] >> t) & 1u) | (((wv[3] >> t) & 1u) << 16)) * one;
+                        o.z = (((wv[4] >> t) & 1u) | (((wv[5] >> t) & 1u) << 16)) * one;
+                        o.w = (((wv[6] >> t) & 1u) | (((wv[7] >> t) & 1u) << 16)) * one;
+                        sts_v4(addr + ((q ^ (r & 7u)) << 4), o);
+                    }
+                }
+            }
+            fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_ready[sb]);
+            // this group's next k-block is two ring stages further
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (++sb == static_cast<uint32_t>(stages_b)) { sb = 0; pb ^= 1u; }
+                if (++sw == static_cast<uint32_t>(stages_w)) { sw = 0; pw ^= 1u; }
             }
         }
     } else if (warp >= 4) {
@@ -222,7 +366,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const int te = q * 32 + lane;                  // 0..127: channel of this thread inside the CTA's 128
         const int n_out = 5 * p.A;
-        if (p.fuse_readout) {                          // this CTA's 128-channel slice of the two 1x1 readout convs
+        const bool fused = kConv && p.fuse_readout != 0;
+        if (fused) {                                   // this CTA's 128-channel slice of the two 1x1 readout convs
             const int c0 = static_cast<int>(rank) * 128;
             for (int i = te; i < kRoMaxOut * 128; i += 128) {
                 const int o = i >> 7, cc = i & 127;
@@ -237,20 +382,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         uint32_t it = 0;
         for (int tile = group; tile < p.total_tiles; tile += n_groups, ++it) {
             const int ut = tile / p.m_tiles, mt = tile - ut * p.m_tiles;
-            const int c = mt * 128 * kCG + static_cast<int>(rank) * 128 + q * 32 + lane;
+            const int c = mt * 128 * kCG + static_cast<int>(rank) * 128 + te;
             int H = 1, W = 1, n = 0, h0 = 0, w0 = 0, lvl = 0;
             uint8_t* trains = reinterpret_cast<uint8_t*>(p.trains);
             unsigned int tile_spikes = 0;
-            if (p.conv) {
-                while (lvl + 1 < p.n_levels && ut >= p.lv[lvl + 1].tile_begin) ++lvl;
-                const LevelDesc& L = p.lv[lvl];
-                int local = ut - L.tile_begin;
-                const int per_img = L.tiles_w * L.tiles_h;
-                n = local / per_img; local -= n * per_img;
-                const int ty = local / L.tiles_w;
-                h0 = ty * p.TH; w0 = (local - ty * L.tiles_w) * p.TW;
-                H = L.H; W = L.W;
-                trains = reinterpret_cast<uint8_t*>(L.trains);
+            if constexpr (kConv) {
+                const TilePos tp = decode_tile(p, ut);
+                lvl = tp.lvl; n = tp.n; h0 = tp.h0; w0 = tp.w0;
+                H = p.lv[lvl].H; W = p.lv[lvl].W;
+                trains = reinterpret_cast<uint8_t*>(p.lv[lvl].trains);
             }
             const float wscale = __ldg(&p.w_scale[c]);
             const uint32_t buf = it & 1u;
@@ -260,117 +400,111 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
 
             for (int sub = 0; sub < kCG; ++sub) {
                 for (int j0 = 0; j0 < p.Jh; j0 += CW) {
-                    float v[CW], cu[CW];
-                    float ii[CW], sk[CW];
+                    float v[CW], ii[CW], sk[CW];
                     uint32_t tr[CW];
 #pragma unroll
                     for (int u = 0; u < CW; ++u) { v[u] = 0.f; ii[u] = 0.f; tr[u] = 0u; sk[u] = 0.f; }
-                    for (int t = p.t0; t < p.T_total; ++t) {
-                        const int tl = t - p.t0;
-                        const bool live = tl < p.T_live;
-                        if (live) {
-                            tmem_ld<CW>(acc + static_cast<uint32_t>(sub * n_half + tl * p.Jh + j0),
-                                        reinterpret_cast<uint32_t*>(cu));
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int u = 0; u < CW; ++u) cu[u] = __fmul_rn(cu[u], wscale);   // exact: power of two
-                        }
+                    // ---- steps that receive an input current (the accumulator columns of this unit chunk)
+                    uint32_t col = acc + static_cast<uint32_t>(sub * n_half + j0);
+                    for (int tl = 0; tl < p.T_live; ++tl, col += p.Jh) {
+                        float cu[CW];
+                        tmem_ld<CW>(col, reinterpret_cast<uint32_t*>(cu));
+                        tmem_ld_wait();
+                        const int t = p.t0 + tl;
                         const float kap = p.kappa[t];
+                        const uint32_t bit = 1u << t;
 #pragma unroll
                         for (int u = 0; u < CW; ++u) {
-                            const float cur = live ? cu[u] : 0.0f;
-                            const uint32_t z = lif_update(v[u], ii[u], cur);
-                            tr[u] |= z << t;
-                            sk[u] = z ? __fadd_rn(sk[u], kap) : sk[u];
+                            cu[u] = __fmul_rn(cu[u], wscale);          // exact: power of two
+                            if (lif_update(v[u], ii[u], cu[u])) { tr[u] |= bit; sk[u] = __fadd_rn(sk[u], kap); }
                         }
-                        if (p.dump != nullptr && live && !p.conv) {
+                        if constexpr (!kConv) {
+                            if (p.dump != nullptr) {
 #pragma unroll
-                            for (int u = 0; u < CW; ++u) {
-                                const int r = ut * p.J + sub * p.Jh + j0 + u;
-                                if (r < p.rows)
-                                    p.dump[(static_cast<size_t>(tl) * p.rows + r) * p.m_total + c] = cu[u];
+                                for (int u = 0; u < CW; ++u) {
+                                    const int r = ut * p.J + sub * p.Jh + j0 + u;
+                                    if (r < p.rows)
+                                        p.dump[(static_cast<size_t>(tl) * p.rows + r) * p.m_total + c] = cu[u];
+                                }
                             }
                         }
                     }
-                    // ---- emit spike trains (+ optional bf16 planes for the next layer)
+                    // ---- remaining steps: the synapse only drains (no new input reaches an output later)
+                    for (int t = p.t0 + p.T_live; t < p.T_total; ++t) {
+                        const float kap = p.kappa[t];
+                        const uint32_t bit = 1u << t;
 #pragma unroll
-                    for (int u = 0; u < CW; ++u) {
-                        const int jh = j0 + u;
-                        size_t r;
-                        bool ok;
-                        if (p.conv) {
-                            const int ty = jh / p.TWh, tx = jh - ty * p.TWh;
-                            const int h = h0 + sub * p.sub_dh + ty, w = w0 + sub * p.sub_dw + tx;
-                            ok = (h < H) && (w < W);
-                            r = (static_cast<size_t>(n) * H + h) * W + w;
-                        } else {
-                            const int rr = ut * p.J + sub * p.Jh + jh;
-                            ok = rr < p.rows;
-                            r = static_cast<size_t>(rr);
-                        }
-                        if (!ok) continue;
-                        tile_spikes += __popc(tr[u]);
-                        if (trains == nullptr) continue;
-                        const size_t e = r * p.m_total + c;
-                        if (p.train_bytes == 1) trains[e] = static_cast<uint8_t>(tr[u]);
-                        else if (p.train_bytes == 2) reinterpret_cast<uint16_t*>(trains)[e] = static_cast<uint16_t>(tr[u]);
-                        else reinterpret_cast<uint32_t*>(trains)[e] = tr[u];
-                        if (p.spikes_out != nullptr) {
-                            for (int t = p.spk_t_lo; t < p.spk_t_hi; ++t)
-                                p.spikes_out[(static_cast<size_t>(t - p.spk_t_lo) * p.rows + r) * p.m_total + c] =
-                                    static_cast<uint16_t>(((tr[u] >> t) & 1u) ? p.spike_one : 0u);
+                        for (int u = 0; u < CW; ++u)
+                            if (lif_update(v[u], ii[u], 0.0f)) { tr[u] |= bit; sk[u] = __fadd_rn(sk[u], kap); }
+                    }
+                    // ---- emit the spike-train words of the chunk
+                    int hh = 0, ww = 0;
+                    bool row_ok;
+                    size_t r0;
+                    int lim;                                   // units u < lim are inside the image / row range
+                    if constexpr (kConv) {                     // a chunk lies inside one tile row (TWh == 8, CW <= 8)
+                        hh = h0 + sub * p.sub_dh + (j0 >> 3);
+                        ww = w0 + sub * p.sub_dw + (j0 & 7);
+                        row_ok = hh < H;
+                        lim = W - ww;
+                        r0 = (static_cast<size_t>(n) * H + hh) * W + ww;
+                    } else {
+                        const int rr = ut * p.J + sub * p.Jh + j0;
+                        row_ok = true;
+                        lim = p.rows - rr;
+                        r0 = static_cast<size_t>(rr);
+                    }
+                    if (row_ok) {
+#pragma unroll
+                        for (int u = 0; u < CW; ++u)
+                            if (u < lim) tile_spikes += __popc(tr[u]);
+                        if (trains != nullptr) {
+                            uint8_t* dst = trains + (r0 * p.m_total + c) * p.train_bytes;
+                            const size_t step = static_cast<size_t>(p.m_total) * p.train_bytes;
+#pragma unroll
+                            for (int u = 0; u < CW; ++u, dst += step) {
+                                if (u >= lim) break;
+                                if (p.train_bytes == 1) *dst = static_cast<uint8_t>(tr[u]);
+                                else if (p.train_bytes == 2) *reinterpret_cast<uint16_t*>(dst) = static_cast<uint16_t>(tr[u]);
+                                else *reinterpret_cast<uint32_t*>(dst) = tr[u];
+                            }
                         }
                     }
                     // ---- fused LI readout: out[o][px] += sum_{c in this CTA} W[o][c] * sk[c][px]
-                    if (p.fuse_readout) {
-                        float* S = ro_s + (chunk_ctr & 1u) * (128 * kRoSStride);
-                        ++chunk_ctr;
+                    if constexpr (kConv) {
+                        if (fused) {
+                            float* S = ro_s + (chunk_ctr & 1u) * (CW * kRoWStride);    // [CW pixels][128 channels + pad]
+                            ++chunk_ctr;
 #pragma unroll
-                        for (int u = 0; u < CW; u += 4)
-                            *reinterpret_cast<float4*>(&S[te * kRoSStride + u]) = make_float4(sk[u], sk[u + 1], sk[u + 2], sk[u + 3]);
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
-                        constexpr int kGroups = 128 / CW;              // thread = (pixel u, output group og)
-                        constexpr int kOPT = (kRoMaxOut + kGroups - 1) / kGroups;
-                        const int u = te % CW, og = te / CW;
-                        float acc[kOPT];
-#pragma unroll
-                        for (int k = 0; k < kOPT; ++k) acc[k] = 0.f;
-                        if (og < kRoMaxOut) {
-#pragma unroll 4
-                            for (int cc = 0; cc < 128; cc += 4) {
-                                const float s0 = S[(cc + 0) * kRoSStride + u], s1 = S[(cc + 1) * kRoSStride + u];
-                                const float s2 = S[(cc + 2) * kRoSStride + u], s3 = S[(cc + 3) * kRoSStride + u];
-#pragma unroll
-                                for (int k = 0; k < kOPT; ++k) {
-                                    const int o = og + k * kGroups;
-                                    if (o < kRoMaxOut) {
-                                        const float4 wv = *reinterpret_cast<const float4*>(&ro_w[o * kRoWStride + cc]);
-                                        acc[k] = fmaf(wv.x, s0, acc[k]); acc[k] = fmaf(wv.y, s1, acc[k]);
-                                        acc[k] = fmaf(wv.z, s2, acc[k]); acc[k] = fmaf(wv.w, s3, acc[k]);
-                                    }
+                            for (int u = 0; u < CW; ++u) S[u * kRoWStride + te] = sk[u];
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            const int u = te % CW, og = te / CW;            // thread = (pixel u, output og)
+                            if (og < kRoMaxOut) {
+                                const float4* s4 = reinterpret_cast<const float4*>(&S[u * kRoWStride]);
+                                const float4* w4 = reinterpret_cast<const float4*>(&ro_w[og * kRoWStride]);
+                                float a = 0.f;
+#pragma unroll 8
+                                for (int cc = 0; cc < 32; ++cc) {
+                                    const float4 sv = s4[cc], wv = w4[cc];
+                                    a = fmaf(wv.x, sv.x, a); a = fmaf(wv.y, sv.y, a);
+                                    a = fmaf(wv.z, sv.z, a); a = fmaf(wv.w, sv.w, a);
                                 }
-                            }
-                            const int jh = j0 + u;
-                            const int ty = jh / p.TWh, tx = jh - ty * p.TWh;
-                            const int h = h0 + sub * p.sub_dh + ty, w = w0 + sub * p.sub_dw + tx;
-                            if (h < H && w < W) {
-                                const LevelDesc& L = p.lv[lvl];
-                                const size_t hw = static_cast<size_t>(H) * W, pix = static_cast<size_t>(h) * W + w;
-#pragma unroll
-                                for (int k = 0; k < kOPT; ++k) {
-                                    const int o = og + k * kGroups;
-                                    if (o < p.A) atomicAdd(&L.logits[(static_cast<size_t>(n) * p.A + o) * hw + pix], acc[k]);
-                                    else if (o < n_out)
-                                        atomicAdd(&L.bbox[(static_cast<size_t>(n) * 4 * p.A + (o - p.A)) * hw + pix], acc[k]);
+                                if (row_ok && u < lim && og < n_out) {
+                                    const LevelDesc& L = p.lv[lvl];
+                                    const size_t hw = static_cast<size_t>(H) * W, pix = static_cast<size_t>(hh) * W + ww + u;
+                                    if (og < p.A) atomicAdd(&L.logits[(static_cast<size_t>(n) * p.A + og) * hw + pix], a);
+                                    else atomicAdd(&L.bbox[(static_cast<size_t>(n) * 4 * p.A + (og - p.A)) * hw + pix], a);
                                 }
                             }
                         }
                     }
                 }
             }
-            if (p.conv && p.lv[lvl].counts != nullptr) {
-                for (int o = 16; o > 0; o >>= 1) tile_spikes += __shfl_xor_sync(0xffffffffu, tile_spikes, o);
-                if (lane == 0 && tile_spikes) atomicAdd(&p.lv[lvl].counts[n], static_cast<unsigned long long>(tile_spikes));
+            if constexpr (kConv) {
+                if (p.lv[lvl].counts != nullptr) {
+                    for (int o = 16; o > 0; o >>= 1) tile_spikes += __shfl_xor_sync(0xffffffffu, tile_spikes, o);
+                    if (lane == 0 && tile_spikes) atomicAdd(&p.lv[lvl].counts[n], static_cast<unsigned long long>(tile_spikes));
+                }
             }
             tcgen05_fence_before();
             __syncwarp();

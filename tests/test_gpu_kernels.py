@@ -14,51 +14,71 @@ pytestmark = pytest.mark.gpu
 def test_library_reports_version_and_rejects_bad_args():
     lib = _lib.load()
     assert lib.snn_version() == 2
-    rc = lib.snn_fc_lif_layer(None, 1, 64, 128, 8, 0, 7, 0, None, None, None, 0, 0, None, 0, None)
+    rc = lib.snn_fc_lif_layer(None, 1, 0, 1, 64, 128, 8, 0, 7, 0, None, None, None, 0, None)
     assert rc == -1 and b"null" in lib.snn_last_error()
 
 
-@pytest.mark.parametrize("mode", [0, 3])
-@pytest.mark.parametrize("T", [1, 7, 8, 12, 32])
-def test_encoder_rows_bit_exact(T, mode):
+def pack_words(z, bit0, nbytes):
+    """[T_live, ...] {0,1} spikes -> spike-train words (bit bit0 + t = z[t]) of `nbytes` bytes."""
+    w = torch.zeros(z.shape[1:], dtype=torch.int64)
+    for t in range(z.shape[0]):
+        w |= z[t].to(torch.int64) << (bit0 + t)
+    if nbytes == 1:
+        return torch.from_numpy(w.numpy().astype(np.uint8))
+    if nbytes == 2:
+        return torch.from_numpy(w.numpy().astype(np.uint16).view(np.int16))
+    return torch.from_numpy(w.numpy().astype(np.uint32).view(np.int32))
+
+
+@pytest.mark.parametrize("T", [1, 7, 8, 12, 16, 17, 32])
+def test_encoder_rows_bit_exact(T):
     lib = _lib.load()
     g = torch.Generator().manual_seed(5)
     x = (torch.randn(37, 192, generator=g) * 1.5)
     x[0, :8] = torch.tensor([0.25, 0.2500001, 0.439, 0.44, -1.0, 0.0, 1e-30, 100.0])
     xd = x.cuda()
-    z = torch.empty(T, 37, 192, dtype=torch.float16 if mode in _lib.FP16_MODES else torch.bfloat16, device="cuda")
-    _lib.check(lib.snn_encode_rows(vp(xd), 37, 192, T, mode, vp(z), stream()), "encode_rows")
+    wb = 1 if T <= 8 else 2 if T <= 16 else 4
+    z = torch.zeros(37, 192, dtype=_TRAIN_DTYPE[wb], device="cuda")
+    _lib.check(lib.snn_encode_rows(vp(xd), 37, 192, T, vp(z), stream()), "encode_rows")
     torch.cuda.synchronize()
     ref = torch.stack(O.encoder_spikes(x, T))
-    assert torch.equal(z.float().cpu(), ref)
+    assert torch.equal(unpack_trains(z.cpu(), T).float(), ref)
     assert T < 8 or ref.sum() > 0
 
 
-def _fc_case(R, K, M, T, t0, T_live, mode, cg, seed=0, density=0.15):
+def _fc_case(R, K, M, T, t0, T_live, mode, cg, seed=0, density=0.15, in_bit0=0, in_wb=None):
+    """One fc spiking layer on random input spike trains; returns the oracle-side spikes and the kernel's
+    trains / raw currents."""
     lib = _lib.load()
     g = torch.Generator().manual_seed(seed)
     z = (torch.rand(T_live, R, K, generator=g) < density).float()
     w = torch.randn(M, K, generator=g) * (1.2 / np.sqrt(density * K))
-    sdt = torch.float16 if mode in _lib.FP16_MODES else torch.bfloat16
-    zd = z.to(sdt).cuda()
+    if in_wb is None:
+        nb = in_bit0 + T_live
+        in_wb = 1 if nb <= 8 else 2 if nb <= 16 else 4
+    words = pack_words(z, in_bit0, in_wb)
+    # bits outside [in_bit0, in_bit0 + T_live) must be ignored by the kernel: set them
+    junk = torch.full_like(words, -1) if in_wb > 1 else torch.full_like(words, 255)
+    mask = pack_words(torch.ones_like(z), in_bit0, in_wb)
+    words = words | (junk & ~mask)
+    zd = words.cuda()
     wd = w.cuda()
     wp = prepared_fc(wd, mode)
     tb = lib.snn_train_word_bytes(T)
     trains = torch.zeros(R, M, dtype=_TRAIN_DTYPE[tb], device="cuda")
     dump = torch.full((T_live, R, M), float("nan"), device="cuda")
-    planes = torch.zeros(T, R, M, dtype=sdt, device="cuda")
-    rc = lib.snn_fc_lif_layer(vp(zd), R, K, M, T, t0, T_live, mode, vp(wp), vp(trains), vp(planes), 0, T, vp(dump), cg,
+    rc = lib.snn_fc_lif_layer(vp(zd), in_wb, in_bit0, R, K, M, T, t0, T_live, mode, vp(wp), vp(trains), vp(dump), cg,
                               stream())
     _lib.check(rc, "fc_lif_layer")
     torch.cuda.synchronize()
-    return z, w, trains.cpu(), dump.cpu(), planes.float().cpu()
+    return z, w, trains.cpu(), dump.cpu()
 
 
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("mode,pieces", [(1, 1), (2, 2), (0, 3), (3, 2), (4, 1)])
 def test_fc_contraction_currents(cg, mode, pieces):
     R, K, M, T, T_live = 50, 192, 256, 8, 6
-    z, w, trains, dump, planes = _fc_case(R, K, M, T, 0, T_live, mode, cg)
+    z, w, trains, dump = _fc_case(R, K, M, T, 0, T_live, mode, cg)
     w_eff = split_reconstruct(w, pieces, fp16=mode in _lib.FP16_MODES)
     ref = torch.einsum("trk,mk->trm", z.double(), w_eff.double())
     err = (dump.double() - ref).abs().max().item()
@@ -77,20 +97,32 @@ def test_fc_contraction_currents(cg, mode, pieces):
                                              (16, 0, 15, 33, 64, 256), (5, 0, 4, 130, 256, 256)])
 @pytest.mark.parametrize("mode", [0, 3])
 def test_fc_lif_epilogue_is_exact_given_currents(cg, T, t0, T_live, R, K, M, mode):
-    z, w, trains, dump, planes = _fc_case(R, K, M, T, t0, T_live, mode, cg, seed=T)
+    z, w, trains, dump = _fc_case(R, K, M, T, t0, T_live, mode, cg, seed=T)
     # LIF recurrence over the kernel's own currents: must match the oracle bit for bit
     spk = O._lif_unroll(dump, T, t0=t0)                      # [T,R,M]
     got = unpack_trains(trains, T)
     assert torch.equal(got, spk)
-    assert torch.equal(planes, spk.float())
     assert spk.sum() > 0 and spk[0].sum() == 0
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("T,t0,T_live,in_bit0,in_wb", [(8, 1, 6, 1, 1), (12, 1, 10, 1, 2), (16, 0, 15, 1, 2),
+                                                      (20, 1, 18, 1, 4), (32, 0, 31, 0, 4), (12, 0, 3, 5, 4)])
+def test_fc_spike_word_operand_formats(cg, T, t0, T_live, in_bit0, in_wb):
+    # every input word size / bit offset the producers expand, junk bits outside the live window ignored
+    R, K, M = 45, 128, 256
+    z, w, trains, dump = _fc_case(R, K, M, T, t0, T_live, 0, cg, seed=T + in_bit0, in_bit0=in_bit0, in_wb=in_wb)
+    ref = torch.einsum("trk,mk->trm", z.double(), w.double())
+    assert not torch.isnan(dump).any()
+    assert (dump.double() - ref).abs().max().item() < 2e-5
+    assert torch.equal(unpack_trains(trains, T), O._lif_unroll(dump, T, t0=t0))
 
 
 def test_fc_large_k_many_tiles():
     # K = 12544 (196 k-blocks, ring wrap-around many times), more tiles than SMs
     R, K, M, T, T_live = 700, 12544, 1024, 12, 10
     for cg in (1, 2):
-        z, w, trains, dump, planes = _fc_case(R, K, M, T, 0, T_live, 1, cg, seed=3, density=0.05)
+        z, w, trains, dump = _fc_case(R, K, M, T, 0, T_live, 1, cg, seed=3, density=0.05)
         w_eff = split_reconstruct(w, 1)
         ref = torch.einsum("trk,mk->trm", z[:, :64].double(), w_eff.double())
         assert (dump[:, :64].double() - ref).abs().max().item() < 5e-5
