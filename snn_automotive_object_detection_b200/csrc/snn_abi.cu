@@ -137,7 +137,7 @@ struct TileCfg { int cg, T_box, J, Jh, TW, TH, TWh, THh, dw, dh, CW, n_mma; };
 // Fold time into the MMA N dimension: N = T_box * J <= 256, N % 16 == 0, J units per tile.
 bool pick_tile_cg(int T_live, bool conv, int cg, TileCfg& out) {
     const int step = conv ? 8 * cg : 4 * cg;
-    const int maxJ = (kMaxPairs * kProducerThreads / 8) * cg;     // producers: Jh * 8 pairs <= kMaxPairs * 128
+    const int maxJ = kMaxUnitsPerCta * cg;                        // producers: Jh * 8 pairs <= kMaxPairs x 64 threads
     int bestJ = 0, bestT = 0;
     for (int J = step; J <= maxJ; J += step)
         for (int Tb = T_live; Tb <= T_live + 1; ++Tb) {
@@ -198,6 +198,11 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
     p.slot_w = static_cast<int>(align_up(static_cast<size_t>(tc.Jh) * 64 * p.in_wb, 128));
     p.stages_w = kRingBytesW / p.slot_w;
     if (p.stages_w > kMaxStagesW) p.stages_w = kMaxStagesW;
+    // producer group g starts on stage g of both rings, so there are at most min(stages) groups (1, 2 or 4)
+    {
+        const int m = p.stages_b < p.stages_w ? p.stages_b : p.stages_w;
+        p.n_pg = m >= 2 ? 2 : 1;      // measured: 2 groups x 4 warps beat 4 x 2 (r01h vs r01f)
+    }
     p.m_tiles = p.m_total / (128 * tc.cg);
     p.total_tiles = p.unit_tiles * p.m_tiles;
     if (p.total_tiles <= 0) return SNN_OK;

@@ -45,12 +45,14 @@ constexpr int kTileBytesA = 128 * 128;      // 128 rows x 64 16-bit
 constexpr int kRingBytesB = 80 * 1024;
 constexpr int kRingBytesW = 16 * 1024;
 constexpr int kBarBytes = 512;
-constexpr int kGemmThreads = 512;           // warps 0-3 control, 4-7 LIF epilogue, 8-15 spike-tile producers (2 groups)
-constexpr int kProducerThreads = 128;       // per producer group
-constexpr int kMaxPairs = 2;                // (unit, 8-channel chunk) pairs a producer thread expands per k-block
+constexpr int kEpiGroups = 1;               // LIF epilogue warp groups (4 warps each): warps 4-7 (+ 16-19)
+constexpr int kGemmThreads = 512 + (kEpiGroups - 1) * 128;   // warps 0-3 control, 4-7 epilogue, 8-15 spike-tile producers
+constexpr int kProducerWarps = 8;           // split into p.n_pg groups (1, 2 or 4); group g expands the k-blocks i = g (mod n_pg)
+constexpr int kMaxPairs = 4;                // (unit, 8-channel chunk) pairs a producer thread expands per k-block
+constexpr int kMaxUnitsPerCta = kMaxPairs * (kProducerWarps * 32 / 4) / 8;   // Jh <= 32: Jh * 8 pairs <= 4 x 64 threads
 constexpr int kRoMaxOut = 16;               // fused readout: objectness + box deltas per pixel (5 * A <= 16)
 constexpr int kRoWStride = 132;             // floats per readout-weight row in smem (128 + pad, 16-B aligned)
-constexpr int kRoSmemBytes = kRoMaxOut * kRoWStride * 4 + 2 * 8 * kRoWStride * 4;   // weights + 2 x [8 px][128 ch] sums
+constexpr int kRoSmemBytes = kRoMaxOut * kRoWStride * 4 + kEpiGroups * 2 * 8 * kRoWStride * 4;   // weights + per epilogue group 2 x [8 px][128 ch] sums
 constexpr size_t kGemmSmemBytes =
     1024 /*align slack*/ + kStagesA * kTileBytesA + kRingBytesB + kRingBytesW + kBarBytes + kRoSmemBytes;
 
@@ -80,6 +82,7 @@ struct GemmLifParams {
     int in_wb, in_bit0;       // input word size; bit of the input word that is step t0 of this layer
     int stages_b, slot_b;     // B ring geometry
     int stages_w, slot_w;     // word ring geometry (slot = Jh units x 64 words)
+    int n_pg;                 // producer groups (each owns every n_pg-th k-block): min(4, stages_b, stages_w) rounded to 1/2/4
     int n_mma;                // T_box * J
     uint32_t idesc;
     void* trains;             // fc: [rows][m_total]
@@ -123,9 +126,6 @@ __device__ __forceinline__ TilePos decode_tile(const GemmLifParams& p, int ut) {
     return tp;
 }
 
-// Raw spike-train words of 8 consecutive input neurons (8, 16 or 32 bytes).
-struct RawWords { uint4 a, b; };
-
 template <int kCG, int CW, bool kConv>
 __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const __grid_constant__ GemmLifParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -160,9 +160,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         for (int l = 0; l < p.n_levels; ++l) tma_prefetch_desc(&p.tmW[l]);
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < kStagesA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < kMaxStagesB; ++s) { mbar_init(&b_ready[s], 4); mbar_init(&b_peer[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < kMaxStagesW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 4); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * kCG); }
+        const uint32_t wpg = static_cast<uint32_t>(kProducerWarps / p.n_pg);      // warps per producer group
+        for (int s = 0; s < kMaxStagesB; ++s) { mbar_init(&b_ready[s], wpg); mbar_init(&b_peer[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < kMaxStagesW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], wpg); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * kEpiGroups * kCG); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<kCG>(tmem_slot, 512);
@@ -263,15 +264,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 }
             }
         }
-    } else if (warp >= 8) {
-        // ============================== spike-tile producers (2 groups x 4 warps): words -> swizzled {0,1} tile
+    } else if (warp >= 8 && warp < 8 + kProducerWarps) {
+        // ============================== spike-tile producers (n_pg groups): words -> swizzled {0,1} tile
         // The k-blocks of this CTA's tile sequence are numbered i = 0, 1, 2, ...; producer group g expands
-        // the k-blocks i = g (mod 2): word-ring stage i % stages_w -> spike-tile ring stage i % stages_b.
-        // A thread owns up to kMaxPairs (unit j, 16-byte chunk q) pairs of the CTA's half tile; per k-block
-        // it reads the pair's 8 input words and writes T_box 16-byte chunks: row r = t * Jh + j,
-        // chunk q ^ (r & 7) -- the 128-byte swizzle TMA would have produced for a K-major bf16 tile.
-        const int grp = (warp - 8) >> 2;
-        const int pt = static_cast<int>(threadIdx.x) - 256 - grp * kProducerThreads;
+        // the k-blocks i = g (mod n_pg): word-ring stage i % stages_w -> spike-tile ring stage i % stages_b,
+        // so n_pg stages are in production at any time.  A thread owns up to kMaxPairs (unit j, 16-byte
+        // chunk q) pairs of the CTA's half tile; per k-block it reads a pair's 8 input words and writes T_box
+        // 16-byte chunks: row r = t * Jh + j, chunk q ^ (r & 7) -- the 128-byte swizzle TMA would have
+        // produced for a K-major 16-bit tile.
+        const int n_pg = p.n_pg;
+        const int tpg = kProducerWarps * 32 / n_pg;    // threads per group
+        const int ptid = static_cast<int>(threadIdx.x) - 256;
+        const int grp = ptid / tpg;
+        const int pt = ptid - grp * tpg;
         const int n_pairs = p.Jh * 8;
         const int wb = p.in_wb;
         const uint32_t tmask = (p.T_live >= 32) ? 0xFFFFFFFFu : ((1u << p.T_live) - 1u);
@@ -283,52 +288,41 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         const uint32_t b_base = smem_u32(b_ring), w_base = smem_u32(w_ring);
         const uint32_t row_step = static_cast<uint32_t>(p.Jh) * 128u;
 
-        uint32_t sb = static_cast<uint32_t>(grp % stages_b), pb = static_cast<uint32_t>((grp / stages_b) & 1);
-        uint32_t sw = static_cast<uint32_t>(grp % stages_w), pw = static_cast<uint32_t>((grp / stages_w) & 1);
-        for (long long i_kb = grp; i_kb < total_kb; i_kb += 2) {
-            // ---- the pair's 8 input words from the word ring
+        // group g starts on stage g of both rings (n_pg <= stages, so its first phase parity is 0)
+        uint32_t sb = static_cast<uint32_t>(grp), pb = 0u, sw = static_cast<uint32_t>(grp), pw = 0u;
+        for (long long i_kb = grp; i_kb < total_kb; i_kb += n_pg) {
             mbar_wait_parked(&w_full[sw], pw);
-            const uint32_t wslot = w_base + sw * p.slot_w;
-            RawWords cur[kMaxPairs];
-#pragma unroll
-            for (int i = 0; i < kMaxPairs; ++i) {
-                const int pr = pt + i * kProducerThreads;
-                cur[i].a = make_uint4(0u, 0u, 0u, 0u); cur[i].b = cur[i].a;
-                if (pr < n_pairs) {
-                    const uint32_t src = wslot + static_cast<uint32_t>(pr) * 8u * wb;
-                    if (wb == 1) { const uint2 v = lds_v2(src); cur[i].a.x = v.x; cur[i].a.y = v.y; }
-                    else if (wb == 2) cur[i].a = lds_v4(src);
-                    else { cur[i].a = lds_v4(src); cur[i].b = lds_v4(src + 16u); }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&w_empty[sw]);
-            // ---- expand into the spike-tile ring
             mbar_wait_parked(&b_empty[sb], pb ^ 1u);
+            const uint32_t wslot = w_base + sw * p.slot_w;
             const uint32_t slot = b_base + sb * p.slot_b;
 #pragma unroll
             for (int i = 0; i < kMaxPairs; ++i) {
-                const int pr = pt + i * kProducerThreads;
-                if (pr >= n_pairs) continue;
+                const int pr = pt + i * tpg;
+                if (pr >= n_pairs) break;
                 const uint32_t j = pr >> 3, q = pr & 7;
+                const uint32_t src = wslot + static_cast<uint32_t>(pr) * 8u * wb;
                 uint32_t r = j, addr = slot + j * 128u;
                 if (packed) {
                     uint32_t P[4];
                     if (wb == 1) {
-                        P[0] = __byte_perm(cur[i].a.x, 0u, 0x4140); P[1] = __byte_perm(cur[i].a.x, 0u, 0x4342);
-                        P[2] = __byte_perm(cur[i].a.y, 0u, 0x4140); P[3] = __byte_perm(cur[i].a.y, 0u, 0x4342);
+                        const uint2 v = lds_v2(src);
+                        P[0] = __byte_perm(v.x, 0u, 0x4140); P[1] = __byte_perm(v.x, 0u, 0x4342);
+                        P[2] = __byte_perm(v.y, 0u, 0x4140); P[3] = __byte_perm(v.y, 0u, 0x4342);
                     } else if (wb == 2) {
-                        P[0] = cur[i].a.x; P[1] = cur[i].a.y; P[2] = cur[i].a.z; P[3] = cur[i].a.w;
+                        const uint4 v = lds_v4(src);
+                        P[0] = v.x; P[1] = v.y; P[2] = v.z; P[3] = v.w;
                     } else {
-                        P[0] = ((cur[i].a.x >> p.in_bit0) & tmask) | (((cur[i].a.y >> p.in_bit0) & tmask) << 16);
-                        P[1] = ((cur[i].a.z >> p.in_bit0) & tmask) | (((cur[i].a.w >> p.in_bit0) & tmask) << 16);
-                        P[2] = ((cur[i].b.x >> p.in_bit0) & tmask) | (((cur[i].b.y >> p.in_bit0) & tmask) << 16);
-                        P[3] = ((cur[i].b.z >> p.in_bit0) & tmask) | (((cur[i].b.w >> p.in_bit0) & tmask) << 16);
+                        const uint4 a = lds_v4(src), c = lds_v4(src + 16u);
+                        P[0] = ((a.x >> p.in_bit0) & tmask) | (((a.y >> p.in_bit0) & tmask) << 16);
+                        P[1] = ((a.z >> p.in_bit0) & tmask) | (((a.w >> p.in_bit0) & tmask) << 16);
+                        P[2] = ((c.x >> p.in_bit0) & tmask) | (((c.y >> p.in_bit0) & tmask) << 16);
+                        P[3] = ((c.z >> p.in_bit0) & tmask) | (((c.w >> p.in_bit0) & tmask) << 16);
                     }
                     if (wb != 4) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) P[e] = (P[e] >> p.in_bit0) & pmask;
                     }
+#pragma unroll 4
                     for (int t = 0; t < p.T_box; ++t, r += p.Jh, addr += row_step) {
                         uint4 o;
                         o.x = ((P[0] >> t) & 0x00010001u) * one; o.y = ((P[1] >> t) & 0x00010001u) * one;
@@ -336,8 +330,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                         sts_v4(addr + ((q ^ (r & 7u)) << 4), o);
                     }
                 } else {                           // T_box > 16: 32-bit words, one neuron per register
-                    uint32_t wv[8] = {cur[i].a.x, cur[i].a.y, cur[i].a.z, cur[i].a.w,
-                                      cur[i].b.x, cur[i].b.y, cur[i].b.z, cur[i].b.w};
+                    const uint4 a = lds_v4(src), c = lds_v4(src + 16u);
+                    uint32_t wv[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
                     for (int e = 0; e < 8; ++e) wv[e] = (wv[e] >> p.in_bit0) & tmask;
                     for (int t = 0; t < p.T_box; ++t, r += p.Jh, addr += row_step) {
@@ -352,17 +346,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             }
             fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core
             __syncwarp();
-            if (lane == 0) mbar_arrive(&b_ready[sb]);
-            // this group's next k-block is two ring stages further
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if (++sb == static_cast<uint32_t>(stages_b)) { sb = 0; pb ^= 1u; }
-                if (++sw == static_cast<uint32_t>(stages_w)) { sw = 0; pw ^= 1u; }
-            }
+            if (lane == 0) { mbar_arrive(&b_ready[sb]); mbar_arrive(&w_empty[sw]); }
+            // this group's next k-block is n_pg ring stages further
+            sb += n_pg; if (sb >= static_cast<uint32_t>(stages_b)) { sb -= stages_b; pb ^= 1u; }
+            sw += n_pg; if (sw >= static_cast<uint32_t>(stages_w)) { sw -= stages_w; pw ^= 1u; }
         }
     } else if (warp >= 4) {
-        // ============================================ LIF epilogue (4 warps)
-        const int q = warp - 4;                        // TMEM lane quadrant of this warp
+        // ============================================ LIF epilogue (2 groups x 4 warps)
+        // Group eg takes every other unit chunk of a tile; a warp reads the TMEM lane quadrant warp % 4.
+        const int eg = warp >= 16 ? 1 : 0;
+        const int q = warp & 3;                        // TMEM lane quadrant of this warp
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const int te = q * 32 + lane;                  // 0..127: channel of this thread inside the CTA's 128
         const int n_out = 5 * p.A;
@@ -376,8 +369,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 else if (o < n_out) wv = p.w_bbox[(o - p.A) * p.m_total + c0 + cc];
                 ro_w[o * kRoWStride + cc] = wv;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
         }
+        float* ro_sg = ro_s + eg * (2 * 8 * kRoWStride);
         uint32_t chunk_ctr = 0;
         uint32_t it = 0;
         for (int tile = group; tile < p.total_tiles; tile += n_groups, ++it) {
@@ -398,8 +392,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             tcgen05_fence_after();
             const uint32_t acc = tmem_base + lane_addr + buf * 256u;
 
-            for (int sub = 0; sub < kCG; ++sub) {
-                for (int j0 = 0; j0 < p.Jh; j0 += CW) {
+            const int chunks_per_sub = p.Jh / CW;
+            for (int ch = eg; ch < kCG * chunks_per_sub; ch += kEpiGroups) {
+                const int sub = ch / chunks_per_sub;
+                const int j0 = (ch - sub * chunks_per_sub) * CW;
+                {
                     float v[CW], ii[CW], sk[CW];
                     uint32_t tr[CW];
 #pragma unroll
@@ -473,17 +470,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                     // ---- fused LI readout: out[o][px] += sum_{c in this CTA} W[o][c] * sk[c][px]
                     if constexpr (kConv) {
                         if (fused) {
-                            float* S = ro_s + (chunk_ctr & 1u) * (CW * kRoWStride);    // [CW pixels][128 channels + pad]
+                            float* S = ro_sg + (chunk_ctr & 1u) * (8 * kRoWStride);    // [CW pixels][128 channels + pad]
                             ++chunk_ctr;
 #pragma unroll
                             for (int u = 0; u < CW; ++u) S[u * kRoWStride + te] = sk[u];
-                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
                             const int u = te % CW, og = te / CW;            // thread = (pixel u, output og)
                             if (og < kRoMaxOut) {
                                 const float4* s4 = reinterpret_cast<const float4*>(&S[u * kRoWStride]);
                                 const float4* w4 = reinterpret_cast<const float4*>(&ro_w[og * kRoWStride]);
                                 float a = 0.f;
-#pragma unroll 8
+#pragma unroll 4
                                 for (int cc = 0; cc < 32; ++cc) {
                                     const float4 sv = s4[cc], wv = w4[cc];
                                     a = fmaf(wv.x, sv.x, a); a = fmaf(wv.y, sv.y, a);
