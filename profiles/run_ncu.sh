@@ -1,13 +1,16 @@
 #!/bin/bash
 # Run on the GPU box (via gpurun).  Usage: profiles/run_ncu.sh <tag> [mode]
-# Produces gpurun_out/<tag>_launches.csv (every launch, device time) and
-# gpurun_out/<tag>_gemm.ncu-rep (--set full of the spike GEMM launches of one step).
+# Produces in gpurun_out/:
+#   <tag>_launches_<mode>.csv   every kernel launch of `bench.py --steps 2 --warmup 3` with its device time
+#   <tag>_gemm_<mode>.ncu-rep   --set full (+source) of the three spike GEMM launches of one step
+#   <tag>_aux_<mode>.ncu-rep    --set full of the encoder / readout / LUT launches of one step
+# Summaries for profiles/ are produced here afterwards with profiles/summarise_ncu.py.
 TAG=${1:-r01}
-MODE=${2:-fp32_exact}
+MODE=${2:-fp16x2}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --mode $MODE --no-e2e --no-cpu-baseline"
-# bench warms up 3 steps (17 launches each + 2 weight-prep) before the 2 timed steps
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:spike_gemm_lif -s 9 -c 3 -o gpurun_out/${TAG}_gemm $CMD > gpurun_out/${TAG}_gemm.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"encode_|readout_" -s 24 -c 12 -o gpurun_out/${TAG}_aux $CMD > gpurun_out/${TAG}_aux.log 2>&1
-ls -la gpurun_out
+CMD="python bench.py --steps 2 --warmup 3 --mode $MODE --no-e2e --no-cpu-baseline --no-other-modes"
+# per step: rpn {lut, encoder, conv gemm} + box {lut, encoder, fc6 gemm, fc7 gemm, readout} = 8 launches; 2 weight-prep first
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${TAG}_launches_${MODE}.csv $CMD > gpurun_out/${TAG}_launches_${MODE}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:spike_gemm_lif -s 9 -c 3 -o gpurun_out/${TAG}_gemm_${MODE} $CMD > gpurun_out/${TAG}_gemm_${MODE}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"encode_|readout_|build_lut" -s 15 -c 5 -o gpurun_out/${TAG}_aux_${MODE} $CMD > gpurun_out/${TAG}_aux_${MODE}.log 2>&1
+ls -la gpurun_out | tail -8

@@ -69,16 +69,38 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restri
 // ---------------------------------------------------------------- encoder
 // Norse lif_current_encoder, op for op: v += 0.1f*((0-v)+x); z = (v-0.25f > 0); v -= z*v.
 // Returns the spike train of the first T steps as a bit word (bit t = z_t).
+// The threshold test is evaluated as v > 0.25f: for fp32 numbers a and b, fl(a - b) > 0 <=> a > b (the
+// difference of two floats near the threshold is a multiple of 2^-26, never flushed), so it is the same bit.
 __device__ __forceinline__ uint32_t encode_train(float x, int T) {
     float v = 0.f;
     uint32_t w = 0u;
     for (int t = 0; t < T; ++t) {
         v = __fadd_rn(v, __fmul_rn(0.1f, __fsub_rn(x, v)));
-        const bool z = __fsub_rn(v, 0.25f) > 0.f;
-        w |= (z ? 1u : 0u) << t;
+        const bool z = v > 0.25f;
+        if (z) w |= 1u << t;
         v = z ? 0.f : v;
     }
     return w;
+}
+
+// The same for N independent inputs in lock-step: one time loop, the step's bit mask computed once, N
+// dependency chains interleaved (the encoders are instruction-issue bound, not HBM bound).
+template <int N>
+__device__ __forceinline__ void encode_trains(const float (&x)[N], int T, uint32_t (&w)[N]) {
+    float v[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { v[k] = 0.f; w[k] = 0u; }
+#pragma unroll 2
+    for (int t = 0; t < T; ++t) {
+        const uint32_t bit = 1u << t;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            v[k] = __fadd_rn(v[k], __fmul_rn(0.1f, __fsub_rn(x[k], v[k])));
+            const bool z = v[k] > 0.25f;
+            w[k] = z ? (w[k] | bit) : w[k];
+            v[k] = z ? 0.f : v[k];
+        }
+    }
 }
 
 constexpr int kEncW = 32;        // pixels per block along W
@@ -117,11 +139,21 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
     const int ld = C + 4;
     const float* xrow = L.x + (static_cast<size_t>(n) * C * H + h) * W + w;
     const size_t cstride = static_cast<size_t>(H) * W;
-#pragma unroll 4
-    for (int c = warp; c < C; c += 8) {
-        float xv = 0.f;
-        if (w < W) xv = __ldg(xrow + c * cstride);
-        s_tr[lane * ld + c] = encode_train(xv, p.T_live);
+    // 8 independent 128-byte row loads in flight per warp before the (compute-heavy) encoder steps
+    for (int c0 = warp; c0 < C; c0 += 64) {
+        float xv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = c0 + 8 * k;
+            xv[k] = (w < W && c < C) ? __ldg(xrow + c * cstride) : 0.f;
+        }
+        uint32_t tw[8];
+        encode_trains<8>(xv, p.T_live, tw);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = c0 + 8 * k;
+            if (c < C) s_tr[lane * ld + c] = tw[k];
+        }
     }
     __syncthreads();
     const int npx = min(kEncW, W - w0);
@@ -154,14 +186,14 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
 // x [R][K] fp32 -> words [R][K] of `wb` bytes; 8 consecutive k per thread (2 x float4 in, 8 words out)
 __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total8, int T_live,
                                                           int wb, uint8_t* __restrict__ z) {
+#pragma unroll 2
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
         const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
         const float xs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         uint32_t tr[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) tr[q] = encode_train(xs[q], T_live);
+        encode_trains<8>(xs, T_live, tr);
         if (wb == 1) {
             uint2 o;
             o.x = tr[0] | (tr[1] << 8) | (tr[2] << 16) | (tr[3] << 24);

@@ -99,11 +99,12 @@ struct GemmLifParams {
 // One LIF step of Norse's lif_feed_forward_step, op for op (no FMA contraction):
 //   v_dec = v + 0.1f*((0 - v) + i);  i_dec = i + (-0.2f)*i;  z = (v_dec - 0.1f > 0);
 //   v' = (1-z)*v_dec + z*0;  i' = i_dec + cur
+// The threshold test is evaluated as v_dec > 0.1f, the same bit as fl(v_dec - 0.1f) > 0 (see encode_train).
 __device__ __forceinline__ bool lif_update(float& v, float& i, float cur) {
     const float dv = __fmul_rn(0.1f, __fsub_rn(i, v));
     const float v_dec = __fadd_rn(v, dv);
     const float i_dec = __fadd_rn(i, __fmul_rn(-0.2f, i));
-    const bool z = __fsub_rn(v_dec, 0.1f) > 0.0f;
+    const bool z = v_dec > 0.1f;
     v = z ? 0.0f : v_dec;
     i = __fadd_rn(i_dec, cur);
     return z;
