@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other weight modes")
     ap.add_argument("--workload", default="cityscapes", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=2, help="images per GPU per step (BASELINE configs[0]/[1]: 2)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong-scaling variant (BASELINE configs[4]): this many images per step in total, split over the ranks")
     ap.add_argument("--t-rpn", type=int, default=T_RPN)
     ap.add_argument("--t-det", type=int, default=T_DET)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -182,6 +184,11 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     levels, C = wl["levels"], wl["classes"]
     B = args.batch
+    strong = args.global_batch > 0
+    if strong:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        B = args.global_batch // world
     lib = _lib.load()
     lib.snn_set_cta_group(args.cta_group)
 
@@ -383,7 +390,7 @@ def run_ours(args):
                "ms_per_sample": ms}
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": DTYPE_OF_MODE[args.mode], "data": "synthetic",
         "config": {"workload": wl["name"], "images_per_gpu_per_step": B, "global_batch": B * world,
                    "T_rpn": args.t_rpn, "T_det": args.t_det, "rois_per_image": ROIS, "classes": C,
