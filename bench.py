@@ -196,7 +196,9 @@ def run_ours(args):
     torch.manual_seed(0)
     rpn = RPNHeadSNN(CH, 3, args.t_rpn, mode=args.mode).to(dev)
     box = FastRCNNPredictorSNNFull(KBOX, HID, C, args.t_det, mode=args.mode).to(dev)
-    rpn.record_rates = box.record_rates = world > 1          # spike statistics are what the ranks gather
+    # spike-rate statistics are part of every step at every N (they are what the ranks gather), so the
+    # per-GPU work is identical in the 1/2/4/8-GPU runs
+    rpn.record_rates = box.record_rates = True
 
     # synthetic inputs, seeded per global image index so shards are reproducible
     def make_inputs(pin):
@@ -217,11 +219,10 @@ def run_ours(args):
     def step_resident():
         lo, bb = rpn(d_feats)
         cls, dl = box(d_rois)
-        if world > 1:
-            rec = parallel.spike_rate_records(rpn.last_spike_counts, levels, CH, args.t_rpn, box.last_spike_counts,
-                                              ROIS, HID, args.t_det)
-            parallel.gather_records(rec, [B] * world)
-        return lo, bb, cls, dl
+        rec = parallel.spike_rate_records(rpn.last_spike_counts, levels, CH, args.t_rpn, box.last_spike_counts,
+                                          ROIS, HID, args.t_det)
+        rec = parallel.gather_records(rec, [B] * world)          # NCCL all-gather when world > 1
+        return lo, bb, cls, dl, rec
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -278,10 +279,9 @@ def run_ours(args):
             main.wait_event(in_done[k])
             lo, bb = rpn(bufs[k][0])
             cls, dl = box(bufs[k][1])
-            if world > 1:
-                rec = parallel.spike_rate_records(rpn.last_spike_counts, levels, CH, args.t_rpn,
-                                                  box.last_spike_counts, ROIS, HID, args.t_det)
-                parallel.gather_records(rec, [B] * world)
+            rec = parallel.spike_rate_records(rpn.last_spike_counts, levels, CH, args.t_rpn,
+                                              box.last_spike_counts, ROIS, HID, args.t_det)
+            parallel.gather_records(rec, [B] * world)
             comp_done[k].record(main)
             with torch.cuda.stream(cs_out):
                 cs_out.wait_event(comp_done[k])
@@ -342,7 +342,7 @@ def run_ours(args):
         if roof["clock_ceiling_tflops"]:
             roof["frac_of_clock_ceiling"] = ach / roof["clock_ceiling_tflops"]
     phase_ms = {k: (v[0] / v[1] if v[1] else None) for k, v in phases.items()}
-    fc6_flops = 2.0 * B * ROIS * KBOX * HID * (args.t_det - 2) * pieces
+    fc6_flops = 2.0 * B * ROIS * KBOX * HID * (args.t_det - 1) * pieces      # + the step only lif6's spike count needs
     fc7_flops = 2.0 * B * ROIS * HID * HID * (args.t_det - 2) * pieces
     extra = {}
     for name, fl in (("fc6_lif_gemm", fc6_flops), ("fc7_lif_gemm", fc7_flops)):

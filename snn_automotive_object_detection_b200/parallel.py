@@ -44,12 +44,10 @@ def spike_rate_records(rpn_counts: torch.Tensor, level_sizes: Sequence[Tuple[int
                        box_counts: torch.Tensor, rois_per_image: int, hidden: int, T_det: int) -> torch.Tensor:
     """Per-image record [n_local, levels + 2] of mean spike rates: shared_lif per FPN level, then lif6
     and lif7 averaged over the image's RoIs (the quantities train.py:482,491 reads from the reference's
-    spike-rate list, indices {0,3,6,9,12} and {15,16})."""
+    spike-rate list, indices {0,3,6,9,12} and {15,16}).  Three small device ops, no host sync."""
     L, N = rpn_counts.shape
-    rec = torch.empty(N, L + 2, device=rpn_counts.device, dtype=torch.float64)
-    for l, (h, w) in enumerate(level_sizes):
-        rec[:, l] = rpn_counts[l].double() / float(h * w * channels * T_rpn)
-    per_img = box_counts.double().view(2, N, rois_per_image).sum(dim=2) / float(rois_per_image * hidden * T_det)
-    rec[:, L] = per_img[0]
-    rec[:, L + 1] = per_img[1]
-    return rec
+    denom = torch.tensor([float(h * w * channels * T_rpn) for (h, w) in level_sizes], device=rpn_counts.device,
+                         dtype=torch.float64)
+    rpn_rates = rpn_counts.double().t() / denom                                        # [N, L]
+    box_rates = box_counts.double().view(2, N, rois_per_image).sum(dim=2).t() / float(rois_per_image * hidden * T_det)
+    return torch.cat([rpn_rates, box_rates], dim=1)
