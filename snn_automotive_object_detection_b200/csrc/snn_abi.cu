@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/snn_heads.h"
@@ -195,6 +196,15 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
     p.slot_b = static_cast<int>(align_up(static_cast<size_t>(tc.n_mma / tc.cg) * 128, 1024));
     p.stages_b = kRingBytesB / p.slot_b;
     if (p.stages_b > kMaxStagesB) p.stages_b = kMaxStagesB;
+    if (const char* e = getenv("SNN_DBG_SWIZZLE")) {       // "shift,sbo,boff" -- scratch/swizzle_experiment.py only
+        int a = 0, b = 0, c = 0;
+        if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && b >= 1024) {
+            p.dbg_shift = a; p.dbg_sbo = b; p.dbg_boff = c;
+            p.slot_b = static_cast<int>(align_up(static_cast<size_t>(tc.n_mma / tc.cg + 7) / 8 * b + 2048, 1024));
+            p.stages_b = kRingBytesB / p.slot_b;
+            if (p.stages_b > kMaxStagesB) p.stages_b = kMaxStagesB;
+        }
+    }
     p.slot_w = static_cast<int>(align_up(static_cast<size_t>(tc.Jh) * 64 * p.in_wb, 128));
     p.stages_w = kRingBytesW / p.slot_w;
     if (p.stages_w > kMaxStagesW) p.stages_w = kMaxStagesW;

@@ -89,6 +89,7 @@ struct GemmLifParams {
     uint32_t spike_one;       // 1.0 as bf16 (0x3F80) or fp16 (0x3C00)
     const float* w_scale;     // [m_total] power of two each accumulator row is multiplied with (1 for bf16 pieces)
     float* dump;              // debug (fc only): raw currents [T_live][rows][m_total]
+    int dbg_shift, dbg_sbo, dbg_boff;   // swizzle experiment (scratch/swizzle_experiment.py): row shift, group stride, base-offset field
     // fused leaky-integrator readout (conv, cta_group 2, m_total == 256): mem_{T-1} = W . sum_t kappa_{T-1-t} spk_t
     int fuse_readout, A;
     const float* w_cls;       // [A][m_total]
@@ -207,7 +208,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                     mbar_wait(&b_ready[sb], pb);
                     if constexpr (kCG == 2) mbar_wait_cluster(&b_peer[sb], pb);
                     tcgen05_fence_after();
-                    const uint64_t b_desc = umma_desc_sw128(smem_u32(b_ring + sb * p.slot_b));
+                    uint64_t b_desc = umma_desc_sw128(smem_u32(b_ring + sb * p.slot_b));
+                    if (p.dbg_sbo != 0) {      // swizzle experiment: shifted start, custom 8-row-group stride, base offset
+                        const uint32_t st = smem_u32(b_ring + sb * p.slot_b) + static_cast<uint32_t>(p.dbg_shift) * 128u;
+                        b_desc = static_cast<uint64_t>((st & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(1) << 16) |
+                                 (static_cast<uint64_t>(p.dbg_sbo >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+                                 (static_cast<uint64_t>(p.dbg_boff & 7) << 49) | (static_cast<uint64_t>(2) << 61);
+                    }
                     for (int s = 0; s < p.nsplit; ++s) {
                         mbar_wait(&a_full[sa], pa);
                         tcgen05_fence_after();
@@ -328,6 +335,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                         uint4 o;
                         o.x = ((P[0] >> t) & 0x00010001u) * one; o.y = ((P[1] >> t) & 0x00010001u) * one;
                         o.z = ((P[2] >> t) & 0x00010001u) * one; o.w = ((P[3] >> t) & 0x00010001u) * one;
+                        if (p.dbg_sbo != 0) {  // swizzle experiment: absolute-address swizzle, rows in groups of 8 at stride dbg_sbo
+                            const uint32_t ra = slot + static_cast<uint32_t>(p.dbg_shift) * 128u + (r >> 3) * p.dbg_sbo + (r & 7u) * 128u;
+                            sts_v4(ra + ((q ^ ((ra >> 7) & 7u)) << 4), o);
+                        } else
                         sts_v4(addr + ((q ^ (r & 7u)) << 4), o);
                     }
                 } else {                           // T_box > 16: 32-bit words, one neuron per register
