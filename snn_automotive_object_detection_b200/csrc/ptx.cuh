@@ -238,6 +238,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= static_cast<uint64_t>(2) << 61;                       // [61,64) SWIZZLE_128B
     return d;
 }
+// the same with an arbitrary 128-B-aligned start row and 8-row-group stride (bytes): the swizzle follows the
+// absolute shared-memory address bits, so shifted / strided windows of one tile are valid operands (base offset 0)
+__device__ __forceinline__ uint64_t umma_desc_sw128_strided(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
 // instruction descriptor (kind::f16): dense, D=f32, A=B=bf16 (format 1) or fp16 (format 0), both K-major
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool bf16) {
     const uint32_t fmt = bf16 ? 1u : 0u;
@@ -246,6 +257,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool bf16) {
 }
 
 // TMEM -> registers, 32 lanes x 32-bit, N consecutive columns per thread.
+__device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -278,7 +292,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 template <int CW>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r) {
-    if constexpr (CW == 4) tmem_ld_x4(taddr, r);
+    if constexpr (CW == 2) tmem_ld_x2(taddr, r);
+    else if constexpr (CW == 4) tmem_ld_x4(taddr, r);
     else if constexpr (CW == 8) tmem_ld_x8(taddr, r);
     else if constexpr (CW == 16) tmem_ld_x16(taddr, r);
     else tmem_ld_x32(taddr, r);

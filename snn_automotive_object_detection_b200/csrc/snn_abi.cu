@@ -137,7 +137,7 @@ struct TileCfg { int cg, T_box, J, Jh, TW, TH, TWh, THh, dw, dh, CW, n_mma; };
 
 // Fold time into the MMA N dimension: N = T_box * J <= 256, N % 16 == 0, J units per tile.
 bool pick_tile_cg(int T_live, bool conv, int cg, TileCfg& out) {
-    const int step = conv ? 8 * cg : 4 * cg;
+    const int step = conv ? 8 * cg : 2 * cg;      // fc: units per CTA a multiple of 2 (epilogue chunks of 2, 4 or 8)
     const int maxJ = kMaxUnitsPerCta * cg;                        // producers: Jh * 8 pairs <= kMaxPairs x 64 threads
     int bestJ = 0, bestT = 0;
     for (int J = step; J <= maxJ; J += step)
@@ -153,7 +153,7 @@ bool pick_tile_cg(int T_live, bool conv, int cg, TileCfg& out) {
     } else {
         out.TW = out.TH = out.TWh = out.THh = 0; out.dw = out.dh = 0;
     }
-    out.CW = (out.Jh % 8 == 0) ? 8 : 4;   // wider chunks do not fit the 384-thread register budget
+    out.CW = (out.Jh % 8 == 0) ? 8 : (out.Jh % 4 == 0) ? 4 : 2;
     return true;
 }
 bool pick_tile(int T_live, bool conv, int m_total, int force_cg, TileCfg& out) {
@@ -183,7 +183,7 @@ cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_
     if (p.conv) {
         if (CW == 8) SNN_LAUNCH(8, true) else SNN_LAUNCH(4, true)
     } else {
-        if (CW == 8) SNN_LAUNCH(8, false) else SNN_LAUNCH(4, false)
+        if (CW == 8) SNN_LAUNCH(8, false) else if (CW == 4) SNN_LAUNCH(4, false) else SNN_LAUNCH(2, false)
     }
 #undef SNN_LAUNCH
 }
@@ -193,9 +193,21 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
     p.sub_dw = tc.dw; p.sub_dh = tc.dh; p.T_box = tc.T_box; p.n_mma = tc.n_mma;
     p.idesc = umma_idesc_f16(128 * tc.cg, tc.n_mma, !is_fp16(mode));
     p.spike_one = one_of(mode);
-    p.slot_b = static_cast<int>(align_up(static_cast<size_t>(tc.n_mma / tc.cg) * 128, 1024));
+    if (p.conv) {    // one halo'd spike tile per 64-channel block: (TH/cg + 2) x T_box x (8 + 2) rows of 128 B
+        p.hrows = tc.THh + 2;
+        p.slot_b = static_cast<int>(align_up(static_cast<size_t>(p.hrows) * tc.T_box * 10 * 128, 1024));
+    } else {
+        p.slot_b = static_cast<int>(align_up(static_cast<size_t>(tc.n_mma / tc.cg) * 128, 1024));
+    }
+    p.stages_a = kStagesA;
     p.stages_b = kRingBytesB / p.slot_b;
     if (p.stages_b > kMaxStagesB) p.stages_b = kMaxStagesB;
+    if (p.stages_b < 1) {        // one spike tile larger than the 80 KB spike ring: it borrows weight-ring stages
+        p.stages_b = 1;
+        p.stages_a = (kStagesA * kTileBytesA + kRingBytesB - p.slot_b) / kTileBytesA;
+        if (p.stages_a < 2) return fail(SNN_E_ARG, "spike tile of %d bytes does not fit shared memory", p.slot_b);
+        if (p.stages_a > kStagesA) p.stages_a = kStagesA;
+    }
     if (const char* e = getenv("SNN_DBG_SWIZZLE")) {       // "shift,sbo,boff" -- scratch/swizzle_experiment.py only
         int a = 0, b = 0, c = 0;
         if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && b >= 1024) {
@@ -205,13 +217,14 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
             if (p.stages_b > kMaxStagesB) p.stages_b = kMaxStagesB;
         }
     }
-    p.slot_w = static_cast<int>(align_up(static_cast<size_t>(tc.Jh) * 64 * p.in_wb, 128));
+    p.slot_w = static_cast<int>(align_up(static_cast<size_t>(p.conv ? p.hrows * 10 : tc.Jh) * 64 * p.in_wb, 128));
     p.stages_w = kRingBytesW / p.slot_w;
     if (p.stages_w > kMaxStagesW) p.stages_w = kMaxStagesW;
     // producer group g starts on stage g of both rings, so there are at most min(stages) groups (1, 2 or 4)
     {
         const int m = p.stages_b < p.stages_w ? p.stages_b : p.stages_w;
         p.n_pg = m >= 2 ? 2 : 1;      // measured: 2 groups x 4 warps beat 4 x 2 (r01h vs r01f)
+        if (p.conv) p.n_pg = 1;       // one stage per 64-channel block serves 9 taps: all 8 warps fill it together
     }
     p.m_tiles = p.m_total / (128 * tc.cg);
     p.total_tiles = p.unit_tiles * p.m_tiles;
@@ -473,11 +486,11 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
             L.H = H[l]; L.W = W[l];
             L.tiles_w = (W[l] + tc.TW - 1) / tc.TW; L.tiles_h = (H[l] + tc.TH - 1) / tc.TH;
             L.tile_begin = tiles; L.trains = trains[l];
-            {   // encoder words [N][H][W][C] as a byte tensor; one box = (64 words, TWh, THh) of one image
+            {   // encoder words [N][H][W][C] as a byte tensor; one box = (64 words, TWh + 2, THh + 2) of one image
                 const cuuint64_t wbz = (cuuint64_t)word_bytes(T_live);
                 cuuint64_t dims[4] = {(cuuint64_t)C_in * wbz, (cuuint64_t)W[l], (cuuint64_t)H[l], (cuuint64_t)N};
                 cuuint64_t str[3] = {(cuuint64_t)C_in * wbz, (cuuint64_t)W[l] * C_in * wbz, (cuuint64_t)H[l] * W[l] * C_in * wbz};
-                cuuint32_t box[4] = {(cuuint32_t)(64 * wbz), (cuuint32_t)tc.TWh, (cuuint32_t)tc.THh, 1};
+                cuuint32_t box[4] = {(cuuint32_t)(64 * wbz), (cuuint32_t)(tc.TWh + 2), (cuuint32_t)(tc.THh + 2), 1};
                 rc = make_tmap(&p.tmW[l], wsp + ws.z_off[l], 4, dims, str, box, true);
                 if (rc) return rc;
             }

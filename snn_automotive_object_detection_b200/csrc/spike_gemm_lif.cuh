@@ -19,11 +19,16 @@
 //    producer warps expand the words of a k-block into the 128-byte-swizzled K-major tile the
 //    tensor core reads (rows ordered (t, unit): ALL timesteps of a unit sit in the same
 //    accumulator tile, time folded into the MMA N dimension, N = T_box * J <= 256):
-//      fc   : words [R][K]            TMA box (64 words, Jh rows)
-//      conv : words [N][H][W][C]      TMA box (64 words, TWh, THh, 1) per (tap, 64-channel block) at the
-//             shifted pixel; the 3x3 halo and the image border are TMA out-of-bounds zero fill.
-//    The word tile of a k-block is 1-2 KB per CTA (vs 14-16 KB for expanded planes), so the
-//    L2->SM feed of the kernel is essentially the weight tiles alone.
+//      fc   : words [R][K]            TMA box (64 words, Jh rows) per k-block; one spike tile per k-block.
+//      conv : words [N][H][W][C]      ONE TMA box (64 words, 8+2, TH/kCG+2, 1) per (tile, 64-channel block): the
+//             CTA's pixels plus a one-pixel halo (image border = TMA out-of-bounds zero fill).  It is expanded
+//             ONCE into a halo'd spike tile with rows ordered (halo row, t, halo column); the 9 taps of the
+//             3x3 conv are 9 MMA descriptors into that same tile: start row (dy * T_box * 10 + dx), 8-row
+//             groups 10 rows (1280 B) apart.  This relies on the 128-byte swizzle of tcgen05.mma following
+//             ABSOLUTE shared-memory address bits (scratch/swizzle_experiment.py: any 128-B row start and
+//             group stride works with base_offset 0), so the producers swizzle by the absolute row address.
+//    The word tile of a stage is 1-3 KB per CTA, so the L2->SM feed of the kernel is the weight tiles alone,
+//    and the expansion work of the conv is 40/16 halo overhead x 1/9 = 0.28 of expanding every tap.
 //  * accumulators: 2 x 256 TMEM columns (double buffered) -> the MMA of tile i+1 overlaps the
 //    LIF epilogue of tile i.  The LIF state (v, i) never leaves registers; nothing of size
 //    T x state is ever written to HBM.  Output per neuron: one time-packed spike-train word
@@ -38,8 +43,8 @@
 namespace snn {
 
 constexpr int kMaxLevels = 8;
-constexpr int kStagesA = 6;                 // 16 KB each
-constexpr int kMaxStagesB = 6;              // ring of p.stages_b slots of p.slot_b bytes, 80 KB in total
+constexpr int kStagesA = 6;                 // weight ring: up to 6 stages of 16 KB (p.stages_a; fewer when one spike tile needs > 80 KB)
+constexpr int kMaxStagesB = 6;              // ring of p.stages_b slots of p.slot_b bytes; weight + spike rings share 176 KB
 constexpr int kMaxStagesW = 8;              // ring of p.stages_w slots of p.slot_w bytes, 16 KB in total
 constexpr int kTileBytesA = 128 * 128;      // 128 rows x 64 16-bit
 constexpr int kRingBytesB = 80 * 1024;
@@ -80,8 +85,10 @@ struct GemmLifParams {
     int total_tiles, unit_tiles;
     int train_bytes;          // output word size: 1, 2 or 4
     int in_wb, in_bit0;       // input word size; bit of the input word that is step t0 of this layer
+    int stages_a;             // weight ring stages (<= kStagesA)
     int stages_b, slot_b;     // B ring geometry
     int stages_w, slot_w;     // word ring geometry (slot = Jh units x 64 words)
+    int hrows;                // conv: halo rows per CTA = TH / kCG + 2 (halo columns = TWh + 2 = 10)
     int n_pg;                 // producer groups (each owns every n_pg-th k-block): min(4, stages_b, stages_w) rounded to 1/2/4
     int n_mma;                // T_box * J
     uint32_t idesc;
@@ -89,7 +96,7 @@ struct GemmLifParams {
     uint32_t spike_one;       // 1.0 as bf16 (0x3F80) or fp16 (0x3C00)
     const float* w_scale;     // [m_total] power of two each accumulator row is multiplied with (1 for bf16 pieces)
     float* dump;              // debug (fc only): raw currents [T_live][rows][m_total]
-    int dbg_shift, dbg_sbo, dbg_boff;   // swizzle experiment (scratch/swizzle_experiment.py): row shift, group stride, base-offset field
+    int dbg_shift, dbg_sbo, dbg_boff;   // swizzle experiment (scratch/swizzle_experiment.py, fc only): row shift, group stride, base-offset field
     // fused leaky-integrator readout (conv, cta_group 2, m_total == 256): mem_{T-1} = W . sum_t kappa_{T-1-t} spk_t
     int fuse_readout, A;
     const float* w_cls;       // [A][m_total]
@@ -133,8 +140,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
-    uint8_t* b_ring = smem + kStagesA * kTileBytesA;
-    uint8_t* w_ring = b_ring + kRingBytesB;
+    const int stages_a = p.stages_a;
+    uint8_t* b_ring = smem + stages_a * kTileBytesA;
+    uint8_t* w_ring = smem + kStagesA * kTileBytesA + kRingBytesB;
     uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + kRingBytesW);
     uint64_t* a_full = bars;                         // [kStagesA]   weight tile landed (TMA tx, leader CTA)
     uint64_t* a_empty = a_full + kStagesA;           // [kStagesA]   MMAs reading it retired
@@ -175,6 +183,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
     const uint32_t tmem_base = *tmem_slot;
 
     const int n_half = p.n_mma / kCG;                 // B rows (= accumulator columns) produced per CTA
+    // spike-tile ring stages per tile, and MMA k-blocks per stage: fc one k-block per stage; conv one stage per
+    // 64-channel block, read by the 9 taps
+    const int n_outer = kConv ? p.cblocks : p.kblocks;
+    const int n_inner = kConv ? 9 : 1;
 
     if (warp == 0) {
         // ===================================================== TMA producer (weight tiles)
@@ -183,14 +195,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             for (int tile = group; tile < p.total_tiles; tile += n_groups) {
                 const int ut = tile / p.m_tiles, mt = tile - ut * p.m_tiles;
                 const int m0 = mt * 128 * kCG + static_cast<int>(rank) * 128;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    for (int s = 0; s < p.nsplit; ++s) {
-                        mbar_wait_parked(&a_empty[sa], pa ^ 1u);
-                        if (rank == 0) mbar_expect_tx(&a_full[sa], kTileBytesA * kCG);
-                        uint8_t* adst = a_ring + sa * kTileBytesA;
-                        if constexpr (kCG == 1) tma_load_2d(adst, &p.tmA, &a_full[sa], kb * 64, s * p.m_total + m0);
-                        else tma_load_2d_2sm(adst, &p.tmA, &a_full[sa], kb * 64, s * p.m_total + m0);
-                        if (++sa == kStagesA) { sa = 0; pa ^= 1u; }
+                // k order: fc kb = 0..K/64; conv (64-channel block outer, tap inner) -- the order the MMA issuer uses
+                for (int ko = 0; ko < n_outer; ++ko) {
+                    for (int ki = 0; ki < n_inner; ++ki) {
+                        const int kcol = kConv ? (ki * p.k_in + ko * 64) : ko * 64;
+                        for (int s = 0; s < p.nsplit; ++s) {
+                            mbar_wait_parked(&a_empty[sa], pa ^ 1u);
+                            if (rank == 0) mbar_expect_tx(&a_full[sa], kTileBytesA * kCG);
+                            uint8_t* adst = a_ring + sa * kTileBytesA;
+                            if constexpr (kCG == 1) tma_load_2d(adst, &p.tmA, &a_full[sa], kcol, s * p.m_total + m0);
+                            else tma_load_2d_2sm(adst, &p.tmA, &a_full[sa], kcol, s * p.m_total + m0);
+                            if (++sa == static_cast<uint32_t>(stages_a)) { sa = 0; pa ^= 1u; }
+                        }
                     }
                 }
             }
@@ -204,28 +220,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 256u;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
+                for (int ko = 0; ko < n_outer; ++ko) {
                     mbar_wait(&b_ready[sb], pb);
                     if constexpr (kCG == 2) mbar_wait_cluster(&b_peer[sb], pb);
                     tcgen05_fence_after();
-                    uint64_t b_desc = umma_desc_sw128(smem_u32(b_ring + sb * p.slot_b));
-                    if (p.dbg_sbo != 0) {      // swizzle experiment: shifted start, custom 8-row-group stride, base offset
-                        const uint32_t st = smem_u32(b_ring + sb * p.slot_b) + static_cast<uint32_t>(p.dbg_shift) * 128u;
-                        b_desc = static_cast<uint64_t>((st & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(1) << 16) |
-                                 (static_cast<uint64_t>(p.dbg_sbo >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
-                                 (static_cast<uint64_t>(p.dbg_boff & 7) << 49) | (static_cast<uint64_t>(2) << 61);
-                    }
-                    for (int s = 0; s < p.nsplit; ++s) {
-                        mbar_wait(&a_full[sa], pa);
-                        tcgen05_fence_after();
-                        const uint64_t a_desc = umma_desc_sw128(smem_u32(a_ring + sa * kTileBytesA));
+                    const uint32_t b_slot = smem_u32(b_ring + sb * p.slot_b);
+                    for (int ki = 0; ki < n_inner; ++ki) {
+                        uint64_t b_desc;
+                        if constexpr (kConv) {         // tap (dy, dx): shifted window of the halo'd tile
+                            const int dy = ki / 3, dx = ki - dy * 3;
+                            b_desc = umma_desc_sw128_strided(b_slot + static_cast<uint32_t>(dy * p.T_box * 10 + dx) * 128u, 1280u);
+                        } else {
+                            b_desc = umma_desc_sw128(b_slot);
+                            if (p.dbg_sbo != 0)        // swizzle experiment: shifted start, custom group stride, base offset
+                                b_desc = umma_desc_sw128_strided(b_slot + static_cast<uint32_t>(p.dbg_shift) * 128u,
+                                                                 static_cast<uint32_t>(p.dbg_sbo)) |
+                                         (static_cast<uint64_t>(p.dbg_boff & 7) << 49);
+                        }
+                        for (int s = 0; s < p.nsplit; ++s) {
+                            mbar_wait(&a_full[sa], pa);
+                            tcgen05_fence_after();
+                            const uint64_t a_desc = umma_desc_sw128(smem_u32(a_ring + sa * kTileBytesA));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)     // 4 x (K = 16 x 16-bit = 32 B) inside the 128-B swizzle span
-                            umma_f16<kCG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, p.idesc,
-                                          (kb | s | k) != 0 ? 1u : 0u);
-                        if constexpr (kCG == 1) umma_commit<1>(&a_empty[sa]);
-                        else umma_commit_2sm_mcast(&a_empty[sa], 0b11);
-                        if (++sa == kStagesA) { sa = 0; pa ^= 1u; }
+                            for (int k = 0; k < 4; ++k)     // 4 x (K = 16 x 16-bit = 32 B) inside the 128-B swizzle span
+                                umma_f16<kCG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, p.idesc,
+                                              (ko | ki | s | k) != 0 ? 1u : 0u);
+                            if constexpr (kCG == 1) umma_commit<1>(&a_empty[sa]);
+                            else umma_commit_2sm_mcast(&a_empty[sa], 0b11);
+                            if (++sa == static_cast<uint32_t>(stages_a)) { sa = 0; pa ^= 1u; }
+                        }
                     }
                     if constexpr (kCG == 1) umma_commit<1>(&b_empty[sb]);
                     else umma_commit_2sm_mcast(&b_empty[sb], 0b11);
@@ -239,7 +262,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             // of the stage is written.  The cluster-scope release costs about a microsecond; one lane per
             // stage keeps stages_b of them in flight, and none of them sits in a producer warp.
             const int my_tiles = (group < p.total_tiles) ? (p.total_tiles - group + n_groups - 1) / n_groups : 0;
-            const long long total_kb = static_cast<long long>(my_tiles) * p.kblocks;
+            const long long total_kb = static_cast<long long>(my_tiles) * n_outer;
             uint32_t pb = 0;
             for (long long i = lane; i < total_kb; i += stages_b, pb ^= 1u) {
                 mbar_wait_parked(&b_ready[lane], pb);
@@ -250,24 +273,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         // ===================================================== TMA producer (input spike-train words)
         if (elect_one()) {
             uint32_t sw = 0, pw = 0;
-            const uint32_t w_bytes = static_cast<uint32_t>(p.Jh) * 64u * static_cast<uint32_t>(p.in_wb);
+            const uint32_t w_bytes = (kConv ? static_cast<uint32_t>(p.hrows) * 10u : static_cast<uint32_t>(p.Jh)) * 64u *
+                                     static_cast<uint32_t>(p.in_wb);
             for (int tile = group; tile < p.total_tiles; tile += n_groups) {
                 const int ut = tile / p.m_tiles;
                 const TilePos tp = decode_tile(p, ut);
                 const int h0 = tp.h0 + static_cast<int>(rank) * p.sub_dh, w0 = tp.w0 + static_cast<int>(rank) * p.sub_dw;
                 const int r0 = ut * p.J + static_cast<int>(rank) * p.Jh;
-                int tap = 0, cb = 0;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
+                for (int ko = 0; ko < n_outer; ++ko) {
                     mbar_wait_parked(&w_empty[sw], pw ^ 1u);
                     mbar_expect_tx(&w_full[sw], w_bytes);
                     uint8_t* wdst = w_ring + sw * p.slot_w;
-                    if (p.conv) {
-                        const int dy = tap / 3, dx = tap - dy * 3;
-                        tma_load_4d(wdst, &p.tmW[tp.lvl], &w_full[sw], cb * 64 * p.in_wb, w0 + dx - 1, h0 + dy - 1, tp.n);
-                        if (++cb == p.cblocks) { cb = 0; ++tap; }
-                    } else {
-                        tma_load_2d(wdst, &p.tmW[0], &w_full[sw], kb * 64 * p.in_wb, r0);
-                    }
+                    if constexpr (kConv)      // the CTA's pixels + one-pixel halo of 64-channel block ko
+                        tma_load_4d(wdst, &p.tmW[tp.lvl], &w_full[sw], ko * 64 * p.in_wb, w0 - 1, h0 - 1, tp.n);
+                    else
+                        tma_load_2d(wdst, &p.tmW[0], &w_full[sw], ko * 64 * p.in_wb, r0);
                     if (++sw == static_cast<uint32_t>(stages_w)) { sw = 0; pw ^= 1u; }
                 }
             }
@@ -285,16 +305,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         const int ptid = static_cast<int>(threadIdx.x) - 256;
         const int grp = ptid / tpg;
         const int pt = ptid - grp * tpg;
-        const int n_pairs = p.Jh * 8;
+        // conv: every pixel of the halo'd region; fc: the CTA's units
+        const int n_pairs = (kConv ? p.hrows * 10 : p.Jh) * 8;
         const int wb = p.in_wb;
         const uint32_t tmask = (p.T_live >= 32) ? 0xFFFFFFFFu : ((1u << p.T_live) - 1u);
         const uint32_t pmask = tmask | (tmask << 16);
         const uint32_t one = p.spike_one;
         const bool packed = p.T_box <= 16;             // both neurons of a 32-bit output fit one register
         const int my_tiles = (group < p.total_tiles) ? (p.total_tiles - group + n_groups - 1) / n_groups : 0;
-        const long long total_kb = static_cast<long long>(my_tiles) * p.kblocks;
+        const long long total_kb = static_cast<long long>(my_tiles) * n_outer;
         const uint32_t b_base = smem_u32(b_ring), w_base = smem_u32(w_ring);
-        const uint32_t row_step = static_cast<uint32_t>(p.Jh) * 128u;
+        // row of (unit j, step t): fc t * Jh + j; conv halo pixel (hh, ww): (hh * T_box + t) * 10 + ww
+        const uint32_t row_step = (kConv ? 10u : static_cast<uint32_t>(p.Jh)) * 128u;
 
         // group g starts on stage g of both rings (n_pg <= stages, so its first phase parity is 0)
         uint32_t sb = static_cast<uint32_t>(grp), pb = 0u, sw = static_cast<uint32_t>(grp), pw = 0u;
@@ -309,7 +331,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 if (pr >= n_pairs) break;
                 const uint32_t j = pr >> 3, q = pr & 7;
                 const uint32_t src = wslot + static_cast<uint32_t>(pr) * 8u * wb;
-                uint32_t r = j, addr = slot + j * 128u;
+                uint32_t r0 = j;
+                if constexpr (kConv) { const uint32_t hh = j / 10u; r0 = hh * static_cast<uint32_t>(p.T_box) * 10u + (j - hh * 10u); }
+                uint32_t addr = slot + r0 * 128u;      // slot is 1024-B aligned: (addr >> 7) & 7 == row & 7
                 if (packed) {
                     uint32_t P[4];
                     if (wb == 1) {
@@ -331,28 +355,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                         for (int e = 0; e < 4; ++e) P[e] = (P[e] >> p.in_bit0) & pmask;
                     }
 #pragma unroll 4
-                    for (int t = 0; t < p.T_box; ++t, r += p.Jh, addr += row_step) {
+                    for (int t = 0; t < p.T_box; ++t, addr += row_step) {
                         uint4 o;
                         o.x = ((P[0] >> t) & 0x00010001u) * one; o.y = ((P[1] >> t) & 0x00010001u) * one;
                         o.z = ((P[2] >> t) & 0x00010001u) * one; o.w = ((P[3] >> t) & 0x00010001u) * one;
-                        if (p.dbg_sbo != 0) {  // swizzle experiment: absolute-address swizzle, rows in groups of 8 at stride dbg_sbo
+                        if (!kConv && p.dbg_sbo != 0) {  // swizzle experiment: rows in groups of 8 at stride dbg_sbo, shifted
+                            const uint32_t r = r0 + static_cast<uint32_t>(t * p.Jh);
                             const uint32_t ra = slot + static_cast<uint32_t>(p.dbg_shift) * 128u + (r >> 3) * p.dbg_sbo + (r & 7u) * 128u;
                             sts_v4(ra + ((q ^ ((ra >> 7) & 7u)) << 4), o);
-                        } else
-                        sts_v4(addr + ((q ^ (r & 7u)) << 4), o);
+                        } else {
+                            sts_v4(addr + ((q ^ ((addr >> 7) & 7u)) << 4), o);     // swizzle by the absolute row address
+                        }
                     }
                 } else {                           // T_box > 16: 32-bit words, one neuron per register
                     const uint4 a = lds_v4(src), c = lds_v4(src + 16u);
                     uint32_t wv[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
                     for (int e = 0; e < 8; ++e) wv[e] = (wv[e] >> p.in_bit0) & tmask;
-                    for (int t = 0; t < p.T_box; ++t, r += p.Jh, addr += row_step) {
+                    for (int t = 0; t < p.T_box; ++t, addr += row_step) {
                         uint4 o;
                         o.x = (((wv[0] >> t) & 1u) | (((wv[1] >> t) & 1u) << 16)) * one;
                         o.y = (((wv[2] >> t) & 1u) | (((wv[3] >> t) & 1u) << 16)) * one;
                         o.z = (((wv[4] >> t) & 1u) | (((wv[5] >> t) & 1u) << 16)) * one;
                         o.w = (((wv[6] >> t) & 1u) | (((wv[7] >> t) & 1u) << 16)) * one;
-                        sts_v4(addr + ((q ^ (r & 7u)) << 4), o);
+                        sts_v4(addr + ((q ^ ((addr >> 7) & 7u)) << 4), o);
                     }
                 }
             }
@@ -414,8 +440,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
 #pragma unroll
                     for (int u = 0; u < CW; ++u) { v[u] = 0.f; ii[u] = 0.f; tr[u] = 0u; sk[u] = 0.f; }
                     // ---- steps that receive an input current (the accumulator columns of this unit chunk)
-                    uint32_t col = acc + static_cast<uint32_t>(sub * n_half + j0);
-                    for (int tl = 0; tl < p.T_live; ++tl, col += p.Jh) {
+                    // accumulator column of (unit j, step t): fc t * Jh + j; conv (tile row, t, tile column)
+                    uint32_t col = acc + static_cast<uint32_t>(sub * n_half + (kConv ? (j0 >> 3) * p.T_box * 8 + (j0 & 7) : j0));
+                    const uint32_t col_step = kConv ? 8u : static_cast<uint32_t>(p.Jh);
+                    for (int tl = 0; tl < p.T_live; ++tl, col += col_step) {
                         float cu[CW];
                         tmem_ld<CW>(col, reinterpret_cast<uint32_t*>(cu));
                         tmem_ld_wait();

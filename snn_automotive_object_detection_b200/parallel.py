@@ -40,14 +40,20 @@ def gather_records(local: torch.Tensor, counts: Sequence[int]) -> torch.Tensor:
     return torch.cat([out[r, : counts[r]] for r in range(world)], dim=0)
 
 
+_DENOM_CACHE = {}
+
+
 def spike_rate_records(rpn_counts: torch.Tensor, level_sizes: Sequence[Tuple[int, int]], channels: int, T_rpn: int,
                        box_counts: torch.Tensor, rois_per_image: int, hidden: int, T_det: int) -> torch.Tensor:
     """Per-image record [n_local, levels + 2] of mean spike rates: shared_lif per FPN level, then lif6
     and lif7 averaged over the image's RoIs (the quantities train.py:482,491 reads from the reference's
     spike-rate list, indices {0,3,6,9,12} and {15,16}).  Three small device ops, no host sync."""
     L, N = rpn_counts.shape
-    denom = torch.tensor([float(h * w * channels * T_rpn) for (h, w) in level_sizes], device=rpn_counts.device,
-                         dtype=torch.float64)
+    key = (str(rpn_counts.device), tuple(level_sizes), channels, T_rpn)
+    denom = _DENOM_CACHE.get(key)
+    if denom is None:        # built once: torch.tensor(list, device=cuda) is a synchronous host->device copy
+        denom = torch.tensor([float(h * w * channels * T_rpn) for (h, w) in level_sizes], dtype=torch.float64)
+        denom = _DENOM_CACHE[key] = denom.to(rpn_counts.device)
     rpn_rates = rpn_counts.double().t() / denom                                        # [N, L]
     box_rates = box_counts.double().view(2, N, rois_per_image).sum(dim=2).t() / float(rois_per_image * hidden * T_det)
     return torch.cat([rpn_rates, box_rates], dim=1)
