@@ -83,23 +83,34 @@ __device__ __forceinline__ uint32_t encode_train(float x, int T) {
     return w;
 }
 
-// The same for N independent inputs in lock-step: one time loop, the step's bit mask computed once, N
-// dependency chains interleaved (the encoders are instruction-issue bound, not HBM bound).
-template <int N>
-__device__ __forceinline__ void encode_trains(const float (&x)[N], int T, uint32_t (&w)[N]) {
-    float v[N];
+// Eight consecutive neurons in lock-step -> their spike PLANE BYTES: byte t = the 8 neurons' spikes at step t
+// (bit k = neuron k), packed 4 steps per 32-bit word: pl[t / 4] byte (t % 4).  One time loop, 8 interleaved
+// dependency chains (the encoders are instruction-issue bound, not HBM bound); planes t >= T stay zero.
+template <int NW>
+__device__ __forceinline__ void encode_planes(const float (&x)[8], int T, uint32_t (&pl)[NW]) {
+    float v[8];
 #pragma unroll
-    for (int k = 0; k < N; ++k) { v[k] = 0.f; w[k] = 0u; }
-#pragma unroll 2
-    for (int t = 0; t < T; ++t) {
-        const uint32_t bit = 1u << t;
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-            v[k] = __fadd_rn(v[k], __fmul_rn(0.1f, __fsub_rn(x[k], v[k])));
-            const bool z = v[k] > 0.25f;
-            w[k] = z ? (w[k] | bit) : w[k];
-            v[k] = z ? 0.f : v[k];
+    for (int tq = 0; tq < NW; ++tq) {
+        uint32_t acc = 0u;
+        if (4 * tq < T) {
+#pragma unroll
+            for (int tt = 0; tt < 4; ++tt) {
+                if (4 * tq + tt < T) {
+                    uint32_t cur = 0u;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        v[k] = __fadd_rn(v[k], __fmul_rn(0.1f, __fsub_rn(x[k], v[k])));
+                        const bool z = v[k] > 0.25f;
+                        cur = z ? (cur | (1u << (8 * tt + k))) : cur;
+                        v[k] = z ? 0.f : v[k];
+                    }
+                    acc |= cur;
+                }
+            }
         }
+        pl[tq] = acc;
     }
 }
 
@@ -108,7 +119,7 @@ constexpr int kEncMaxLevels = 8;
 
 struct EncLevel {
     const float* x;             // [N][C][H][W] fp32
-    uint8_t* z;                 // [N][H][W][C] spike-train words of `wb` bytes (bit t = z_t, t < T_live)
+    uint8_t* z;                 // [N][H][W][C/8][8*wb] spike plane bytes (plane t = z_t of 8 channels, t < T_live)
     int H, W, wchunks, block_begin;
 };
 struct EncParams {
@@ -117,13 +128,15 @@ struct EncParams {
 };
 
 // All FPN levels in one launch.  One block = one (level, n, h, 32-pixel run):
-//   phase 1: coalesced 128-B reads along W (one channel per warp instruction), the encoder's T_live
-//            steps in registers, spike-train words transposed through shared memory;
-//   phase 2: NHWC words out, 16 bytes per thread (16 / 8 / 4 channels for 1- / 2- / 4-byte words): a
-//            pixel's C words are contiguous, so the block writes one contiguous run of 32 * C words.
+//   phase 1: thread = pixel (lane) x group of 8 consecutive channels: 8 coalesced 128-B row reads in flight,
+//            the encoder's T_live steps in lock-step, plane bytes to shared memory [px][C/8][Tp] (row pitch
+//            C*wb + 4 bytes: conflict-free 32-bit stores);
+//   phase 2: NHWC plane bytes out, 16 bytes per thread: a pixel's C*wb bytes are contiguous, so the block
+//            writes one contiguous run of 32 * C * wb bytes.
 // HBM traffic: 4 B read + wb B written per input neuron (the per-timestep planes never exist).
+template <int NW>
 __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant__ EncParams p) {
-    extern __shared__ uint32_t s_tr[];            // [kEncW][C + 4]
+    extern __shared__ uint32_t s_pl[];            // [kEncW][C * wb / 4 + 1] words
     int lvl = 0;
     const int bid = blockIdx.x;
     while (lvl + 1 < p.n_levels && bid >= p.lv[lvl + 1].block_begin) ++lvl;
@@ -136,75 +149,49 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
     const int C = p.C, H = L.H, W = L.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = w0 + lane;
-    const int ld = C + 4;
+    const int row_words = C * p.wb / 4;           // words of plane bytes per pixel
+    const int ld = row_words + 1;
     const float* xrow = L.x + (static_cast<size_t>(n) * C * H + h) * W + w;
     const size_t cstride = static_cast<size_t>(H) * W;
-    // 8 independent 128-byte row loads in flight per warp before the (compute-heavy) encoder steps
-    for (int c0 = warp; c0 < C; c0 += 64) {
+    for (int g = warp; g < C / 8; g += 8) {       // group of channels 8g .. 8g+7
         float xv[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int c = c0 + 8 * k;
-            xv[k] = (w < W && c < C) ? __ldg(xrow + c * cstride) : 0.f;
-        }
-        uint32_t tw[8];
-        encode_trains<8>(xv, p.T_live, tw);
+        for (int k = 0; k < 8; ++k) xv[k] = (w < W) ? __ldg(xrow + (8 * g + k) * cstride) : 0.f;
+        uint32_t pl[NW];
+        encode_planes<NW>(xv, p.T_live, pl);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int c = c0 + 8 * k;
-            if (c < C) s_tr[lane * ld + c] = tw[k];
-        }
+        for (int i = 0; i < NW; ++i) s_pl[lane * ld + g * NW + i] = pl[i];
     }
     __syncthreads();
     const int npx = min(kEncW, W - w0);
-    const int per16 = 16 / p.wb;                  // channels per 16-byte store
-    const int groups = C / per16;
-    uint8_t* dst0 = L.z + ((static_cast<size_t>(n) * H + h) * W + w0) * C * p.wb;
-    for (int idx = threadIdx.x; idx < npx * groups; idx += blockDim.x) {
-        const int px = idx / groups, g = idx - px * groups;
-        const uint32_t* src = &s_tr[px * ld + g * per16];
-        uint4 o;
-        if (p.wb == 1) {
-            uint32_t v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint4 a = *reinterpret_cast<const uint4*>(src + 4 * k);
-                v[k] = (a.x & 0xFFu) | ((a.y & 0xFFu) << 8) | ((a.z & 0xFFu) << 16) | (a.w << 24);
-            }
-            o = make_uint4(v[0], v[1], v[2], v[3]);
-        } else if (p.wb == 2) {
-            const uint4 a = *reinterpret_cast<const uint4*>(src), b = *reinterpret_cast<const uint4*>(src + 4);
-            o = make_uint4((a.x & 0xFFFFu) | (a.y << 16), (a.z & 0xFFFFu) | (a.w << 16),
-                           (b.x & 0xFFFFu) | (b.y << 16), (b.z & 0xFFFFu) | (b.w << 16));
-        } else {
-            o = *reinterpret_cast<const uint4*>(src);
-        }
-        *reinterpret_cast<uint4*>(dst0 + static_cast<size_t>(idx) * 16) = o;
+    const int q16 = row_words / 4;                // 16-byte pieces per pixel
+    uint4* dst0 = reinterpret_cast<uint4*>(L.z + ((static_cast<size_t>(n) * H + h) * W + w0) * C * p.wb);
+    for (int idx = threadIdx.x; idx < npx * q16; idx += blockDim.x) {
+        const int px = idx / q16, k4 = idx - px * q16;
+        const uint32_t* src = &s_pl[px * ld + 4 * k4];
+        dst0[idx] = make_uint4(src[0], src[1], src[2], src[3]);
     }
 }
 
-// x [R][K] fp32 -> words [R][K] of `wb` bytes; 8 consecutive k per thread (2 x float4 in, 8 words out)
+// x [R][K] fp32 -> plane bytes [R][K/8][8*wb]; one group of 8 consecutive k per thread (2 x float4 in, 8*wb bytes out)
+template <int NW>
 __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total8, int T_live,
-                                                          int wb, uint8_t* __restrict__ z) {
+                                                          uint8_t* __restrict__ z) {
 #pragma unroll 2
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
         const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
         const float xs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t tr[8];
-        encode_trains<8>(xs, T_live, tr);
-        if (wb == 1) {
-            uint2 o;
-            o.x = tr[0] | (tr[1] << 8) | (tr[2] << 16) | (tr[3] << 24);
-            o.y = tr[4] | (tr[5] << 8) | (tr[6] << 16) | (tr[7] << 24);
-            reinterpret_cast<uint2*>(z)[i] = o;
-        } else if (wb == 2) {
-            reinterpret_cast<uint4*>(z)[i] =
-                make_uint4(tr[0] | (tr[1] << 16), tr[2] | (tr[3] << 16), tr[4] | (tr[5] << 16), tr[6] | (tr[7] << 16));
+        uint32_t pl[NW];
+        encode_planes<NW>(xs, T_live, pl);
+        if constexpr (NW == 2) {
+            reinterpret_cast<uint2*>(z)[i] = make_uint2(pl[0], pl[1]);
+        } else if constexpr (NW == 4) {
+            reinterpret_cast<uint4*>(z)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         } else {
-            reinterpret_cast<uint4*>(z)[2 * i] = make_uint4(tr[0], tr[1], tr[2], tr[3]);
-            reinterpret_cast<uint4*>(z)[2 * i + 1] = make_uint4(tr[4], tr[5], tr[6], tr[7]);
+            reinterpret_cast<uint4*>(z)[2 * i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            reinterpret_cast<uint4*>(z)[2 * i + 1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
         }
     }
 }
