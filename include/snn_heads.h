@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 3
+#define SNN_ABI_VERSION 2
 
 #define SNN_MODE_FP32_EXACT 0 /* 3 bf16 pieces per weight (24 mantissa bits): the parity mode          */
 #define SNN_MODE_BF16 1       /* 1 piece: weights rounded to bf16, the throughput mode                 */
@@ -98,23 +98,19 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
                          snn_stream_t stream);
 
 /* ---- building blocks exposed for tests / profiling ---------------------------------------------------
- * Between kernels, the spikes a contraction consumes travel as bit-packed SPIKE PLANE BYTES: for every group
- * of 8 consecutive neurons Tp bytes (Tp = 8 / 16 / 32 for up to 8 / 16 / 32 steps), byte t = the 8 neurons'
- * spikes at step t (bit k = neuron 8g + k).  Layout [unit][K/8][Tp]: the same bytes per neuron
- * (Tp / 8 = 1, 2 or 4) as a per-neuron spike-train word.  The per-neuron spike-train WORDS (bit t = spike at
- * step t) remain the public spike output of a layer.
+ * Spikes travel between kernels only as time-packed spike-train WORDS: one word per neuron, bit t = spike
+ * at step t, 1 / 2 / 4 bytes for up to 8 / 16 / 32 steps.
  *
- * encoder only: x [R][K] fp32 -> z_planes [R][K/8][Tp], Tp = 8/16/32 for T_live <= 8/16/32
+ * encoder only: x [R][K] fp32 -> z_words [R][K], words of 1/2/4 bytes for T_live <= 8/16/32, bit t = z_t
  * (Norse lif_current_encoder, faster_rcnn.py:494). */
-int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_planes, snn_stream_t stream);
-/* one fully-connected spiking layer: z_planes [R][K/8][8*in_word_bytes] whose plane (in_bit0 + i) is the input
- * spike injected at step t0 + i (i < T_live; other planes are ignored); w_prep [pieces][M][K] + scales; runs
- * the LIF recurrence for steps 0..T-1 and writes trains [R][M] (words of snn_train_word_bytes(T)); optional
- * planes_out [R][M/8][8*snn_train_word_bytes(T)] (this layer's spikes as the next layer's input) and raw
- * currents dump [T_live][R][M] fp32.  cta_group 1 or 2 (0 = auto). */
-int snn_fc_lif_layer(const void* z_planes, int in_word_bytes, int in_bit0, int R, int K, int M, int T, int t0,
-                     int T_live, int mode, const void* w_prep, void* trains, void* planes_out, float* dump,
-                     int cta_group, snn_stream_t stream);
+int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_words, snn_stream_t stream);
+/* one fully-connected spiking layer: z_words [R][K] input spike-train words of `in_word_bytes` bytes whose
+ * bit (in_bit0 + i) is the input spike injected at step t0 + i (i < T_live); w_prep [pieces][M][K] + scales;
+ * runs the LIF recurrence for steps 0..T-1 and writes trains [R][M] (words of snn_train_word_bytes(T));
+ * optional raw currents dump [T_live][R][M] fp32.  cta_group 1 or 2 (0 = auto). */
+int snn_fc_lif_layer(const void* z_words, int in_word_bytes, int in_bit0, int R, int K, int M, int T, int t0,
+                     int T_live, int mode, const void* w_prep, void* trains, float* dump, int cta_group,
+                     snn_stream_t stream);
 
 /* number of kernels the last forward call on this thread enqueued (for bench accounting) */
 int snn_last_launch_count(void);

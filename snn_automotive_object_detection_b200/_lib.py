@@ -48,7 +48,7 @@ def _declare(lib):
     lib.snn_box_head_workspace_bytes.argtypes = [i, i, i, i, i]; lib.snn_box_head_workspace_bytes.restype = sz
     lib.snn_box_head_forward.argtypes = [vp, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.snn_box_head_forward.restype = i
-    lib.snn_fc_lif_layer.argtypes = [vp, i, i, i, i, i, i, i, i, i, vp, vp, vp, vp, i, vp]; lib.snn_fc_lif_layer.restype = i
+    lib.snn_fc_lif_layer.argtypes = [vp, i, i, i, i, i, i, i, i, i, vp, vp, vp, i, vp]; lib.snn_fc_lif_layer.restype = i
     lib.snn_encode_rows.argtypes = [vp, i, i, i, vp, vp]; lib.snn_encode_rows.restype = i
     lib.snn_last_launch_count.restype = i
     lib.snn_set_cta_group.argtypes = [i]; lib.snn_set_cta_group.restype = None

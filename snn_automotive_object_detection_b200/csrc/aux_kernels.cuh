@@ -83,34 +83,23 @@ __device__ __forceinline__ uint32_t encode_train(float x, int T) {
     return w;
 }
 
-// Eight consecutive neurons in lock-step -> their spike PLANE BYTES: byte t = the 8 neurons' spikes at step t
-// (bit k = neuron k), packed 4 steps per 32-bit word: pl[t / 4] byte (t % 4).  One time loop, 8 interleaved
-// dependency chains (the encoders are instruction-issue bound, not HBM bound); planes t >= T stay zero.
-template <int NW>
-__device__ __forceinline__ void encode_planes(const float (&x)[8], int T, uint32_t (&pl)[NW]) {
-    float v[8];
+// The same for N independent inputs in lock-step: one time loop, the step's bit mask computed once, N
+// dependency chains interleaved (the encoders are instruction-issue bound, not HBM bound).
+template <int N>
+__device__ __forceinline__ void encode_trains(const float (&x)[N], int T, uint32_t (&w)[N]) {
+    float v[N];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    for (int k = 0; k < N; ++k) { v[k] = 0.f; w[k] = 0u; }
+#pragma unroll 2
+    for (int t = 0; t < T; ++t) {
+        const uint32_t bit = 1u << t;
 #pragma unroll
-    for (int tq = 0; tq < NW; ++tq) {
-        uint32_t acc = 0u;
-        if (4 * tq < T) {
-#pragma unroll
-            for (int tt = 0; tt < 4; ++tt) {
-                if (4 * tq + tt < T) {
-                    uint32_t cur = 0u;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        v[k] = __fadd_rn(v[k], __fmul_rn(0.1f, __fsub_rn(x[k], v[k])));
-                        const bool z = v[k] > 0.25f;
-                        cur = z ? (cur | (1u << (8 * tt + k))) : cur;
-                        v[k] = z ? 0.f : v[k];
-                    }
-                    acc |= cur;
-                }
-            }
+        for (int k = 0; k < N; ++k) {
+            v[k] = __fadd_rn(v[k], __fmul_rn(0.1f, __fsub_rn(x[k], v[k])));
+            const bool z = v[k] > 0.25f;
+            w[k] = z ? (w[k] | bit) : w[k];
+            v[k] = z ? 0.f : v[k];
         }
-        pl[tq] = acc;
     }
 }
 
@@ -119,7 +108,7 @@ constexpr int kEncMaxLevels = 8;
 
 struct EncLevel {
     const float* x;             // [N][C][H][W] fp32
-    uint8_t* z;                 // [N][H][W][C/8][8*wb] spike plane bytes (plane t = z_t of 8 channels, t < T_live)
+    uint8_t* z;                 // [N][H][W][C] spike-train words of `wb` bytes (bit t = z_t, t < T_live)
     int H, W, wchunks, block_begin;
 };
 struct EncParams {
@@ -128,15 +117,14 @@ struct EncParams {
 };
 
 // All FPN levels in one launch.  One block = one (level, n, h, 32-pixel run):
-//   phase 1: thread = pixel (lane) x group of 8 consecutive channels: 8 coalesced 128-B row reads in flight,
-//            the encoder's T_live steps in lock-step, plane bytes to shared memory [px][C/8][Tp] (row pitch
-//            C*wb + 4 bytes: conflict-free 32-bit stores);
-//   phase 2: NHWC plane bytes out, 16 bytes per thread: a pixel's C*wb bytes are contiguous, so the block
-//            writes one contiguous run of 32 * C * wb bytes.
+//   phase 1: thread = pixel (lane) x 8 consecutive channels: 8 coalesced 128-B row reads in flight, the
+//            encoder's T_live steps for the 8 neurons in lock-step, their words packed to shared memory
+//            [px][C words] (row pitch C*wb + 4 bytes: conflict-free 32-bit stores);
+//   phase 2: NHWC words out, 16 bytes per thread: a pixel's C words are contiguous, so the block writes one
+//            contiguous run of 32 * C words.
 // HBM traffic: 4 B read + wb B written per input neuron (the per-timestep planes never exist).
-template <int NW>
 __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant__ EncParams p) {
-    extern __shared__ uint32_t s_pl[];            // [kEncW][C * wb / 4 + 1] words
+    extern __shared__ uint32_t s_tr[];            // [kEncW][C * wb / 4 + 1] 32-bit words of packed spike-train words
     int lvl = 0;
     const int bid = blockIdx.x;
     while (lvl + 1 < p.n_levels && bid >= p.lv[lvl + 1].block_begin) ++lvl;
@@ -149,18 +137,28 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
     const int C = p.C, H = L.H, W = L.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = w0 + lane;
-    const int row_words = C * p.wb / 4;           // words of plane bytes per pixel
+    const int row_words = C * p.wb / 4;           // 32-bit words per pixel
     const int ld = row_words + 1;
+    const int gw = 2 * p.wb;                      // 32-bit words per group of 8 channels
     const float* xrow = L.x + (static_cast<size_t>(n) * C * H + h) * W + w;
     const size_t cstride = static_cast<size_t>(H) * W;
-    for (int g = warp; g < C / 8; g += 8) {       // group of channels 8g .. 8g+7
+    for (int g = warp; g < C / 8; g += 8) {       // channels 8g .. 8g+7
         float xv[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) xv[k] = (w < W) ? __ldg(xrow + (8 * g + k) * cstride) : 0.f;
-        uint32_t pl[NW];
-        encode_planes<NW>(xv, p.T_live, pl);
+        uint32_t tw[8];
+        encode_trains<8>(xv, p.T_live, tw);
+        uint32_t* dst = &s_tr[lane * ld + g * gw];
+        if (p.wb == 1) {
+            dst[0] = tw[0] | (tw[1] << 8) | (tw[2] << 16) | (tw[3] << 24);
+            dst[1] = tw[4] | (tw[5] << 8) | (tw[6] << 16) | (tw[7] << 24);
+        } else if (p.wb == 2) {
 #pragma unroll
-        for (int i = 0; i < NW; ++i) s_pl[lane * ld + g * NW + i] = pl[i];
+            for (int k = 0; k < 4; ++k) dst[k] = tw[2 * k] | (tw[2 * k + 1] << 16);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dst[k] = tw[k];
+        }
     }
     __syncthreads();
     const int npx = min(kEncW, W - w0);
@@ -168,30 +166,33 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
     uint4* dst0 = reinterpret_cast<uint4*>(L.z + ((static_cast<size_t>(n) * H + h) * W + w0) * C * p.wb);
     for (int idx = threadIdx.x; idx < npx * q16; idx += blockDim.x) {
         const int px = idx / q16, k4 = idx - px * q16;
-        const uint32_t* src = &s_pl[px * ld + 4 * k4];
+        const uint32_t* src = &s_tr[px * ld + 4 * k4];
         dst0[idx] = make_uint4(src[0], src[1], src[2], src[3]);
     }
 }
 
-// x [R][K] fp32 -> plane bytes [R][K/8][8*wb]; one group of 8 consecutive k per thread (2 x float4 in, 8*wb bytes out)
-template <int NW>
+// x [R][K] fp32 -> words [R][K] of `wb` bytes; 8 consecutive k per thread (2 x float4 in, 8 words out)
 __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total8, int T_live,
-                                                          uint8_t* __restrict__ z) {
+                                                          int wb, uint8_t* __restrict__ z) {
 #pragma unroll 2
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
         const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
         const float xs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t pl[NW];
-        encode_planes<NW>(xs, T_live, pl);
-        if constexpr (NW == 2) {
-            reinterpret_cast<uint2*>(z)[i] = make_uint2(pl[0], pl[1]);
-        } else if constexpr (NW == 4) {
-            reinterpret_cast<uint4*>(z)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        uint32_t tr[8];
+        encode_trains<8>(xs, T_live, tr);
+        if (wb == 1) {
+            uint2 o;
+            o.x = tr[0] | (tr[1] << 8) | (tr[2] << 16) | (tr[3] << 24);
+            o.y = tr[4] | (tr[5] << 8) | (tr[6] << 16) | (tr[7] << 24);
+            reinterpret_cast<uint2*>(z)[i] = o;
+        } else if (wb == 2) {
+            reinterpret_cast<uint4*>(z)[i] =
+                make_uint4(tr[0] | (tr[1] << 16), tr[2] | (tr[3] << 16), tr[4] | (tr[5] << 16), tr[6] | (tr[7] << 16));
         } else {
-            reinterpret_cast<uint4*>(z)[2 * i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-            reinterpret_cast<uint4*>(z)[2 * i + 1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+            reinterpret_cast<uint4*>(z)[2 * i] = make_uint4(tr[0], tr[1], tr[2], tr[3]);
+            reinterpret_cast<uint4*>(z)[2 * i + 1] = make_uint4(tr[4], tr[5], tr[6], tr[7]);
         }
     }
 }

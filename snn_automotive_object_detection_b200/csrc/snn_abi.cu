@@ -21,7 +21,6 @@ namespace {
 thread_local std::string g_err;
 thread_local int g_launches = 0;
 thread_local int g_force_cg = 0;
-thread_local unsigned long long* g_dbg_times = nullptr;
 
 // Optional per-phase device timing (CUDA events recorded on the launch stream around each phase).
 enum Phase { PH_ENC_RPN = 0, PH_GEMM_RPN, PH_RO_RPN, PH_ENC_BOX, PH_GEMM_FC6, PH_GEMM_FC7, PH_RO_BOX, PH_COUNT };
@@ -192,7 +191,6 @@ cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_
 int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int mode, cudaStream_t st) {
     p.J = tc.J; p.Jh = tc.Jh; p.TW = tc.TW; p.TH = tc.TH; p.TWh = tc.TWh; p.THh = tc.THh;
     p.sub_dw = tc.dw; p.sub_dh = tc.dh; p.T_box = tc.T_box; p.n_mma = tc.n_mma;
-    p.dbg_times = g_dbg_times;
     p.idesc = umma_idesc_f16(128 * tc.cg, tc.n_mma, !is_fp16(mode));
     p.spike_one = one_of(mode);
     if (p.conv) {    // one halo'd spike tile per 64-channel block: (TH/cg + 2) x T_box x (8 + 2) rows of 128 B
@@ -210,7 +208,6 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
         if (p.stages_a < 2) return fail(SNN_E_ARG, "spike tile of %d bytes does not fit shared memory", p.slot_b);
         if (p.stages_a > kStagesA) p.stages_a = kStagesA;
     }
-    if (getenv("SNN_DBG_RELAXED_RELAY")) p.dbg_boff = 99;      // experiment: relay without the cluster-scope release
     if (const char* e = getenv("SNN_DBG_SWIZZLE")) {       // "shift,sbo,boff" -- scratch/swizzle_experiment.py only
         int a = 0, b = 0, c = 0;
         if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && b >= 1024) {
@@ -287,7 +284,7 @@ int rpn_ws_layout(const int* H, const int* W, int L, int N, int C, int T, int mo
     return SNN_OK;
 }
 
-struct BoxWs { size_t z_off, p6_off, tr6_off, tr7_off, lut_off, total; };
+struct BoxWs { size_t z_off, tr6_off, tr7_off, lut_off, total; };
 
 int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, TileCfg& t6, TileCfg& t7) {
     if (T < 3 || T > 32) return fail(SNN_E_ARG, "num_steps %d outside [3,32]", T);
@@ -303,8 +300,7 @@ int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, 
     if (!pick_tile(T - 2, false, Hd, g_force_cg, t7)) return fail(SNN_E_ARG, "no tile shape for T=%d", T);
     const int tb = snn_train_word_bytes(T);
     size_t off = 0;
-    ws.z_off = off; off = align_up(off + static_cast<size_t>(R) * K * word_bytes(T - 1), 1024);   // encoder plane bytes
-    ws.p6_off = off; off = align_up(off + static_cast<size_t>(R) * Hd * tb, 1024);                 // lif6 plane bytes (fc7's input)
+    ws.z_off = off; off = align_up(off + static_cast<size_t>(R) * K * word_bytes(T - 1), 1024);   // encoder words
     ws.tr6_off = off; off = align_up(off + static_cast<size_t>(R) * Hd * tb, 1024);
     ws.tr7_off = off; off = align_up(off + static_cast<size_t>(R) * Hd * tb, 1024);
     ws.lut_off = off; off += kMaxTrainBytes * 256 * sizeof(float);
@@ -313,8 +309,7 @@ int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, 
 }
 
 int fc_layer(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, int R, int K, int M, int T, int t0,
-             int T_live, int mode, const void* w_prep, void* trains, void* planes_out, float* dump, const TileCfg& tc,
-             cudaStream_t st) {
+             int T_live, int mode, const void* w_prep, void* trains, float* dump, const TileCfg& tc, cudaStream_t st) {
     GemmLifParams p;
     memset(&p, 0, sizeof(p));
     const int nsplit = nsplit_of(mode);
@@ -340,15 +335,8 @@ int fc_layer(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, 
         if (rc) return rc;
     }
     p.trains = trains;
-    p.planes_out = reinterpret_cast<uint8_t*>(planes_out);
     p.dump = dump;
     return launch_gemm(p, tc, di, mode, st);
-}
-
-void launch_encode_rows(const float* x, size_t total8, int T_live, int wb, uint8_t* z, int blocks, cudaStream_t st) {
-    if (wb == 1) encode_rows_kernel<2><<<blocks, 256, 0, st>>>(x, total8, T_live, z);
-    else if (wb == 2) encode_rows_kernel<4><<<blocks, 256, 0, st>>>(x, total8, T_live, z);
-    else encode_rows_kernel<8><<<blocks, 256, 0, st>>>(x, total8, T_live, z);
 }
 
 template <typename T>
@@ -386,8 +374,6 @@ extern "C" {
 int snn_version(void) { return SNN_ABI_VERSION; }
 const char* snn_last_error(void) { return g_err.c_str(); }
 int snn_last_launch_count(void) { return g_launches; }
-/* debug: per-CTA cycle counters of the next spike GEMM launches (148 x 8 u64), see spike_gemm_lif.cuh */
-void snn_debug_set_times(void* ptr) { g_dbg_times = reinterpret_cast<unsigned long long*>(ptr); }
 void snn_set_cta_group(int cg) { g_force_cg = (cg == 1 || cg == 2) ? cg : 0; }
 int snn_train_word_bytes(int T) { return T <= 8 ? 1 : T <= 16 ? 2 : 4; }
 int snn_mode_pieces(int mode) { return nsplit_of(mode); }
@@ -478,10 +464,9 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
             }
             ep.n_levels = n_levels; ep.N = N; ep.C = C_in; ep.T_live = T_live; ep.wb = word_bytes(T_live); ep.total_blocks = blocks;
             const size_t smem = static_cast<size_t>(kEncW) * (C_in * ep.wb / 4 + 1) * 4;
-            if (smem > 48 * 1024) return fail(SNN_E_ARG, "in_channels %d too large for the encoder tile", C_in);
-            if (ep.wb == 1) encode_nchw_kernel<2><<<blocks, 256, smem, st>>>(ep);
-            else if (ep.wb == 2) encode_nchw_kernel<4><<<blocks, 256, smem, st>>>(ep);
-            else encode_nchw_kernel<8><<<blocks, 256, smem, st>>>(ep);
+            if (smem > 48 * 1024)
+                CUDA_TRY(cudaFuncSetAttribute(encode_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            encode_nchw_kernel<<<blocks, 256, smem, st>>>(ep);
             CUDA_TRY(cudaGetLastError()); ++g_launches;
         }
         phase_end(PH_ENC_RPN, st);
@@ -604,19 +589,18 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
         const size_t total8 = static_cast<size_t>(R) * K / 8;
         const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
         phase_begin(PH_ENC_BOX, st);
-        launch_encode_rows(reinterpret_cast<const float*>(x), total8, T_live6, word_bytes(T - 1), reinterpret_cast<uint8_t*>(z),
-                           blocks, st);
+        encode_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), total8, T_live6, word_bytes(T - 1),
+                                                   reinterpret_cast<uint8_t*>(z));
         phase_end(PH_ENC_BOX, st);
         CUDA_TRY(cudaGetLastError()); ++g_launches;
     }
     phase_begin(PH_GEMM_FC6, st);
-    void* p6 = wsp + ws.p6_off;
-    rc = fc_layer(di, z, word_bytes(T - 1), 0, R, K, Hdim, T, 0, T_live6, mode, w6_prep, tr6, p6, nullptr, t6, st);
+    rc = fc_layer(di, z, word_bytes(T - 1), 0, R, K, Hdim, T, 0, T_live6, mode, w6_prep, tr6, nullptr, t6, st);
     phase_end(PH_GEMM_FC6, st);
     if (rc) return rc;
     phase_begin(PH_GEMM_FC7, st);
-    // fc7 contracts lif6's spike plane bytes directly: its step t0 = 1 is plane 1
-    rc = fc_layer(di, p6, tb, 1, R, Hdim, Hdim, T, 1, T_live7, mode, w7_prep, tr7, nullptr, nullptr, t7, st);
+    // fc7 contracts lif6's spike-train words directly: its step t0 = 1 is bit 1 of the word
+    rc = fc_layer(di, tr6, tb, 1, R, Hdim, Hdim, T, 1, T_live7, mode, w7_prep, tr7, nullptr, t7, st);
     phase_end(PH_GEMM_FC7, st);
     if (rc) return rc;
     phase_begin(PH_RO_BOX, st);
@@ -653,33 +637,34 @@ int snn_profile_read(float* ms_out, int* counts_out) {
     return SNN_OK;
 }
 
-int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_planes, snn_stream_t stream) {
-    if (!x || !z_planes || R < 1 || K % 8 != 0 || T_live < 1 || T_live > 32)
+int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_words, snn_stream_t stream) {
+    if (!x || !z_words || R < 1 || K % 8 != 0 || T_live < 1 || T_live > 32)
         return fail(SNN_E_ARG, "encode_rows: bad argument");
     const size_t total8 = static_cast<size_t>(R) * K / 8;
     const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
-    launch_encode_rows(x, total8, T_live, word_bytes(T_live), reinterpret_cast<uint8_t*>(z_planes), blocks, (cudaStream_t)stream);
+    encode_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, total8, T_live, word_bytes(T_live),
+                                                                 reinterpret_cast<uint8_t*>(z_words));
     CUDA_TRY(cudaGetLastError());
     return SNN_OK;
 }
 
-int snn_fc_lif_layer(const void* z_planes, int in_word_bytes, int in_bit0, int R, int K, int M, int T, int t0,
-                     int T_live, int mode, const void* w_prep, void* trains, void* planes_out, float* dump,
-                     int cta_group, snn_stream_t stream) {
+int snn_fc_lif_layer(const void* z_words, int in_word_bytes, int in_bit0, int R, int K, int M, int T, int t0,
+                     int T_live, int mode, const void* w_prep, void* trains, float* dump, int cta_group,
+                     snn_stream_t stream) {
     g_launches = 0;
-    if (!z_planes || !w_prep || !trains) return fail(SNN_E_ARG, "fc_lif_layer: null argument");
+    if (!z_words || !w_prep || !trains) return fail(SNN_E_ARG, "fc_lif_layer: null argument");
     if (K % 64 != 0 || M % 128 != 0 || R < 1 || T < 1 || T > 32 || T_live < 1 || t0 < 0 || t0 + T_live > T)
         return fail(SNN_E_ARG, "fc_lif_layer: unsupported shape R=%d K=%d M=%d T=%d t0=%d T_live=%d", R, K, M, T, t0, T_live);
     if ((in_word_bytes != 1 && in_word_bytes != 2 && in_word_bytes != 4) || in_bit0 < 0 ||
         in_bit0 + T_live > 8 * in_word_bytes)
-        return fail(SNN_E_ARG, "fc_lif_layer: %d steps from plane %d do not fit %d planes", T_live, in_bit0, 8 * in_word_bytes);
+        return fail(SNN_E_ARG, "fc_lif_layer: %d steps from bit %d do not fit %d-byte words", T_live, in_bit0, in_word_bytes);
     if (nsplit_of(mode) == 0) return fail(SNN_E_ARG, "unknown mode %d", mode);
     DeviceInfo di;
     int rc = device_info(di);
     if (rc) return rc;
     TileCfg tc;
     if (!pick_tile(T_live, false, M, cta_group, tc)) return fail(SNN_E_ARG, "no tile shape for T_live=%d cta_group=%d", T_live, cta_group);
-    return fc_layer(di, z_planes, in_word_bytes, in_bit0, R, K, M, T, t0, T_live, mode, w_prep, trains, planes_out, dump, tc,
+    return fc_layer(di, z_words, in_word_bytes, in_bit0, R, K, M, T, t0, T_live, mode, w_prep, trains, dump, tc,
                     (cudaStream_t)stream);
 }
 

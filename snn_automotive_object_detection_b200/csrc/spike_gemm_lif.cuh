@@ -13,14 +13,12 @@
 //    operand is exactly {0,1} every product is exact and the pieces are simply extra k-steps.
 //    fp16 modes keep 1 or 2 fp16 pieces of the power-of-two row-scaled weight (11 bits each) and
 //    the epilogue multiplies the accumulator row by the inverse scale (exact).
-//  * B operand  = input spikes.  They live in HBM ONLY as bit-packed "spike plane bytes": for every group of
-//    8 consecutive input neurons Tp bytes (Tp = 8, 16 or 32), byte t = the 8 neurons' spikes at step t
-//    (the encoder's output, or the previous layer's epilogue output) -- 1-4 bits per neuron-step instead of
-//    one 16-bit plane per timestep.  Eight producer warps expand them into the 128-byte-swizzled K-major
-//    tile the tensor core reads with ONE 16-byte table lookup + ONE 16-byte store per (8 neurons, step)
-//    (256-entry table byte -> eight 16-bit {0,1} values in shared memory).  Rows are ordered (t, unit): ALL
-//    timesteps of a unit sit in the same accumulator tile, time folded into the MMA N dimension,
-//    N = T_box * J <= 256:
+//  * B operand  = input spikes.  They live in HBM ONLY as time-packed spike-train words (one word
+//    per input neuron, bit t = spike at step t: the encoder's output, or the previous layer's
+//    epilogue output) -- 1-2 bytes per neuron instead of one 16-bit plane per timestep.  Four
+//    producer warps expand the words of a k-block into the 128-byte-swizzled K-major tile the
+//    tensor core reads (rows ordered (t, unit): ALL timesteps of a unit sit in the same
+//    accumulator tile, time folded into the MMA N dimension, N = T_box * J <= 256):
 //      fc   : words [R][K]            TMA box (64 words, Jh rows) per k-block; one spike tile per k-block.
 //      conv : words [N][H][W][C]      ONE TMA box (64 words, 8+2, TH/kCG+2, 1) per (tile, 64-channel block): the
 //             CTA's pixels plus a one-pixel halo (image border = TMA out-of-bounds zero fill).  It is expanded
@@ -47,12 +45,11 @@ namespace snn {
 constexpr int kMaxLevels = 8;
 constexpr int kStagesA = 6;                 // weight ring: up to 6 stages of 16 KB (p.stages_a; fewer when one spike tile needs > 80 KB)
 constexpr int kMaxStagesB = 6;              // ring of p.stages_b slots of p.slot_b bytes; weight + spike rings share 176 KB
-constexpr int kMaxStagesW = 16;             // ring of p.stages_w slots of p.slot_w bytes, 16 KB in total
+constexpr int kMaxStagesW = 8;              // ring of p.stages_w slots of p.slot_w bytes, 16 KB in total
 constexpr int kTileBytesA = 128 * 128;      // 128 rows x 64 16-bit
 constexpr int kRingBytesB = 80 * 1024;
 constexpr int kRingBytesW = 16 * 1024;
-constexpr int kBarBytes = 1024;
-constexpr int kLutBytes = 256 * 16;         // byte of 8 spikes -> eight 16-bit {0,1} values
+constexpr int kBarBytes = 512;
 constexpr int kEpiGroups = 1;               // LIF epilogue warp groups (4 warps each): warps 4-7 (+ 16-19)
 constexpr int kGemmThreads = 512 + (kEpiGroups - 1) * 128;   // warps 0-3 control, 4-7 epilogue, 8-15 spike-tile producers
 constexpr int kProducerWarps = 8;           // split into p.n_pg groups (1, 2 or 4); group g expands the k-blocks i = g (mod n_pg)
@@ -62,7 +59,7 @@ constexpr int kRoMaxOut = 16;               // fused readout: objectness + box d
 constexpr int kRoWStride = 132;             // floats per readout-weight row in smem (128 + pad, 16-B aligned)
 constexpr int kRoSmemBytes = kRoMaxOut * kRoWStride * 4 + kEpiGroups * 2 * 8 * kRoWStride * 4;   // weights + per epilogue group 2 x [8 px][128 ch] sums
 constexpr size_t kGemmSmemBytes =
-    1024 /*align slack*/ + kStagesA * kTileBytesA + kRingBytesB + kRingBytesW + kBarBytes + kRoSmemBytes + kLutBytes;
+    1024 /*align slack*/ + kStagesA * kTileBytesA + kRingBytesB + kRingBytesW + kBarBytes + kRoSmemBytes;
 
 struct LevelDesc {
     int H, W, tiles_w, tiles_h;
@@ -76,7 +73,7 @@ struct LevelDesc {
 
 struct GemmLifParams {
     CUtensorMap tmA;
-    CUtensorMap tmW[kMaxLevels];   // input spike plane bytes as byte tensors: conv [N][H][W][k_in*in_wb], fc [rows][k_in*in_wb]
+    CUtensorMap tmW[kMaxLevels];   // input spike-train words as byte tensors: conv [N][H][W][k_in*in_wb], fc [rows][k_in*in_wb]
     LevelDesc lv[kMaxLevels];
     int n_levels, conv, n_images;
     int m_total, m_tiles, nsplit;
@@ -87,8 +84,7 @@ struct GemmLifParams {
     int rows;                 // fc: number of units (RoIs)
     int total_tiles, unit_tiles;
     int train_bytes;          // output word size: 1, 2 or 4
-    int in_wb, in_bit0;       // input: Tp / 8 (bytes per neuron); plane index that is step t0 of this layer
-    uint8_t* planes_out;      // fc, nullable: this layer's spikes as plane bytes [rows][m_total/8][8*train_bytes] (next layer's input)
+    int in_wb, in_bit0;       // input word size; bit of the input word that is step t0 of this layer
     int stages_a;             // weight ring stages (<= kStagesA)
     int stages_b, slot_b;     // B ring geometry
     int stages_w, slot_w;     // word ring geometry (slot = Jh units x 64 words)
@@ -100,7 +96,6 @@ struct GemmLifParams {
     uint32_t spike_one;       // 1.0 as bf16 (0x3F80) or fp16 (0x3C00)
     const float* w_scale;     // [m_total] power of two each accumulator row is multiplied with (1 for bf16 pieces)
     float* dump;              // debug (fc only): raw currents [T_live][rows][m_total]
-    unsigned long long* dbg_times;   // debug: per CTA 8 counters of cycles (producer warp 8: w_full wait, b_empty wait, expand, publish; MMA thread: acc wait, b wait, a wait, total)
     int dbg_shift, dbg_sbo, dbg_boff;   // swizzle experiment (scratch/swizzle_experiment.py, fc only): row shift, group stride, base-offset field
     // fused leaky-integrator readout (conv, cta_group 2, m_total == 256): mem_{T-1} = W . sum_t kappa_{T-1-t} spk_t
     int fuse_readout, A;
@@ -161,7 +156,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* ro_w = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);   // [kRoMaxOut][kRoWStride]
     float* ro_s = ro_w + kRoMaxOut * kRoWStride;                                              // [2][CW][kRoWStride]
-    uint8_t* lut = reinterpret_cast<uint8_t*>(bars) + kBarBytes + kRoSmemBytes;               // [256][16 B]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -221,22 +215,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         // ======================================================= MMA issuer
         if (rank == 0 && elect_one()) {
             uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-            const bool timing = p.dbg_times != nullptr;
-            long long ta = 0, tb_ = 0, tc_ = 0;
-            const long long tstart = timing ? clock64() : 0;
             for (int tile = group; tile < p.total_tiles; tile += n_groups, ++it) {
                 const uint32_t buf = it & 1u;
-                const long long m0_ = timing ? clock64() : 0;
                 mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);
-                if (timing) ta += clock64() - m0_;
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 256u;
                 for (int ko = 0; ko < n_outer; ++ko) {
-                    const long long m1_ = timing ? clock64() : 0;
                     mbar_wait(&b_ready[sb], pb);
-                    const long long m2_ = timing ? clock64() : 0;
                     if constexpr (kCG == 2) mbar_wait_cluster(&b_peer[sb], pb);
-                    if (timing) { const long long m3_ = clock64(); tb_ += m2_ - m1_; tc_ += m3_ - m2_; }
                     tcgen05_fence_after();
                     const uint32_t b_slot = smem_u32(b_ring + sb * p.slot_b);
                     for (int ki = 0; ki < n_inner; ++ki) {
@@ -271,10 +257,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 if constexpr (kCG == 1) umma_commit<1>(&acc_full[buf]);
                 else umma_commit_2sm_mcast(&acc_full[buf], 0b11);
             }
-            if (timing) {
-                unsigned long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 8;
-                d[4] = ta; d[5] = tb_; d[6] = tc_; d[7] = clock64() - tstart;
-            }
         } else if (kCG == 2 && rank == 1 && lane < stages_b) {
             // relay (one lane per spike-tile ring stage): tell the leader's MMA thread that this CTA's half
             // of the stage is written.  The cluster-scope release costs about a microsecond; one lane per
@@ -284,8 +266,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             uint32_t pb = 0;
             for (long long i = lane; i < total_kb; i += stages_b, pb ^= 1u) {
                 mbar_wait_parked(&b_ready[lane], pb);
-                if (p.dbg_boff == 99) mbar_arrive_cluster_relaxed(&b_peer[lane], 0);
-                else mbar_arrive_cluster(&b_peer[lane], 0);
+                mbar_arrive_cluster(&b_peer[lane], 0);
             }
         }
     } else if (warp == 3) {
@@ -312,13 +293,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             }
         }
     } else if (warp >= 8 && warp < 8 + kProducerWarps) {
-        // ============================== spike-tile producers (n_pg groups): plane bytes -> swizzled {0,1} tile
-        // The stages of this CTA's tile sequence are numbered i = 0, 1, 2, ...; producer group g expands
-        // the stages i = g (mod n_pg): input ring stage i % stages_w -> spike-tile ring stage i % stages_b.
-        // A thread owns up to kMaxPairs (unit j, 8-neuron group q) pairs; per stage, for every step t it
-        // reads the pair's plane byte, looks up its eight 16-bit values and stores the 16-byte chunk q of
-        // row r (fc: t * Jh + j; conv: the halo'd (row, t, column) order) at chunk position q ^ (r & 7) --
-        // the 128-byte swizzle by absolute row address that TMA would have produced for a K-major tile.
+        // ============================== spike-tile producers (n_pg groups): words -> swizzled {0,1} tile
+        // The k-blocks of this CTA's tile sequence are numbered i = 0, 1, 2, ...; producer group g expands
+        // the k-blocks i = g (mod n_pg): word-ring stage i % stages_w -> spike-tile ring stage i % stages_b,
+        // so n_pg stages are in production at any time.  A thread owns up to kMaxPairs (unit j, 16-byte
+        // chunk q) pairs of the CTA's half tile; per k-block it reads a pair's 8 input words and writes T_box
+        // 16-byte chunks: row r = t * Jh + j, chunk q ^ (r & 7) -- the 128-byte swizzle TMA would have
+        // produced for a K-major 16-bit tile.
         const int n_pg = p.n_pg;
         const int tpg = kProducerWarps * 32 / n_pg;    // threads per group
         const int ptid = static_cast<int>(threadIdx.x) - 256;
@@ -327,32 +308,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         // conv: every pixel of the halo'd region; fc: the CTA's units
         const int n_pairs = (kConv ? p.hrows * 10 : p.Jh) * 8;
         const int wb = p.in_wb;
+        const uint32_t tmask = (p.T_live >= 32) ? 0xFFFFFFFFu : ((1u << p.T_live) - 1u);
+        const uint32_t pmask = tmask | (tmask << 16);
+        const uint32_t one = p.spike_one;
+        const bool packed = p.T_box <= 16;             // both neurons of a 32-bit output fit one register
         const int my_tiles = (group < p.total_tiles) ? (p.total_tiles - group + n_groups - 1) / n_groups : 0;
         const long long total_kb = static_cast<long long>(my_tiles) * n_outer;
-        const uint32_t b_base = smem_u32(b_ring), w_base = smem_u32(w_ring), lut_base = smem_u32(lut);
+        const uint32_t b_base = smem_u32(b_ring), w_base = smem_u32(w_ring);
         // row of (unit j, step t): fc t * Jh + j; conv halo pixel (hh, ww): (hh * T_box + t) * 10 + ww
         const uint32_t row_step = (kConv ? 10u : static_cast<uint32_t>(p.Jh)) * 128u;
-        {   // table: byte of 8 spikes -> eight 16-bit values (1.0 in the operand format, or 0)
-            const uint32_t bv = static_cast<uint32_t>(ptid), one = p.spike_one;
-            uint4 e;
-            e.x = ((bv & 1u) ? one : 0u) | ((bv & 2u) ? one << 16 : 0u);
-            e.y = ((bv & 4u) ? one : 0u) | ((bv & 8u) ? one << 16 : 0u);
-            e.z = ((bv & 16u) ? one : 0u) | ((bv & 32u) ? one << 16 : 0u);
-            e.w = ((bv & 64u) ? one : 0u) | ((bv & 128u) ? one << 16 : 0u);
-            sts_v4(lut_base + bv * 16u, e);
-            asm volatile("bar.sync 3, 256;" ::: "memory");         // the 8 producer warps
-        }
 
         // group g starts on stage g of both rings (n_pg <= stages, so its first phase parity is 0)
         uint32_t sb = static_cast<uint32_t>(grp), pb = 0u, sw = static_cast<uint32_t>(grp), pw = 0u;
-        long long tm0 = 0, tm1 = 0, tm2 = 0, tm3 = 0;
-        const bool timing = p.dbg_times != nullptr && warp == 8 && lane == 0;
         for (long long i_kb = grp; i_kb < total_kb; i_kb += n_pg) {
-            const long long c0 = timing ? clock64() : 0;
             mbar_wait_parked(&w_full[sw], pw);
-            const long long c1 = timing ? clock64() : 0;
             mbar_wait_parked(&b_empty[sb], pb ^ 1u);
-            const long long c2 = timing ? clock64() : 0;
             const uint32_t wslot = w_base + sw * p.slot_w;
             const uint32_t slot = b_base + sb * p.slot_b;
 #pragma unroll
@@ -360,59 +330,64 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 const int pr = pt + i * tpg;
                 if (pr >= n_pairs) break;
                 const uint32_t j = pr >> 3, q = pr & 7;
-                // the pair's Tp = 8 * wb plane bytes; plane in_bit0 + t is step t of this layer
-                const uint32_t src = wslot + static_cast<uint32_t>(pr) * 8u * wb + static_cast<uint32_t>(p.in_bit0);
+                const uint32_t src = wslot + static_cast<uint32_t>(pr) * 8u * wb;
                 uint32_t r0 = j;
                 if constexpr (kConv) { const uint32_t hh = j / 10u; r0 = hh * static_cast<uint32_t>(p.T_box) * 10u + (j - hh * 10u); }
                 uint32_t addr = slot + r0 * 128u;      // slot is 1024-B aligned: (addr >> 7) & 7 == row & 7
-                // kBatch steps at a time, loads first: the plane bytes, then their table rows, then the stores (the
-                // shared-memory accesses are volatile asm, so source order is issue order; issuing the independent
-                // loads back to back overlaps their latencies instead of exposing them one by one)
-                constexpr int kBatch = 4;
-                for (int t0 = 0; t0 < p.T_box; t0 += kBatch) {
-                    uint32_t pbv[kBatch];
-                    uint4 o[kBatch];
+                if (packed) {
+                    uint32_t P[4];
+                    if (wb == 1) {
+                        const uint2 v = lds_v2(src);
+                        P[0] = __byte_perm(v.x, 0u, 0x4140); P[1] = __byte_perm(v.x, 0u, 0x4342);
+                        P[2] = __byte_perm(v.y, 0u, 0x4140); P[3] = __byte_perm(v.y, 0u, 0x4342);
+                    } else if (wb == 2) {
+                        const uint4 v = lds_v4(src);
+                        P[0] = v.x; P[1] = v.y; P[2] = v.z; P[3] = v.w;
+                    } else {
+                        const uint4 a = lds_v4(src), c = lds_v4(src + 16u);
+                        P[0] = ((a.x >> p.in_bit0) & tmask) | (((a.y >> p.in_bit0) & tmask) << 16);
+                        P[1] = ((a.z >> p.in_bit0) & tmask) | (((a.w >> p.in_bit0) & tmask) << 16);
+                        P[2] = ((c.x >> p.in_bit0) & tmask) | (((c.y >> p.in_bit0) & tmask) << 16);
+                        P[3] = ((c.z >> p.in_bit0) & tmask) | (((c.w >> p.in_bit0) & tmask) << 16);
+                    }
+                    if (wb != 4) {
 #pragma unroll
-                    for (int e = 0; e < kBatch; ++e) pbv[e] = (t0 + e < p.T_live) ? lds_u8(src + t0 + e) : 0u;
-#pragma unroll
-                    for (int e = 0; e < kBatch; ++e) {
-                        if constexpr (kConv) {       // table row: one 16-byte shared-memory load
-                            o[e] = lds_v4(lut_base + pbv[e] * 16u);
-                        } else {                     // fc is shared-memory-bandwidth bound (MMA operand reads + these stores):
-                            // expand in registers instead.  y has bit k and bit k+15 = spike k, so
-                            // (y >> 2i) & 0x00010001 is the pair (spike 2i, spike 2i+1) as two 16-bit lanes.
-                            const uint32_t y = pbv[e] * 0x8001u;
-                            o[e].x = (y & 0x00010001u) * p.spike_one;          o[e].y = ((y >> 2) & 0x00010001u) * p.spike_one;
-                            o[e].z = ((y >> 4) & 0x00010001u) * p.spike_one;   o[e].w = ((y >> 6) & 0x00010001u) * p.spike_one;
+                        for (int e = 0; e < 4; ++e) P[e] = (P[e] >> p.in_bit0) & pmask;
+                    }
+#pragma unroll 4
+                    for (int t = 0; t < p.T_box; ++t, addr += row_step) {
+                        uint4 o;
+                        o.x = ((P[0] >> t) & 0x00010001u) * one; o.y = ((P[1] >> t) & 0x00010001u) * one;
+                        o.z = ((P[2] >> t) & 0x00010001u) * one; o.w = ((P[3] >> t) & 0x00010001u) * one;
+                        if (!kConv && p.dbg_sbo != 0) {  // swizzle experiment: rows in groups of 8 at stride dbg_sbo, shifted
+                            const uint32_t r = r0 + static_cast<uint32_t>(t * p.Jh);
+                            const uint32_t ra = slot + static_cast<uint32_t>(p.dbg_shift) * 128u + (r >> 3) * p.dbg_sbo + (r & 7u) * 128u;
+                            sts_v4(ra + ((q ^ ((ra >> 7) & 7u)) << 4), o);
+                        } else {
+                            sts_v4(addr + ((q ^ ((addr >> 7) & 7u)) << 4), o);     // swizzle by the absolute row address
                         }
                     }
+                } else {                           // T_box > 16: 32-bit words, one neuron per register
+                    const uint4 a = lds_v4(src), c = lds_v4(src + 16u);
+                    uint32_t wv[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
-                    for (int e = 0; e < kBatch; ++e) {
-                        if (t0 + e < p.T_box) {
-                            if (!kConv && p.dbg_sbo != 0) {  // swizzle experiment: rows in groups of 8 at stride dbg_sbo, shifted
-                                const uint32_t r = r0 + static_cast<uint32_t>((t0 + e) * p.Jh);
-                                const uint32_t ra = slot + static_cast<uint32_t>(p.dbg_shift) * 128u + (r >> 3) * p.dbg_sbo + (r & 7u) * 128u;
-                                sts_v4(ra + ((q ^ ((ra >> 7) & 7u)) << 4), o[e]);
-                            } else {
-                                sts_v4(addr + ((q ^ ((addr >> 7) & 7u)) << 4), o[e]);     // swizzle by the absolute row address
-                            }
-                            addr += row_step;
-                        }
+                    for (int e = 0; e < 8; ++e) wv[e] = (wv[e] >> p.in_bit0) & tmask;
+                    for (int t = 0; t < p.T_box; ++t, addr += row_step) {
+                        uint4 o;
+                        o.x = (((wv[0] >> t) & 1u) | (((wv[1] >> t) & 1u) << 16)) * one;
+                        o.y = (((wv[2] >> t) & 1u) | (((wv[3] >> t) & 1u) << 16)) * one;
+                        o.z = (((wv[4] >> t) & 1u) | (((wv[5] >> t) & 1u) << 16)) * one;
+                        o.w = (((wv[6] >> t) & 1u) | (((wv[7] >> t) & 1u) << 16)) * one;
+                        sts_v4(addr + ((q ^ ((addr >> 7) & 7u)) << 4), o);
                     }
                 }
             }
-            const long long c3 = timing ? clock64() : 0;
             fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) { mbar_arrive(&b_ready[sb]); mbar_arrive(&w_empty[sw]); }
-            if (timing) { const long long c4 = clock64(); tm0 += c1 - c0; tm1 += c2 - c1; tm2 += c3 - c2; tm3 += c4 - c3; }
             // this group's next k-block is n_pg ring stages further
             sb += n_pg; if (sb >= static_cast<uint32_t>(stages_b)) { sb -= stages_b; pb ^= 1u; }
             sw += n_pg; if (sw >= static_cast<uint32_t>(stages_w)) { sw -= stages_w; pw ^= 1u; }
-        }
-        if (timing) {
-            unsigned long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 8;
-            d[0] = tm0; d[1] = tm1; d[2] = tm2; d[3] = tm3;
         }
     } else if (warp >= 4) {
         // ============================================ LIF epilogue (2 groups x 4 warps)
@@ -529,28 +504,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                                 if (p.train_bytes == 1) *dst = static_cast<uint8_t>(tr[u]);
                                 else if (p.train_bytes == 2) *reinterpret_cast<uint16_t*>(dst) = static_cast<uint16_t>(tr[u]);
                                 else *reinterpret_cast<uint32_t*>(dst) = tr[u];
-                            }
-                        }
-                    }
-                    // ---- fc: this layer's spikes as plane bytes for the next layer's producers.  A warp holds 32
-                    // consecutive channels = 4 groups of 8: one ballot per (unit, step) is the 4 plane bytes.
-                    if constexpr (!kConv) {
-                        if (p.planes_out != nullptr) {
-                            const int tp = 8 * p.train_bytes;
-                            const int gbase = (c - lane) >> 3;                   // first 8-neuron group of this warp
-#pragma unroll
-                            for (int u = 0; u < CW; ++u) {
-                                if (u >= lim) break;                             // warp-uniform
-                                uint32_t mine = 0u;
-                                for (int t = 0; t < p.T_total; ++t) {
-                                    const uint32_t bal = __ballot_sync(0xffffffffu, (tr[u] >> t) & 1u);
-                                    if (lane == t) mine = bal;
-                                }
-                                if (lane < tp) {
-                                    uint8_t* dst = p.planes_out + ((r0 + u) * (p.m_total >> 3) + gbase) * tp + lane;
-#pragma unroll
-                                    for (int g = 0; g < 4; ++g) dst[g * tp] = static_cast<uint8_t>(mine >> (8 * g));
-                                }
                             }
                         }
                     }

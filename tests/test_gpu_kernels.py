@@ -13,30 +13,21 @@ pytestmark = pytest.mark.gpu
 
 def test_library_reports_version_and_rejects_bad_args():
     lib = _lib.load()
-    assert lib.snn_version() == 3
-    rc = lib.snn_fc_lif_layer(None, 1, 0, 1, 64, 128, 8, 0, 7, 0, None, None, None, None, 0, None)
+    assert lib.snn_version() == 2
+    rc = lib.snn_fc_lif_layer(None, 1, 0, 1, 64, 128, 8, 0, 7, 0, None, None, None, 0, None)
     assert rc == -1 and b"null" in lib.snn_last_error()
 
 
-def pack_planes(z, plane0, nbytes, junk=False):
-    """[T_live, R, K] {0,1} spikes -> spike plane bytes [R, K/8, 8*nbytes] uint8: byte (plane0 + t) of group g =
-    bits of neurons 8g..8g+7 at step t.  junk=True fills every other plane with 0xFF (must be ignored)."""
-    T_live, R, K = z.shape
-    tp = 8 * nbytes
-    out = np.full((R, K // 8, tp), 255 if junk else 0, dtype=np.uint8)
-    zz = z.numpy().astype(np.uint8).reshape(T_live, R, K // 8, 8)
-    weights = (1 << np.arange(8)).astype(np.uint8)
-    for t in range(T_live):
-        out[:, :, plane0 + t] = (zz[t] * weights).sum(axis=-1).astype(np.uint8)
-    return torch.from_numpy(out)
-
-
-def unpack_planes(planes, T):
-    """plane bytes [R, K/8, Tp] uint8 -> [T, R, K] uint8 spikes."""
-    pl = planes.numpy()
-    R, G, _ = pl.shape
-    bits = ((pl[:, :, :T, None] >> np.arange(8)) & 1).astype(np.uint8)          # [R, G, T, 8]
-    return torch.from_numpy(np.ascontiguousarray(bits.transpose(2, 0, 1, 3).reshape(T, R, G * 8)))
+def pack_words(z, bit0, nbytes):
+    """[T_live, ...] {0,1} spikes -> spike-train words (bit bit0 + t = z[t]) of `nbytes` bytes."""
+    w = torch.zeros(z.shape[1:], dtype=torch.int64)
+    for t in range(z.shape[0]):
+        w |= z[t].to(torch.int64) << (bit0 + t)
+    if nbytes == 1:
+        return torch.from_numpy(w.numpy().astype(np.uint8))
+    if nbytes == 2:
+        return torch.from_numpy(w.numpy().astype(np.uint16).view(np.int16))
+    return torch.from_numpy(w.numpy().astype(np.uint32).view(np.int32))
 
 
 @pytest.mark.parametrize("T", [1, 7, 8, 12, 16, 17, 32])
@@ -47,12 +38,11 @@ def test_encoder_rows_bit_exact(T):
     x[0, :8] = torch.tensor([0.25, 0.2500001, 0.439, 0.44, -1.0, 0.0, 1e-30, 100.0])
     xd = x.cuda()
     wb = 1 if T <= 8 else 2 if T <= 16 else 4
-    z = torch.full((37, 192 // 8, 8 * wb), 77, dtype=torch.uint8, device="cuda")
+    z = torch.zeros(37, 192, dtype=_TRAIN_DTYPE[wb], device="cuda")
     _lib.check(lib.snn_encode_rows(vp(xd), 37, 192, T, vp(z), stream()), "encode_rows")
     torch.cuda.synchronize()
     ref = torch.stack(O.encoder_spikes(x, T))
-    assert torch.equal(unpack_planes(z.cpu(), T).float(), ref)
-    assert (z.cpu()[:, :, T:] == 0).all()                      # padding planes are written as zeros
+    assert torch.equal(unpack_trains(z.cpu(), T).float(), ref)
     assert T < 8 or ref.sum() > 0
 
 
@@ -66,20 +56,21 @@ def _fc_case(R, K, M, T, t0, T_live, mode, cg, seed=0, density=0.15, in_bit0=0, 
     if in_wb is None:
         nb = in_bit0 + T_live
         in_wb = 1 if nb <= 8 else 2 if nb <= 16 else 4
-    # planes outside [in_bit0, in_bit0 + T_live) must be ignored by the kernel: fill them with junk
-    zd = pack_planes(z, in_bit0, in_wb, junk=True).cuda()
+    words = pack_words(z, in_bit0, in_wb)
+    # bits outside [in_bit0, in_bit0 + T_live) must be ignored by the kernel: set them
+    junk = torch.full_like(words, -1) if in_wb > 1 else torch.full_like(words, 255)
+    mask = pack_words(torch.ones_like(z), in_bit0, in_wb)
+    words = words | (junk & ~mask)
+    zd = words.cuda()
     wd = w.cuda()
     wp = prepared_fc(wd, mode)
     tb = lib.snn_train_word_bytes(T)
     trains = torch.zeros(R, M, dtype=_TRAIN_DTYPE[tb], device="cuda")
     dump = torch.full((T_live, R, M), float("nan"), device="cuda")
-    planes = torch.full((R, M // 8, 8 * tb), 99, dtype=torch.uint8, device="cuda")
-    rc = lib.snn_fc_lif_layer(vp(zd), in_wb, in_bit0, R, K, M, T, t0, T_live, mode, vp(wp), vp(trains), vp(planes),
-                              vp(dump), cg, stream())
+    rc = lib.snn_fc_lif_layer(vp(zd), in_wb, in_bit0, R, K, M, T, t0, T_live, mode, vp(wp), vp(trains), vp(dump), cg,
+                              stream())
     _lib.check(rc, "fc_lif_layer")
     torch.cuda.synchronize()
-    # the plane-byte output (next layer's input) must be the same spikes as the spike-train words
-    assert torch.equal(unpack_planes(planes.cpu(), T), unpack_trains(trains.cpu(), T))
     return z, w, trains.cpu(), dump.cpu()
 
 
