@@ -199,14 +199,19 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
     } else {
         p.slot_b = static_cast<int>(align_up(static_cast<size_t>(tc.n_mma / tc.cg) * 128, 1024));
     }
+    // The weight ring (16 KB stages) and the spike-tile ring share 176 KB.  Default: 6 weight stages + 80 KB of
+    // spike tiles.  A conv spike tile (one 64-channel block of the halo'd region, read by 9 taps) can be large:
+    // keep two of them in flight when possible (producers refill one while the MMAs read the other) by
+    // borrowing weight stages, down to 3.
+    const int ring_total = kStagesA * kTileBytesA + kRingBytesB;
     p.stages_a = kStagesA;
     p.stages_b = kRingBytesB / p.slot_b;
     if (p.stages_b > kMaxStagesB) p.stages_b = kMaxStagesB;
-    if (p.stages_b < 1) {        // one spike tile larger than the 80 KB spike ring: it borrows weight-ring stages
-        p.stages_b = 1;
-        p.stages_a = (kStagesA * kTileBytesA + kRingBytesB - p.slot_b) / kTileBytesA;
-        if (p.stages_a < 2) return fail(SNN_E_ARG, "spike tile of %d bytes does not fit shared memory", p.slot_b);
+    if (p.stages_b < 2) {
+        p.stages_b = (ring_total - 3 * kTileBytesA) / p.slot_b >= 2 ? 2 : 1;
+        p.stages_a = (ring_total - p.stages_b * p.slot_b) / kTileBytesA;
         if (p.stages_a > kStagesA) p.stages_a = kStagesA;
+        if (p.stages_a < 2) return fail(SNN_E_ARG, "spike tile of %d bytes does not fit shared memory", p.slot_b);
     }
     if (const char* e = getenv("SNN_DBG_SWIZZLE")) {       // "shift,sbo,boff" -- scratch/swizzle_experiment.py only
         int a = 0, b = 0, c = 0;
