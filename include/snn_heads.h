@@ -112,6 +112,21 @@ int snn_fc_lif_layer(const void* z_words, int in_word_bytes, int in_bit0, int R,
                      int T_live, int mode, const void* w_prep, void* trains, float* dump, int cta_group,
                      snn_stream_t stream);
 
+/* ---- "next" row 8f-1: the proposal selection that follows RPNHeadSNN in RegionProposalNetwork.forward ----------
+ * (rpn.py:636-670: concat_box_prediction_layers + AnchorGenerator + BoxCoder.decode + sigmoid, applied by the
+ * reference to ALL A*H*W anchors of every level before the per-level top-k).  The top-k is taken on the head's
+ * native NCHW logits; this call decodes ONLY the selected anchors.
+ * logits[l] / deltas[l]: the head outputs of level l, fp32 NCHW [N][A][H][W] / [N][4A][H][W];
+ * base_anchors[l]: [A][4] fp32 cell anchors of level l (AnchorGenerator.cell_anchors); stride_h/w[l] = image size
+ * // feature size; idx [N][K] (K = sum k_per_level): per image and level the selected positions inside that
+ * level's [A][H][W] logits; boxes_out [N][K][4] (x1,y1,x2,y2, BoxCoder weights (1,1,1,1), dw/dh clamped to
+ * log(1000/16)), scores_out [N][K] = sigmoid(logit); optional logits_out [N][K] and ref_index_out [N][K] = the
+ * anchor's index in the reference's concatenated (level, h, w, a) order. */
+int snn_rpn_decode_selected(const void* const* logits, const void* const* deltas, const float* const* base_anchors,
+                            const int* H, const int* W, const int* stride_h, const int* stride_w, const int* k_per_level,
+                            int n_levels, int N, int A, const long long* idx, float* boxes_out, float* scores_out,
+                            float* logits_out, long long* ref_index_out, snn_stream_t stream);
+
 /* number of kernels the last forward call on this thread enqueued (for bench accounting) */
 int snn_last_launch_count(void);
 /* force cta_group (1 or 2; 0 = auto) for subsequent forward calls on this thread -- tests/profiling only */

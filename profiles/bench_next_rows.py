@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""Timing of the "next" rows at the Cityscapes batch-2 shapes, CUDA events, one JSON line.
+
+  rpn_select  : per-level top-k on the head's NCHW outputs + decode of the selected anchors (ours) against the path
+                the reference runs after RPNHeadSNN (rpn.py:636-670): permute/reshape of all logits and deltas,
+                AnchorGenerator, BoxCoder.decode of every anchor, per-level top-k, gather, sigmoid -- restated here with
+                the torchvision pieces the reference itself calls.
+  postprocess : vectorised RoIHeadsSNN.postprocess_detections against the reference's per-detection Python loop
+                (roi_heads.py:1143-1146, restated for timing only).
+"""
+import json
+import os
+import sys
+
+import torch
+from torchvision.models.detection import _utils as det_utils
+from torchvision.models.detection.anchor_utils import AnchorGenerator
+from torchvision.models.detection.image_list import ImageList
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from snn_automotive_object_detection_b200 import detection_post as DP  # noqa: E402
+
+LEVELS = [(192, 384), (96, 192), (48, 96), (24, 48), (12, 24)]
+N, A, IMG = 2, 3, (768, 1536)
+
+
+def timed(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    obj = [torch.randn(N, A, h, w, device=dev) for (h, w) in LEVELS]
+    dlt = [torch.randn(N, 4 * A, h, w, device=dev) * 0.3 for (h, w) in LEVELS]
+    ag = AnchorGenerator(((32,), (64,), (128,), (256,), (512,)), ((0.5, 1.0, 2.0),) * 5)
+    images = ImageList(torch.zeros(N, 3, *IMG, device=dev), [IMG] * N)
+    feats = [torch.zeros(N, 1, h, w, device=dev) for (h, w) in LEVELS]
+    coder = det_utils.BoxCoder((1.0, 1.0, 1.0, 1.0))
+    strides = [(IMG[0] // h, IMG[1] // w) for (h, w) in LEVELS]
+
+    def reference_path():
+        anchors = ag(images, feats)
+        o = torch.cat([x.view(N, -1, 1, *x.shape[-2:]).permute(0, 3, 4, 1, 2).reshape(N, -1, 1) for x in obj], dim=1).flatten(0, -2)
+        d = torch.cat([x.view(N, -1, 4, *x.shape[-2:]).permute(0, 3, 4, 1, 2).reshape(N, -1, 4) for x in dlt], dim=1).reshape(-1, 4)
+        props = coder.decode(d, anchors).view(N, -1, 4)
+        o = o.reshape(N, -1)
+        r, off = [], 0
+        for ob in o.split([A * h * w for (h, w) in LEVELS], 1):
+            _, idx = ob.topk(min(1000, ob.shape[1]), dim=1)
+            r.append(idx + off); off += ob.shape[1]
+        top = torch.cat(r, dim=1)
+        b = torch.arange(N, device=dev)[:, None]
+        return props[b, top], torch.sigmoid(o[b, top]), props, o
+
+    def ours():
+        return DP.rpn_select_proposals(obj, dlt, ag.cell_anchors, strides, 1000)
+
+    # same entries?  compare through the reference-order anchor index each selected entry reports (equal logits at
+    # two anchors may legitimately swap places between the two top-k calls)
+    _, sr, all_props, all_logits = reference_path()
+    po, so, _, ref_index = ours()
+    b = torch.arange(N, device=dev)[:, None]
+    pr = all_props[b, ref_index]
+    assert torch.equal(torch.sigmoid(all_logits[b, ref_index]), so) or (torch.sigmoid(all_logits[b, ref_index]) - so).abs().max() <= 1e-6
+    ds, db = (sr - so).abs().max().item(), ((pr - po).abs() / (1.0 + pr.abs())).max().item()
+    assert ds <= 1e-6 and db <= 1e-5, f"fast path differs from the reference path: scores {ds}, boxes (relative) {db}"
+
+    # ---- detection post-processing: 2 x 1000 RoIs, 9 classes, thresholds of model.py:98-99
+    C, R = 9, 1000
+    logits = torch.randn(N * R, C, device=dev) * 2.5
+    reg = torch.randn(N * R, 4 * C, device=dev) * 0.5
+    xy = torch.rand(N * R, 2, device=dev) * torch.tensor([IMG[1] * 0.8, IMG[0] * 0.8], device=dev)
+    wh = torch.rand(N * R, 2, device=dev) * 300 + 4
+    props = list(torch.cat([xy, xy + wh], dim=1).split(R))
+    coder2 = det_utils.BoxCoder((10.0, 10.0, 5.0, 5.0))
+
+    def vectorised():
+        return DP.postprocess_detections(logits, reg, props, [IMG] * N, coder2, 0.4, 0.5, 100)
+
+    def loop_mask_only():      # the part the reference does per detection in Python (roi_heads.py:1136-1147)
+        scores = torch.softmax(logits, -1)
+        for sc in scores.split(R):
+            s = sc[:, 1:].reshape(-1)
+            inds = torch.where(s > 0.4)[0]
+            which = torch.div(inds, C - 1, rounding_mode="trunc")
+            inds_bg = torch.where(sc[:, 0] >= 0)[0]
+            mask = torch.ones(*inds_bg.shape, dtype=torch.int32, device=dev)
+            for i in which:
+                pos = torch.where(inds_bg == i)[0]
+                if len(pos):
+                    mask[pos] = 0
+
+    line = {"rows": "SURVEY 8f-1 / 8f-4", "shapes": "cityscapes batch 2 (294 624 anchors/img, 1000 RoIs/img)",
+            "rpn_select_ms": {"reference_path": timed(reference_path), "ours": timed(ours)},
+            "postprocess_ms": {"reference_python_mask_loop_only": timed(loop_mask_only, iters=3), "ours_whole_function": timed(vectorised)}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

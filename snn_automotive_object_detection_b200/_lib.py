@@ -22,7 +22,7 @@ EXPORTS = [
     "snn_version", "snn_last_error", "snn_train_word_bytes", "snn_mode_pieces", "snn_prepared_weight_bytes",
     "snn_prepare_conv3x3_weights", "snn_prepare_fc_weights", "snn_rpn_head_workspace_bytes", "snn_rpn_head_forward",
     "snn_box_head_workspace_bytes", "snn_box_head_forward", "snn_fc_lif_layer", "snn_encode_rows",
-    "snn_last_launch_count", "snn_set_cta_group", "snn_profile_enable", "snn_profile_read",
+    "snn_last_launch_count", "snn_set_cta_group", "snn_profile_enable", "snn_profile_read", "snn_rpn_decode_selected",
 ]
 PHASES = ["rpn_encoder", "rpn_conv_lif_gemm", "rpn_readout", "box_encoder", "fc6_lif_gemm", "fc7_lif_gemm", "box_readout"]
 
@@ -50,6 +50,8 @@ def _declare(lib):
     lib.snn_box_head_forward.restype = i
     lib.snn_fc_lif_layer.argtypes = [vp, i, i, i, i, i, i, i, i, i, vp, vp, vp, i, vp]; lib.snn_fc_lif_layer.restype = i
     lib.snn_encode_rows.argtypes = [vp, i, i, i, vp, vp]; lib.snn_encode_rows.restype = i
+    lib.snn_rpn_decode_selected.argtypes = [pvp, pvp, pvp, pi, pi, pi, pi, pi, i, i, i, vp, vp, vp, vp, vp, vp]
+    lib.snn_rpn_decode_selected.restype = i
     lib.snn_last_launch_count.restype = i
     lib.snn_set_cta_group.argtypes = [i]; lib.snn_set_cta_group.restype = None
     lib.snn_profile_enable.argtypes = [i]; lib.snn_profile_enable.restype = None

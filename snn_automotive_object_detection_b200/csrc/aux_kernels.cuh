@@ -354,3 +354,64 @@ __global__ void __launch_bounds__(256) readout_rows_kernel(const TrainT* __restr
 }
 
 }  // namespace snn
+
+// ------------------------------------------------------- RPN proposal decode
+// The step after RPNHeadSNN in RegionProposalNetwork.forward (rpn.py:636-670): the reference permutes all
+// A*H*W logits and 4*A*H*W deltas of every level to (H, W, A) order, generates every anchor, decodes every
+// box and only then keeps the per-level top-k.  Here the top-k runs on the head's native NCHW logits
+// (index = (a*H + h)*W + w) and this kernel touches ONLY the selected entries: it regenerates their anchors
+// analytically (torchvision AnchorGenerator: rounded base anchor + (w*stride_w, h*stride_h)), gathers the 4
+// deltas from the NCHW tensor, decodes with BoxCoder(1,1,1,1) (det_utils.BoxCoder.decode_single, dw/dh clamped
+// to log(1000/16)) and applies the sigmoid -- one thread per selected anchor.
+constexpr int kPropMaxLevels = 8;
+struct PropLevel {
+    const float* logits;      // [N][A][H][W]
+    const float* deltas;      // [N][4A][H][W]
+    const float* base;        // [A][4] base anchors of this level (x1, y1, x2, y2)
+    int H, W, k, k_begin;     // k selected per image, offset of this level inside the K_total selected of an image
+    int stride_h, stride_w;
+    long long anchor_begin;   // index of the level's first anchor in the reference's concatenated (level, h, w, a) order
+};
+struct PropParams {
+    PropLevel lv[kPropMaxLevels];
+    int n_levels, N, A, K_total;
+    float clip;               // log(1000 / 16)
+    const long long* idx;     // [N][K_total] selected index inside the level's [A][H][W] logits of that image
+    float* boxes;             // [N][K_total][4]
+    float* scores;            // [N][K_total] sigmoid(objectness)
+    float* logit_out;         // [N][K_total] raw objectness (nullable)
+    long long* ref_index;     // [N][K_total] index in the reference's (level, h, w, a) anchor order (nullable)
+};
+
+__global__ void __launch_bounds__(256) rpn_decode_selected_kernel(const __grid_constant__ PropParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.N * p.K_total) return;
+    const int n = i / p.K_total, kk = i - n * p.K_total;
+    int l = 0;
+    while (l + 1 < p.n_levels && kk >= p.lv[l + 1].k_begin) ++l;
+    const PropLevel& L = p.lv[l];
+    const long long id = p.idx[i];
+    const int hw = L.H * L.W;
+    const int a = static_cast<int>(id / hw);
+    const int rem = static_cast<int>(id - static_cast<long long>(a) * hw);
+    const int h = rem / L.W, w = rem - h * L.W;
+    const float logit = L.logits[(static_cast<size_t>(n) * p.A + a) * hw + rem];
+    const float* d = L.deltas + (static_cast<size_t>(n) * 4 * p.A + 4 * a) * hw + rem;
+    const float dx = d[0], dy = d[hw];
+    const float dw = fminf(d[2 * static_cast<size_t>(hw)], p.clip), dh = fminf(d[3 * static_cast<size_t>(hw)], p.clip);
+    const float sx = static_cast<float>(w * L.stride_w), sy = static_cast<float>(h * L.stride_h);
+    const float x1 = L.base[4 * a + 0] + sx, y1 = L.base[4 * a + 1] + sy;
+    const float x2 = L.base[4 * a + 2] + sx, y2 = L.base[4 * a + 3] + sy;
+    // det_utils.BoxCoder.decode_single, weights (1, 1, 1, 1), op for op (no FMA contraction)
+    const float widths = __fsub_rn(x2, x1), heights = __fsub_rn(y2, y1);
+    const float ctr_x = __fadd_rn(x1, __fmul_rn(0.5f, widths)), ctr_y = __fadd_rn(y1, __fmul_rn(0.5f, heights));
+    const float pcx = __fadd_rn(__fmul_rn(dx, widths), ctr_x), pcy = __fadd_rn(__fmul_rn(dy, heights), ctr_y);
+    const float pw = __fmul_rn(expf(dw), widths), ph = __fmul_rn(expf(dh), heights);
+    const float cw = __fmul_rn(0.5f, pw), ch = __fmul_rn(0.5f, ph);
+    float4 o;
+    o.x = __fsub_rn(pcx, cw); o.y = __fsub_rn(pcy, ch); o.z = __fadd_rn(pcx, cw); o.w = __fadd_rn(pcy, ch);
+    reinterpret_cast<float4*>(p.boxes)[i] = o;
+    p.scores[i] = 1.0f / (1.0f + expf(-logit));
+    if (p.logit_out != nullptr) p.logit_out[i] = logit;
+    if (p.ref_index != nullptr) p.ref_index[i] = L.anchor_begin + (static_cast<long long>(h) * L.W + w) * p.A + a;
+}

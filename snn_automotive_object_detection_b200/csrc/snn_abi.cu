@@ -620,6 +620,41 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
     return SNN_OK;
 }
 
+int snn_rpn_decode_selected(const void* const* logits, const void* const* deltas, const float* const* base_anchors,
+                            const int* H, const int* W, const int* stride_h, const int* stride_w, const int* k_per_level,
+                            int n_levels, int N, int A, const long long* idx, float* boxes_out, float* scores_out,
+                            float* logits_out, long long* ref_index_out, snn_stream_t stream) {
+    if (!logits || !deltas || !base_anchors || !H || !W || !stride_h || !stride_w || !k_per_level || !idx || !boxes_out ||
+        !scores_out)
+        return fail(SNN_E_ARG, "rpn_decode_selected: null argument");
+    if (n_levels < 1 || n_levels > kPropMaxLevels || N < 1 || A < 1)
+        return fail(SNN_E_ARG, "rpn_decode_selected: bad sizes (levels %d, N %d, A %d)", n_levels, N, A);
+    PropParams p;
+    memset(&p, 0, sizeof(p));
+    int kb = 0;
+    long long ab = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        PropLevel& L = p.lv[l];
+        if (!logits[l] || !deltas[l] || !base_anchors[l] || H[l] < 1 || W[l] < 1 || k_per_level[l] < 0 ||
+            k_per_level[l] > A * H[l] * W[l])
+            return fail(SNN_E_ARG, "rpn_decode_selected: level %d: bad argument", l);
+        L.logits = reinterpret_cast<const float*>(logits[l]); L.deltas = reinterpret_cast<const float*>(deltas[l]);
+        L.base = base_anchors[l];
+        L.H = H[l]; L.W = W[l]; L.k = k_per_level[l]; L.k_begin = kb; L.stride_h = stride_h[l]; L.stride_w = stride_w[l];
+        L.anchor_begin = ab;
+        kb += k_per_level[l];
+        ab += static_cast<long long>(A) * H[l] * W[l];
+    }
+    if (kb == 0) return SNN_OK;
+    p.n_levels = n_levels; p.N = N; p.A = A; p.K_total = kb;
+    p.clip = static_cast<float>(log(1000.0 / 16.0));
+    p.idx = idx; p.boxes = boxes_out; p.scores = scores_out; p.logit_out = logits_out; p.ref_index = ref_index_out;
+    const int total = N * kb;
+    rpn_decode_selected_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return SNN_OK;
+}
+
 void snn_profile_enable(int on) {
     g_profile = on != 0;
     for (int k = 0; k < PH_COUNT; ++k) g_ph[k].used = 0;

@@ -1,0 +1,203 @@
+"""The two steps around the spiking heads that SURVEY.md section 8f ranks "next":
+
+  * rank 1 -- RPN proposal selection fed from the head's native layout.  The reference
+    (RegionProposalNetwork.forward, rpn.py:636-670; filter_proposals, rpn.py:448-525) permutes every level's
+    logits/deltas to (H, W, A) order, generates all anchors, decodes ALL boxes and only then takes the
+    per-level top-k.  `rpn_select_proposals` takes the top-k on the NCHW logits as the head wrote them and lets
+    one small CUDA kernel (csrc/aux_kernels.cuh::rpn_decode_selected_kernel, through the C ABI) regenerate the
+    anchors of the selected entries, gather their deltas, decode and apply the sigmoid.  NMS stays torchvision.
+  * rank 4 -- `postprocess_detections`: RoIHeadsSNN.postprocess_detections (roi_heads.py:1075-1176) with its
+    per-detection Python loop (`for i in inds...: torch.where(inds_bg == i)`, roi_heads.py:1143-1146; one device
+    sync per kept detection) replaced by a scatter on a mask.  Same outputs, same order.
+
+Both are inference-only and keep the reference's (modified) return values: per-image pre-NMS proposals +
+objectness, background boxes kept, `all_scores` / `all_boxes`.
+"""
+import ctypes
+import math
+import types
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+from torchvision.ops import boxes as box_ops
+
+from . import _lib
+
+
+# --------------------------------------------------------------------------- rank 4
+def postprocess_detections(class_logits: Tensor, box_regression: Tensor, proposals: List[Tensor],
+                           image_shapes: List[Tuple[int, int]], box_coder, score_thresh: float, nms_thresh: float,
+                           detections_per_img: int):
+    """Vectorised RoIHeadsSNN.postprocess_detections (roi_heads.py:1075-1176); returns the same 5 lists:
+    boxes, scores, labels (objects first, then every surviving background box), all_scores, all_boxes."""
+    device = class_logits.device
+    num_classes = class_logits.shape[-1]
+    boxes_per_image = [b.shape[0] for b in proposals]
+    pred_boxes = box_coder.decode(box_regression, proposals)
+    pred_scores = F.softmax(class_logits, -1)
+    pred_boxes_list = pred_boxes.split(boxes_per_image, 0)
+    pred_scores_list = pred_scores.split(boxes_per_image, 0)
+
+    all_boxes, all_scores, all_labels, all_scores_all_classes, all_pre_nms_boxes = [], [], [], [], []
+    for boxes, scores, image_shape in zip(pred_boxes_list, pred_scores_list, image_shapes):
+        boxes = box_ops.clip_boxes_to_image(boxes, image_shape)
+        labels = torch.arange(num_classes, device=device).view(1, -1).expand_as(scores)
+        boxes_all_classes = boxes.detach().clone()
+        scores_all_classes = scores.detach().clone()
+
+        boxes_bg = boxes[:, 0].detach().reshape(-1, 4)
+        scores_bg = scores[:, 0].detach().reshape(-1)
+        labels_bg = labels[:, 0].reshape(-1)
+        boxes = boxes[:, 1:].reshape(-1, 4)
+        scores = scores[:, 1:].reshape(-1)
+        labels = labels[:, 1:].reshape(-1)
+
+        inds = torch.where(scores > score_thresh)[0]
+        boxes, scores, labels = boxes[inds], scores[inds], labels[inds]
+
+        # A background box is dropped when any class of the same RoI passed the threshold.  The reference loops over
+        # `inds` in Python (roi_heads.py:1143-1146); the same mask is one scatter.  (`scores_bg >= 0` keeps NaN rows
+        # out exactly as the reference's torch.where does.)
+        roi_of_kept = torch.div(inds, num_classes - 1, rounding_mode="trunc")
+        keep_bg_mask = scores_bg >= 0
+        keep_bg_mask[roi_of_kept] = False
+        inds_bg = torch.where(keep_bg_mask)[0]
+        boxes_bg, scores_bg, labels_bg = boxes_bg[inds_bg], scores_bg[inds_bg], labels_bg[inds_bg]
+
+        keep = box_ops.remove_small_boxes(boxes, min_size=1e-2)
+        boxes, scores, labels = boxes[keep], scores[keep], labels[keep]
+        keep_bg = box_ops.remove_small_boxes(boxes_bg, min_size=1e-2)
+        boxes_bg, scores_bg, labels_bg = boxes_bg[keep_bg], scores_bg[keep_bg], labels_bg[keep_bg]
+
+        keep = box_ops.batched_nms(boxes, scores, labels, nms_thresh)
+        keep_bg = box_ops.batched_nms(boxes_bg, scores_bg, labels_bg, nms_thresh)
+        keep = keep[:detections_per_img]
+        boxes, scores, labels = boxes[keep], scores[keep], labels[keep]
+        boxes_bg, scores_bg, labels_bg = boxes_bg[keep_bg], scores_bg[keep_bg], labels_bg[keep_bg]
+
+        all_boxes.append(torch.cat((boxes, boxes_bg), dim=0))
+        all_scores.append(torch.cat((scores, scores_bg), dim=0))
+        all_labels.append(torch.cat((labels, labels_bg), dim=0))
+        all_scores_all_classes.append(scores_all_classes)
+        all_pre_nms_boxes.append(boxes_all_classes)
+    return all_boxes, all_scores, all_labels, all_scores_all_classes, all_pre_nms_boxes
+
+
+def patch_postprocess(roi_heads):
+    """Bind the vectorised post-processing to a RoIHeadsSNN instance (same signature as the reference method)."""
+    def _pp(self, class_logits, box_regression, proposals, image_shapes):
+        return postprocess_detections(class_logits, box_regression, proposals, image_shapes, self.box_coder,
+                                      self.score_thresh, self.nms_thresh, self.detections_per_img)
+    roi_heads.postprocess_detections = types.MethodType(_pp, roi_heads)
+    return roi_heads
+
+
+# --------------------------------------------------------------------------- rank 1
+def nchw_index_to_reference_order(idx: Tensor, A: int, H: int, W: int) -> Tensor:
+    """Position inside a level's [A][H][W] logits -> position in the reference's (H, W, A) flattening
+    (permute_and_flatten, rpn.py:248-259)."""
+    a = torch.div(idx, H * W, rounding_mode="floor")
+    rem = idx - a * (H * W)
+    return rem * A + a
+
+
+def rpn_select_proposals(objectness: Sequence[Tensor], pred_bbox_deltas: Sequence[Tensor], cell_anchors: Sequence[Tensor],
+                         strides: Sequence[Tuple[int, int]], pre_nms_top_n: int):
+    """Per-level top-k on the head's NCHW logits + decode of the selected anchors only (CUDA).
+
+    objectness[l] [N,A,H,W], pred_bbox_deltas[l] [N,4A,H,W] (CUDA fp32, as RPNHeadSNN returns them),
+    cell_anchors[l] [A,4], strides[l] = (stride_h, stride_w).
+    Returns proposals [N,K,4], objectness_prob [N,K], levels [N,K] (int64) and ref_index [N,K] (the anchor index in
+    the reference's concatenated order), K = sum_l min(pre_nms_top_n, A*H*W), level-major like the reference."""
+    lib = _lib.load()
+    L = len(objectness)
+    if L == 0:
+        raise RuntimeError("rpn_select_proposals: no feature levels")
+    dev = objectness[0].device
+    if not objectness[0].is_cuda:
+        raise RuntimeError("rpn_select_proposals: expected CUDA tensors (B200); there is no CPU fallback")
+    N, A = objectness[0].shape[:2]
+    logits = [o.detach().float().contiguous() for o in objectness]
+    deltas = [d.detach().float().contiguous() for d in pred_bbox_deltas]
+    bases = [c.detach().to(device=dev, dtype=torch.float32).contiguous() for c in cell_anchors]
+    ks, idxs, lvls = [], [], []
+    for l, o in enumerate(logits):
+        n_anchors = o[0].numel()
+        k = min(int(pre_nms_top_n), n_anchors)
+        _, top = o.view(N, -1).topk(k, dim=1)                      # NCHW order: no permute / reshape copy
+        ks.append(k); idxs.append(top)
+        lvls.append(torch.full((k,), l, dtype=torch.int64, device=dev))
+    idx = torch.cat(idxs, dim=1).contiguous()
+    K = idx.shape[1]
+    boxes = torch.empty(N, K, 4, device=dev, dtype=torch.float32)
+    scores = torch.empty(N, K, device=dev, dtype=torch.float32)
+    ref_index = torch.empty(N, K, device=dev, dtype=torch.int64)
+    VP = ctypes.c_void_p * L
+    IA = ctypes.c_int * L
+    with torch.cuda.device(dev):
+        rc = lib.snn_rpn_decode_selected(
+            VP(*[t.data_ptr() for t in logits]), VP(*[t.data_ptr() for t in deltas]), VP(*[t.data_ptr() for t in bases]),
+            IA(*[t.shape[2] for t in logits]), IA(*[t.shape[3] for t in logits]),
+            IA(*[int(s[0]) for s in strides]), IA(*[int(s[1]) for s in strides]), IA(*ks), L, N, A,
+            ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(boxes.data_ptr()), ctypes.c_void_p(scores.data_ptr()),
+            None, ctypes.c_void_p(ref_index.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "snn_rpn_decode_selected")
+    levels = torch.cat(lvls).reshape(1, -1).expand(N, -1)
+    return boxes, scores, levels, ref_index
+
+
+def filter_selected(proposals: Tensor, objectness_prob: Tensor, levels: Tensor, image_shapes: List[Tuple[int, int]],
+                    min_size: float, score_thresh: float, nms_thresh: float, post_nms_top_n: int):
+    """The tail of RegionProposalNetwork.filter_proposals (rpn.py:493-525) on the already selected / decoded entries."""
+    pre_nms = [{"proposals": prop, "objectness": objectness_prob[i]} for i, prop in enumerate(proposals)]
+    final_boxes, final_scores = [], []
+    for boxes, scores, lvl, img_shape in zip(proposals, objectness_prob, levels, image_shapes):
+        boxes = box_ops.clip_boxes_to_image(boxes, img_shape)
+        keep = box_ops.remove_small_boxes(boxes, min_size)
+        boxes, scores, lvl = boxes[keep], scores[keep], lvl[keep]
+        keep = torch.where(scores >= score_thresh)[0]
+        boxes, scores, lvl = boxes[keep], scores[keep], lvl[keep]
+        keep = box_ops.batched_nms(boxes, scores, lvl, nms_thresh)
+        keep = keep[:post_nms_top_n]
+        final_boxes.append(boxes[keep]); final_scores.append(scores[keep])
+    return final_boxes, final_scores, pre_nms
+
+
+def fast_rpn_forward(rpn, images, features: Dict[str, Tensor]):
+    """Inference-time replacement of RegionProposalNetwork.forward (rpn.py:563-703): returns (boxes, extras) with
+    extras = the per-image pre-NMS proposals + objectness, as the reference's modified forward does in eval mode."""
+    feats = list(features.values())
+    objectness, pred_bbox_deltas = rpn.head(feats)
+    image_size = images.tensors.shape[-2:]
+    strides = [(image_size[0] // f.shape[-2], image_size[1] // f.shape[-1]) for f in feats]
+    props, probs, levels, _ = rpn_select_proposals(objectness, pred_bbox_deltas, rpn.anchor_generator.cell_anchors,
+                                                   strides, rpn.pre_nms_top_n())
+    boxes, _scores, pre_nms = filter_selected(props, probs, levels, images.image_sizes, rpn.min_size, rpn.score_thresh,
+                                              rpn.nms_thresh, rpn.post_nms_top_n())
+    return boxes, pre_nms
+
+
+def attach_fast_postprocessing(model):
+    """Patch a Faster R-CNN built like the reference's (model.py): eval-mode `rpn.forward` selects proposals from the
+    head's native layout, and `roi_heads.postprocess_detections` is the vectorised one.  Training keeps the originals."""
+    rpn = model.rpn
+    original = rpn.forward
+    reference_style = hasattr(model.roi_heads, "box_head_and_predictor")
+
+    def _forward(self, images, features, targets=None):
+        if self.training:
+            return original(images, features, targets)
+        boxes, pre_nms = fast_rpn_forward(self, images, features)
+        # the reference's modified RPN returns the pre-NMS proposals in place of the (empty) loss dict;
+        # a stock torchvision GeneralizedRCNN expects a dict there
+        return boxes, (pre_nms if reference_style else {})
+
+    rpn.forward = types.MethodType(_forward, rpn)
+    if reference_style:                                              # the reference's RoIHeadsSNN
+        patch_postprocess(model.roi_heads)
+    return model
+
+
+BBOX_XFORM_CLIP = math.log(1000.0 / 16)

@@ -1,0 +1,122 @@
+"""The "next" rows against goldens produced by the UNMODIFIED reference classes
+(oracle/gen_golden_post.py): vectorised RoIHeadsSNN.postprocess_detections (CPU and GPU) and the proposal
+selection fed from the RPN head's native NCHW layout (GPU, through the C ABI)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from torchvision.models.detection import _utils as det_utils
+
+from snn_automotive_object_detection_b200 import detection_post as DP
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def _post_inputs(g, device="cpu"):
+    per_img = [int(v) for v in g["per_img"]]
+    props = [torch.from_numpy(g[f"props{i}"]).to(device) for i in range(len(per_img))]
+    shapes = [tuple(int(v) for v in s) for s in g["shapes"]]
+    return torch.from_numpy(g["logits"]).to(device), torch.from_numpy(g["reg"]).to(device), props, shapes
+
+
+def _check_post(g, out, exact):
+    boxes, scores, labels, all_scores, all_boxes = out
+    for i in range(len(boxes)):
+        assert torch.equal(labels[i].cpu(), torch.from_numpy(g[f"labels{i}"])), "same detections in the same order"
+        if exact:
+            assert torch.equal(boxes[i].cpu(), torch.from_numpy(g[f"boxes{i}"]))
+            assert torch.equal(scores[i].cpu(), torch.from_numpy(g[f"scores{i}"]))
+            assert torch.equal(all_scores[i].cpu(), torch.from_numpy(g[f"all_scores{i}"]))
+            assert torch.equal(all_boxes[i].cpu(), torch.from_numpy(g[f"all_boxes{i}"]))
+        else:
+            assert torch.allclose(boxes[i].cpu(), torch.from_numpy(g[f"boxes{i}"]), atol=2e-3)
+            assert torch.allclose(scores[i].cpu(), torch.from_numpy(g[f"scores{i}"]), atol=1e-6)
+            assert torch.allclose(all_boxes[i].cpu(), torch.from_numpy(g[f"all_boxes{i}"]), atol=2e-3)
+
+
+def test_vectorised_postprocess_equals_the_reference_loop(golden_dir):
+    g = _load(golden_dir, "post_detections")
+    logits, reg, props, shapes = _post_inputs(g)
+    coder = det_utils.BoxCoder((10.0, 10.0, 5.0, 5.0))                    # roi_heads.py:938-940 default
+    out = DP.postprocess_detections(logits, reg, props, shapes, coder, float(g["score_thresh"]),
+                                    float(g["nms_thresh"]), int(g["detections_per_img"]))
+    n_bg = [int((out[2][i] == 0).sum()) for i in range(2)]
+    assert min(n_bg) > 0 and all(int((out[2][i] > 0).sum()) > 0 for i in range(2)), "both objects and background kept"
+    _check_post(g, out, exact=True)
+
+
+def test_patch_binds_the_reference_signature(golden_dir):
+    g = _load(golden_dir, "post_detections")
+    logits, reg, props, shapes = _post_inputs(g)
+
+    class Holder:
+        box_coder = det_utils.BoxCoder((10.0, 10.0, 5.0, 5.0))
+        score_thresh, nms_thresh, detections_per_img = 0.4, 0.5, 100
+
+    h = DP.patch_postprocess(Holder())
+    _check_post(g, h.postprocess_detections(logits, reg, props, shapes), exact=True)
+
+
+def test_nchw_index_maps_to_the_reference_flattening():
+    A, H, W = 3, 5, 7
+    x = torch.arange(A * H * W).view(1, A, H, W)
+    ref = x.view(1, -1, 1, H, W).permute(0, 3, 4, 1, 2).reshape(-1)        # permute_and_flatten, rpn.py:256-258
+    idx = torch.arange(A * H * W)
+    assert torch.equal(ref[DP.nchw_index_to_reference_order(idx, A, H, W)], idx)
+
+
+@pytest.mark.gpu
+def test_vectorised_postprocess_on_gpu(golden_dir):
+    g = _load(golden_dir, "post_detections")
+    logits, reg, props, shapes = _post_inputs(g, "cuda")
+    coder = det_utils.BoxCoder((10.0, 10.0, 5.0, 5.0))
+    out = DP.postprocess_detections(logits, reg, props, shapes, coder, 0.4, 0.5, 100)
+    _check_post(g, out, exact=False)
+
+
+@pytest.mark.gpu
+def test_rpn_proposals_from_native_layout_match_the_reference(golden_dir):
+    g = _load(golden_dir, "post_rpn")
+    L = len(g["levels"])
+    obj = [torch.from_numpy(g[f"obj{l}"]).cuda() for l in range(L)]
+    dlt = [torch.from_numpy(g[f"dlt{l}"]).cuda() for l in range(L)]
+    cells = [torch.from_numpy(g[f"cell{l}"]) for l in range(L)]
+    img = tuple(int(v) for v in g["img"])
+    strides = [(img[0] // int(h), img[1] // int(w)) for (h, w) in g["levels"]]
+    props, probs, levels, ref_index = DP.rpn_select_proposals(obj, dlt, cells, strides, int(g["pre_nms_top_n"]))
+    torch.cuda.synchronize()
+    N = props.shape[0]
+    for i in range(N):
+        # pre-NMS: same selected set, same decoded boxes / probabilities (top-k order may differ only between ties)
+        want_p, want_o = torch.from_numpy(g[f"pre_props{i}"]), torch.from_numpy(g[f"pre_obj{i}"])
+        assert props[i].shape == want_p.shape
+        assert torch.allclose(probs[i].cpu(), want_o, atol=1e-6)           # both sorted by objectness per level
+        assert torch.allclose(props[i].cpu(), want_p, atol=2e-3, rtol=1e-5)
+        assert ref_index[i].unique().numel() == ref_index[i].numel()
+    image_sizes = [tuple(int(v) for v in s) for s in g["image_sizes"]]
+    boxes, scores, pre = DP.filter_selected(props, probs, levels, image_sizes, float(g["min_size"]), 0.0,
+                                            float(g["nms_thresh"]), int(g["post_nms_top_n"]))
+    for i in range(N):
+        want = torch.from_numpy(g[f"boxes{i}"])
+        assert boxes[i].shape == want.shape
+        assert torch.allclose(boxes[i].cpu(), want, atol=2e-3, rtol=1e-5)
+        assert torch.equal(pre[i]["proposals"], props[i])
+
+
+@pytest.mark.gpu
+def test_ref_index_points_at_the_reference_anchor(golden_dir):
+    # the anchor index reported for a selected entry is its position in the reference's (level, h, w, a) order
+    g = _load(golden_dir, "post_rpn")
+    L = len(g["levels"])
+    obj = [torch.from_numpy(g[f"obj{l}"]).cuda() for l in range(L)]
+    dlt = [torch.from_numpy(g[f"dlt{l}"]).cuda() for l in range(L)]
+    cells = [torch.from_numpy(g[f"cell{l}"]) for l in range(L)]
+    img = tuple(int(v) for v in g["img"])
+    strides = [(img[0] // int(h), img[1] // int(w)) for (h, w) in g["levels"]]
+    props, probs, levels, ref_index = DP.rpn_select_proposals(obj, dlt, cells, strides, 50)
+    flat = torch.cat([o.permute(0, 2, 3, 1).reshape(o.shape[0], -1) for o in obj], dim=1)   # (level, h, w, a)
+    got = torch.sigmoid(torch.gather(flat, 1, ref_index))
+    assert torch.allclose(got, probs, atol=1e-6)

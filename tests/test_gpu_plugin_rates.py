@@ -116,3 +116,29 @@ def test_full_size_level_shapes_parity(workload):
     keep = ~(f6.any(dim=1) | f7.any(dim=1)).unsqueeze(1)
     assert ((cls.cpu() - rc).abs() * keep).max().item() <= 1e-3 * rc.abs().max().item()
     assert ((dl.cpu() - rd).abs() * keep).max().item() <= 1e-3 * rd.abs().max().item()
+
+
+def test_fast_postprocessing_keeps_the_detections_of_the_stock_path():
+    """attach_fast_postprocessing: proposals selected from the head's NCHW outputs + decode of the
+    selected anchors only must give the detections of torchvision's own RegionProposalNetwork.forward."""
+    from torchvision.models.detection import fasterrcnn_resnet50_fpn
+    torch.manual_seed(1)
+    model = fasterrcnn_resnet50_fpn(weights=None, weights_backbone=None, num_classes=9, min_size=256, max_size=384,
+                                    box_score_thresh=0.0)
+    S.attach_snn_heads(model, num_steps_rpn=8, num_steps_detector=12, num_classes=9)
+    model = model.cuda().eval()
+    imgs = [torch.rand(3, 240, 320, device="cuda"), torch.rand(3, 200, 300, device="cuda")]
+    props_seen = []
+    model.roi_heads.register_forward_pre_hook(lambda m, args: props_seen.append([p.detach().cpu() for p in args[1]]))
+    with torch.no_grad():
+        want = model(imgs)
+        S.attach_fast_postprocessing(model)
+        got = model(imgs)
+    ref_props, fast_props = props_seen
+    for a, b in zip(ref_props, fast_props):               # the proposals handed to the RoI heads
+        assert a.shape == b.shape and a.shape[0] > 0
+        assert torch.allclose(a, b, atol=2e-3, rtol=1e-5)
+    for a, b in zip(want, got):
+        assert a["boxes"].shape == b["boxes"].shape
+        assert torch.allclose(a["boxes"], b["boxes"], atol=5e-2)
+        assert torch.equal(a["labels"], b["labels"])
