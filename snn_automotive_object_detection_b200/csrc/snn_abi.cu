@@ -228,8 +228,9 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
     // producer group g starts on stage g of both rings, so there are at most min(stages) groups (1, 2 or 4)
     {
         const int m = p.stages_b < p.stages_w ? p.stages_b : p.stages_w;
-        p.n_pg = m >= 2 ? 2 : 1;      // measured: 2 groups x 4 warps beat 4 x 2 (r01h vs r01f)
+        p.n_pg = m >= 2 ? 2 : 1;      // pair-loop producers: 2 groups x 4 warps beat 4 x 2 (r01h vs r01f)
         if (p.conv) p.n_pg = 1;       // one stage per 64-channel block serves 9 taps: all 8 warps fill it together
+        if (!p.conv && tc.T_box <= 16) p.n_pg = 1;   // fc item-parallel producers: all 8 warps fill every stage
     }
     p.m_tiles = p.m_total / (128 * tc.cg);
     p.total_tiles = p.unit_tiles * p.m_tiles;

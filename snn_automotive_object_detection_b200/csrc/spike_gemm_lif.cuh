@@ -318,6 +318,70 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         // row of (unit j, step t): fc t * Jh + j; conv halo pixel (hh, ww): (hh * T_box + t) * 10 + ww
         const uint32_t row_step = (kConv ? 10u : static_cast<uint32_t>(p.Jh)) * 128u;
 
+        // ---- fc fast path: the spike tile of a k-block is produced by ALL producer threads, one 16-byte chunk
+        // (row t * Jh + j, chunk q) per item, at most 8 items per thread (4 with cta_group 2).  The item geometry does not depend on the
+        // k-block, so each thread keeps its items' word offset, swizzled store offset and step in registers; a stage
+        // is then ~14 instructions per item with every item independent (the per-pair loop below walks the T_box
+        // steps of a pair serially: ~5x the latency per stage, which the fc pipeline -- one stage per k-block,
+        // handed across the CTA pair -- cannot hide).
+        if (!kConv && packed && p.dbg_sbo == 0 && n_pg == 1) {
+            constexpr int kMaxItems = 8;                     // 256 rows x 8 chunks / 256 threads (cta_group 1); 4 with cta_group 2
+            const int n_items = n_pairs * p.T_box;           // <= 128 rows * 8 chunks
+            uint32_t it_src[kMaxItems], it_dst[kMaxItems], it_t[kMaxItems];
+            int n_my = 0;
+#pragma unroll
+            for (int i = 0; i < kMaxItems; ++i) {
+                const int item = ptid + i * (kProducerWarps * 32);
+                it_src[i] = it_dst[i] = 0u; it_t[i] = 0u;
+                if (item < n_items) {
+                    const int t = item / n_pairs, pr = item - t * n_pairs;
+                    const uint32_t j = pr >> 3, q = pr & 7, r = static_cast<uint32_t>(t * p.Jh) + j;
+                    it_src[i] = static_cast<uint32_t>(pr) * 8u * wb;
+                    it_dst[i] = r * 128u + ((q ^ (r & 7u)) << 4);      // slots are 1024-B aligned
+                    it_t[i] = (t < p.T_live) ? static_cast<uint32_t>(t) : 32u;     // 32: padding step, zero row
+                    n_my = i + 1;
+                }
+            }
+            uint32_t sb = 0u, pb = 0u, sw = 0u, pw = 0u;
+            for (long long i_kb = 0; i_kb < total_kb; ++i_kb) {
+                mbar_wait_parked(&w_full[sw], pw);
+                mbar_wait_parked(&b_empty[sb], pb ^ 1u);
+                const uint32_t wslot = w_base + sw * p.slot_w;
+                const uint32_t slot = b_base + sb * p.slot_b;
+#pragma unroll
+                for (int i = 0; i < kMaxItems; ++i) {
+                    if (i >= n_my) break;
+                    uint32_t P[4];
+                    const uint32_t src = wslot + it_src[i];
+                    if (wb == 1) {
+                        const uint2 v = lds_v2(src);
+                        P[0] = __byte_perm(v.x, 0u, 0x4140); P[1] = __byte_perm(v.x, 0u, 0x4342);
+                        P[2] = __byte_perm(v.y, 0u, 0x4140); P[3] = __byte_perm(v.y, 0u, 0x4342);
+                    } else if (wb == 2) {
+                        const uint4 v = lds_v4(src);
+                        P[0] = v.x; P[1] = v.y; P[2] = v.z; P[3] = v.w;
+                    } else {
+                        const uint4 v = lds_v4(src), c = lds_v4(src + 16u);
+                        P[0] = ((v.x >> p.in_bit0) & tmask) | (((v.y >> p.in_bit0) & tmask) << 16);
+                        P[1] = ((v.z >> p.in_bit0) & tmask) | (((v.w >> p.in_bit0) & tmask) << 16);
+                        P[2] = ((c.x >> p.in_bit0) & tmask) | (((c.y >> p.in_bit0) & tmask) << 16);
+                        P[3] = ((c.z >> p.in_bit0) & tmask) | (((c.w >> p.in_bit0) & tmask) << 16);
+                    }
+                    const uint32_t sh = (wb == 4 ? 0u : static_cast<uint32_t>(p.in_bit0)) + (it_t[i] & 31u);
+                    const uint32_t m = (it_t[i] < 32u) ? 0x00010001u : 0u;
+                    uint4 o;
+                    o.x = ((P[0] >> sh) & m) * one; o.y = ((P[1] >> sh) & m) * one;
+                    o.z = ((P[2] >> sh) & m) * one; o.w = ((P[3] >> sh) & m) * one;
+                    sts_v4(slot + it_dst[i], o);
+                }
+                fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&b_ready[sb]); mbar_arrive(&w_empty[sw]); }
+                if (++sb == static_cast<uint32_t>(stages_b)) { sb = 0u; pb ^= 1u; }
+                if (++sw == static_cast<uint32_t>(stages_w)) { sw = 0u; pw ^= 1u; }
+            }
+        } else {
+        // ---- general path (conv halo tiles; T_box > 16)
         // group g starts on stage g of both rings (n_pg <= stages, so its first phase parity is 0)
         uint32_t sb = static_cast<uint32_t>(grp), pb = 0u, sw = static_cast<uint32_t>(grp), pw = 0u;
         for (long long i_kb = grp; i_kb < total_kb; i_kb += n_pg) {
@@ -388,6 +452,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             // this group's next k-block is n_pg ring stages further
             sb += n_pg; if (sb >= static_cast<uint32_t>(stages_b)) { sb -= stages_b; pb ^= 1u; }
             sw += n_pg; if (sw >= static_cast<uint32_t>(stages_w)) { sw -= stages_w; pw ^= 1u; }
+        }
         }
     } else if (warp >= 4) {
         // ============================================ LIF epilogue (2 groups x 4 warps)
