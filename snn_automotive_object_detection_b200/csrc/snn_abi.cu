@@ -441,13 +441,14 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
     const int T_live = T - 1;
     float* lut = reinterpret_cast<float*>(wsp + ws.lut_off);
 
-    build_lut_kernel<<<(tb * 256 + 255) / 256, 256, 0, st>>>(T, tb, lut);
-    CUDA_TRY(cudaGetLastError()); ++g_launches;
-
     // The LI readout (and the spike counts) are fused into the GEMM epilogue when a CTA pair covers all
     // output channels (cta_group 2, C_in == 256) and the 5A outputs fit one pass; otherwise a separate
-    // readout kernel consumes the spike trains.
+    // readout kernel consumes the spike trains (and needs the kappa lookup table).
     const bool fused = T_live > 0 && tc.cg == 2 && C_in == 256 && 5 * A <= kRoMaxOut;
+    if (!fused) {
+        build_lut_kernel<<<(tb * 256 + 255) / 256, 256, 0, st>>>(T, tb, lut);
+        CUDA_TRY(cudaGetLastError()); ++g_launches;
+    }
     void* trains[kMaxLevels];
     for (int l = 0; l < n_levels; ++l) {
         trains[l] = (spike_trains_out && spike_trains_out[l]) ? spike_trains_out[l] : (wsp + ws.tr_off[l]);
@@ -506,8 +507,23 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
         }
         if (fused) {
             p.fuse_readout = 1;
+            // the two CTAs of a pair add their channel halves onto zeroed outputs.  Outputs the caller laid out
+            // back to back (logits of all levels, then box deltas of all levels) are cleared with ONE memset.
+            bool adjacent = true;
+            const uint8_t* expect = reinterpret_cast<const uint8_t*>(logits_out[0]);
+            for (int l = 0; l < n_levels && adjacent; ++l) {
+                adjacent = reinterpret_cast<const uint8_t*>(logits_out[l]) == expect;
+                expect += static_cast<size_t>(N) * A * H[l] * W[l] * 4;
+            }
+            for (int l = 0; l < n_levels && adjacent; ++l) {
+                adjacent = reinterpret_cast<const uint8_t*>(bbox_out[l]) == expect;
+                expect += static_cast<size_t>(N) * 4 * A * H[l] * W[l] * 4;
+            }
+            if (adjacent)
+                CUDA_TRY(cudaMemsetAsync(logits_out[0], 0, expect - reinterpret_cast<const uint8_t*>(logits_out[0]), st));
             for (int l = 0; l < n_levels; ++l) {
                 if (!(spike_trains_out && spike_trains_out[l])) p.lv[l].trains = nullptr;   // nobody reads them
+                if (adjacent) continue;
                 CUDA_TRY(cudaMemsetAsync(logits_out[l], 0, static_cast<size_t>(N) * A * H[l] * W[l] * 4, st));
                 CUDA_TRY(cudaMemsetAsync(bbox_out[l], 0, static_cast<size_t>(N) * 4 * A * H[l] * W[l] * 4, st));
             }

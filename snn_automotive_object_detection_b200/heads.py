@@ -140,8 +140,15 @@ class RPNHeadSNN(nn.Module):
         C, A = self.in_channels, self.num_anchors
         Hs = (ctypes.c_int * L)(*[f.shape[2] for f in feats])
         Ws = (ctypes.c_int * L)(*[f.shape[3] for f in feats])
-        logits = [torch.empty(N, A, f.shape[2], f.shape[3], device=dev, dtype=torch.float32) for f in feats]
-        bbox = [torch.empty(N, 4 * A, f.shape[2], f.shape[3], device=dev, dtype=torch.float32) for f in feats]
+        # one allocation, outputs back to back (all logits, then all box deltas): the library clears them with a
+        # single memset before the two CTAs of a pair add their channel halves
+        sizes = [N * A * f.shape[2] * f.shape[3] for f in feats]
+        flat = torch.empty(5 * sum(sizes), device=dev, dtype=torch.float32)
+        logits, bbox, off = [], [], 0
+        for f, n in zip(feats, sizes):
+            logits.append(flat[off:off + n].view(N, A, f.shape[2], f.shape[3])); off += n
+        for f, n in zip(feats, sizes):
+            bbox.append(flat[off:off + 4 * n].view(N, 4 * A, f.shape[2], f.shape[3])); off += 4 * n
         if N == 0:
             return logits, bbox
         w_prep = self._w_shared.get(self.shared_conv.weight, mode, conv=True)
