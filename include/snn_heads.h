@@ -112,6 +112,23 @@ int snn_fc_lif_layer(const void* z_words, int in_word_bytes, int in_bit0, int R,
                      int T_live, int mode, const void* w_prep, void* trains, float* dump, int cta_group,
                      snn_stream_t stream);
 
+/* ---- "next" row 8f-2: MultiScaleRoIAlign fused with the box head's encoder --------------------------------------
+ * (roi_heads.py:1217 box_roi_pool -> faster_rcnn.py:474-494 flatten + lif_current_encoder).  feat_ptrs[l]: FPN level l,
+ * fp32 NCHW [N][C][H[l]][W[l]], scales[l] = its spatial scale (2^-k); rois [R][5] = (batch index, x1, y1, x2, y2) in
+ * image coordinates, roi_level [R] = the level torchvision's LevelMapper assigns; torchvision roi_align arithmetic
+ * (aligned = False, sampling_ratio samples per bin).  words_out [R][C*P*P] spike-train words of 1/2/4 bytes for
+ * T_live <= 8/16/32 (k = c*P*P + ph*P + pw, faster_rcnn.py:474); optional pooled_out [R][C*P*P] fp32 (tests). */
+int snn_roi_align_encode(const void* const* feat_ptrs, const int* H, const int* W, const float* scales, int n_levels,
+                         int C, const float* rois, const int* roi_level, int R, int pooled_size, int sampling_ratio,
+                         int T_live, void* words_out, float* pooled_out, snn_stream_t stream);
+/* snn_box_head_forward on input that is already encoded: words [R][K] of snn_train_word_bytes-like size for T - 1 steps
+ * (1/2/4 bytes for T - 1 <= 8/16/32), e.g. from snn_roi_align_encode(..., T_live = T - 1, ...). */
+int snn_box_head_forward_encoded(const void* words, int R, int K, int Hdim, int C, int n_box_out, int T, int mode,
+                                 const void* w6_prep, const void* w7_prep, const float* w_cls, const float* w_bbox,
+                                 float* cls_out, float* bbox_out, void* spk6_trains, void* spk7_trains,
+                                 unsigned int* spike_counts_out, void* workspace, size_t workspace_bytes,
+                                 snn_stream_t stream);
+
 /* ---- "next" row 8f-1: the proposal selection that follows RPNHeadSNN in RegionProposalNetwork.forward ----------
  * (rpn.py:636-670: concat_box_prediction_layers + AnchorGenerator + BoxCoder.decode + sigmoid, applied by the
  * reference to ALL A*H*W anchors of every level before the per-level top-k).  The top-k is taken on the head's

@@ -101,7 +101,27 @@ def main():
                 if len(pos):
                     mask[pos] = 0
 
-    line = {"rows": "SURVEY 8f-1 / 8f-4", "shapes": "cityscapes batch 2 (294 624 anchors/img, 1000 RoIs/img)",
+    # ---- RoIAlign -> encoder: torchvision MultiScaleRoIAlign + the box head's encoder kernel, against the fused kernel
+    import ctypes
+    from collections import OrderedDict
+    from torchvision.ops import MultiScaleRoIAlign
+    from snn_automotive_object_detection_b200 import _lib
+    fmaps = OrderedDict((str(i), torch.randn(N, 256, h, w, device=dev)) for i, (h, w) in enumerate(LEVELS[:4]))
+    pooler = MultiScaleRoIAlign(featmap_names=["0", "1", "2", "3"], output_size=7, sampling_ratio=2)
+    fused = DP.FusedRoIAlignEncoder.from_pooler(pooler, 12)
+    lib = _lib.load()
+    zbuf = torch.empty(N * R, 12544, dtype=torch.int16, device=dev)
+
+    def pool_then_encode():
+        x = pooler(fmaps, props, [IMG] * N).flatten(1).contiguous()
+        lib.snn_encode_rows(ctypes.c_void_p(x.data_ptr()), N * R, 12544, 11, ctypes.c_void_p(zbuf.data_ptr()),
+                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+    def fused_pool():
+        return fused(fmaps, props, [IMG] * N)
+
+    line = {"rows": "SURVEY 8f-1 / 8f-2 / 8f-4",
+            "roi_align_encode_ms": {"torchvision_roi_align_then_encoder": timed(pool_then_encode), "fused": timed(fused_pool)}, "shapes": "cityscapes batch 2 (294 624 anchors/img, 1000 RoIs/img)",
             "rpn_select_ms": {"reference_path": timed(reference_path), "ours": timed(ours)},
             "postprocess_ms": {"reference_python_mask_loop_only": timed(loop_mask_only, iters=3), "ours_whole_function": timed(vectorised)}}
     print(json.dumps(line))

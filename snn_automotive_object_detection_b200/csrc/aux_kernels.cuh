@@ -353,7 +353,6 @@ __global__ void __launch_bounds__(256) readout_rows_kernel(const TrainT* __restr
     }
 }
 
-}  // namespace snn
 
 // ------------------------------------------------------- RPN proposal decode
 // The step after RPNHeadSNN in RegionProposalNetwork.forward (rpn.py:636-670): the reference permutes all
@@ -415,3 +414,93 @@ __global__ void __launch_bounds__(256) rpn_decode_selected_kernel(const __grid_c
     if (p.logit_out != nullptr) p.logit_out[i] = logit;
     if (p.ref_index != nullptr) p.ref_index[i] = L.anchor_begin + (static_cast<long long>(h) * L.W + w) * p.A + a;
 }
+
+// ------------------------------------------------- RoIAlign fused with the encoder
+// The step before FastRCNNPredictorSNNFull in RoIHeadsSNN.forward (roi_heads.py:1217 -> faster_rcnn.py:474-494):
+// MultiScaleRoIAlign writes [R][C][7][7] fp32 only for the encoder to threshold it into spikes.  Here one thread
+// computes 8 consecutive k = c*49 + ph*7 + pw of a RoI with torchvision's roi_align arithmetic (aligned = False,
+// sampling_ratio samples per bin, bilinear_interpolate with its border rules) and feeds them straight into the
+// lock-step encoder: the pooled tensor never exists in HBM (50 MB written + read per image).
+constexpr int kRoiMaxLevels = 8;
+struct RoiLevel { const float* x; int H, W; float scale; };
+struct RoiEncParams {
+    RoiLevel lv[kRoiMaxLevels];
+    int n_levels, C, R, P, sampling, T_live, wb;
+    const float* rois;        // [R][5]: batch index, x1, y1, x2, y2 (image coordinates)
+    const int* roi_level;     // [R] FPN level of each RoI (torchvision LevelMapper)
+    uint8_t* words;           // [R][C*P*P] spike-train words of wb bytes
+    float* pooled;            // nullable (tests): [R][C*P*P] the RoIAlign values themselves
+};
+
+__device__ __forceinline__ float roi_bilinear(const float* __restrict__ f, int H, int W, float y, float x) {
+    if (y < -1.0f || y > static_cast<float>(H) || x < -1.0f || x > static_cast<float>(W)) return 0.f;
+    if (y <= 0.f) y = 0.f;
+    if (x <= 0.f) x = 0.f;
+    int y_low = static_cast<int>(y), x_low = static_cast<int>(x);
+    int y_high, x_high;
+    if (y_low >= H - 1) { y_high = y_low = H - 1; y = static_cast<float>(y_low); } else { y_high = y_low + 1; }
+    if (x_low >= W - 1) { x_high = x_low = W - 1; x = static_cast<float>(x_low); } else { x_high = x_low + 1; }
+    const float ly = y - y_low, lx = x - x_low, hy = 1.f - ly, hx = 1.f - lx;
+    const float v1 = __ldg(f + y_low * W + x_low), v2 = __ldg(f + y_low * W + x_high);
+    const float v3 = __ldg(f + y_high * W + x_low), v4 = __ldg(f + y_high * W + x_high);
+    const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+    return w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
+}
+
+__global__ void __launch_bounds__(256) roi_align_encode_kernel(const __grid_constant__ RoiEncParams p) {
+    const int PP = p.P * p.P;
+    const int K = p.C * PP;
+    const size_t total8 = static_cast<size_t>(p.R) * K / 8;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / (K / 8));
+        const int k0 = static_cast<int>(i - static_cast<size_t>(r) * (K / 8)) * 8;
+        const float* roi = p.rois + 5 * static_cast<size_t>(r);
+        const RoiLevel& L = p.lv[p.roi_level[r]];
+        const int b = static_cast<int>(roi[0]);
+        const float rsw = roi[1] * L.scale, rsh = roi[2] * L.scale, rew = roi[3] * L.scale, reh = roi[4] * L.scale;
+        const float roi_w = fmaxf(rew - rsw, 1.f), roi_h = fmaxf(reh - rsh, 1.f);
+        const float bin_h = roi_h / static_cast<float>(p.P), bin_w = roi_w / static_cast<float>(p.P);
+        const int gh = p.sampling > 0 ? p.sampling : static_cast<int>(ceilf(roi_h / p.P));
+        const int gw = p.sampling > 0 ? p.sampling : static_cast<int>(ceilf(roi_w / p.P));
+        const float count = fmaxf(static_cast<float>(gh * gw), 1.f);
+        float xv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = k0 + e;
+            const int c = k / PP, rem = k - c * PP;
+            const int ph = rem / p.P, pw = rem - ph * p.P;
+            const float* f = L.x + (static_cast<size_t>(b) * p.C + c) * L.H * L.W;
+            float acc = 0.f;
+            for (int iy = 0; iy < gh; ++iy) {
+                const float y = rsh + ph * bin_h + static_cast<float>(iy + .5f) * bin_h / static_cast<float>(gh);
+                for (int ix = 0; ix < gw; ++ix) {
+                    const float x = rsw + pw * bin_w + static_cast<float>(ix + .5f) * bin_w / static_cast<float>(gw);
+                    acc += roi_bilinear(f, L.H, L.W, y, x);
+                }
+            }
+            xv[e] = acc / count;
+        }
+        if (p.pooled != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) p.pooled[static_cast<size_t>(r) * K + k0 + e] = xv[e];
+        }
+        uint32_t tr[8];
+        encode_trains<8>(xv, p.T_live, tr);
+        uint8_t* z = p.words;
+        if (p.wb == 1) {
+            uint2 o;
+            o.x = tr[0] | (tr[1] << 8) | (tr[2] << 16) | (tr[3] << 24);
+            o.y = tr[4] | (tr[5] << 8) | (tr[6] << 16) | (tr[7] << 24);
+            reinterpret_cast<uint2*>(z)[i] = o;
+        } else if (p.wb == 2) {
+            reinterpret_cast<uint4*>(z)[i] =
+                make_uint4(tr[0] | (tr[1] << 16), tr[2] | (tr[3] << 16), tr[4] | (tr[5] << 16), tr[6] | (tr[7] << 16));
+        } else {
+            reinterpret_cast<uint4*>(z)[2 * i] = make_uint4(tr[0], tr[1], tr[2], tr[3]);
+            reinterpret_cast<uint4*>(z)[2 * i + 1] = make_uint4(tr[4], tr[5], tr[6], tr[7]);
+        }
+    }
+}
+
+}  // namespace snn

@@ -570,11 +570,11 @@ size_t snn_box_head_workspace_bytes(int R, int K, int Hdim, int T, int mode) {
     return ws.total;
 }
 
-int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box_out, int T, int mode,
-                         const void* w6_prep, const void* w7_prep, const float* w_cls, const float* w_bbox,
-                         float* cls_out, float* bbox_out, void* spk6_trains, void* spk7_trains,
-                         unsigned int* spike_counts_out, void* workspace, size_t workspace_bytes,
-                         snn_stream_t stream) {
+static int box_head_forward_impl(const void* x, bool x_is_words, int R, int K, int Hdim, int C, int n_box_out, int T,
+                                 int mode, const void* w6_prep, const void* w7_prep, const float* w_cls,
+                                 const float* w_bbox, float* cls_out, float* bbox_out, void* spk6_trains,
+                                 void* spk7_trains, unsigned int* spike_counts_out, void* workspace,
+                                 size_t workspace_bytes, snn_stream_t stream) {
     g_launches = 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (!x || !w6_prep || !w7_prep || !w_cls || !w_bbox || !cls_out || !bbox_out || !workspace)
@@ -598,7 +598,9 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
     float* lut = reinterpret_cast<float*>(wsp + ws.lut_off);
     void* tr6 = spk6_trains ? spk6_trains : (wsp + ws.tr6_off);
     void* tr7 = spk7_trains ? spk7_trains : (wsp + ws.tr7_off);
-    void* z = wsp + ws.z_off;
+    // x_is_words: the caller already holds the encoder's spike-train words (snn_roi_align_encode), [R][K] words of
+    // word_bytes(T - 1) bytes; bits beyond the live steps are ignored by the producers
+    const void* z = x_is_words ? x : static_cast<const void*>(wsp + ws.z_off);
 
     build_lut_kernel<<<(tb * 256 + 255) / 256, 256, 0, st>>>(T, tb, lut);
     CUDA_TRY(cudaGetLastError()); ++g_launches;
@@ -607,12 +609,12 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
     // the fc6 spike statistics are wanted.  fc7 is live for steps 1..T-2.
     const int T_live6 = stats ? T - 1 : T - 2;
     const int T_live7 = T - 2;
-    {
+    if (!x_is_words) {
         const size_t total8 = static_cast<size_t>(R) * K / 8;
         const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
         phase_begin(PH_ENC_BOX, st);
         encode_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), total8, T_live6, word_bytes(T - 1),
-                                                   reinterpret_cast<uint8_t*>(z));
+                                                   wsp + ws.z_off);
         phase_end(PH_ENC_BOX, st);
         CUDA_TRY(cudaGetLastError()); ++g_launches;
     }
@@ -634,6 +636,49 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
     if (e != cudaSuccess) return fail(SNN_E_CUDA, "readout_rows launch failed: %s", cudaGetErrorString(e));
     ++g_launches;
     phase_end(PH_RO_BOX, st);
+    return SNN_OK;
+}
+
+int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box_out, int T, int mode,
+                         const void* w6_prep, const void* w7_prep, const float* w_cls, const float* w_bbox,
+                         float* cls_out, float* bbox_out, void* spk6_trains, void* spk7_trains,
+                         unsigned int* spike_counts_out, void* workspace, size_t workspace_bytes,
+                         snn_stream_t stream) {
+    return box_head_forward_impl(x, false, R, K, Hdim, C, n_box_out, T, mode, w6_prep, w7_prep, w_cls, w_bbox, cls_out,
+                                 bbox_out, spk6_trains, spk7_trains, spike_counts_out, workspace, workspace_bytes, stream);
+}
+
+int snn_box_head_forward_encoded(const void* words, int R, int K, int Hdim, int C, int n_box_out, int T, int mode,
+                                 const void* w6_prep, const void* w7_prep, const float* w_cls, const float* w_bbox,
+                                 float* cls_out, float* bbox_out, void* spk6_trains, void* spk7_trains,
+                                 unsigned int* spike_counts_out, void* workspace, size_t workspace_bytes,
+                                 snn_stream_t stream) {
+    return box_head_forward_impl(words, true, R, K, Hdim, C, n_box_out, T, mode, w6_prep, w7_prep, w_cls, w_bbox, cls_out,
+                                 bbox_out, spk6_trains, spk7_trains, spike_counts_out, workspace, workspace_bytes, stream);
+}
+
+int snn_roi_align_encode(const void* const* feat_ptrs, const int* H, const int* W, const float* scales, int n_levels,
+                         int C, const float* rois, const int* roi_level, int R, int pooled_size, int sampling_ratio,
+                         int T_live, void* words_out, float* pooled_out, snn_stream_t stream) {
+    if (!feat_ptrs || !H || !W || !scales || !rois || !roi_level || !words_out)
+        return fail(SNN_E_ARG, "roi_align_encode: null argument");
+    if (n_levels < 1 || n_levels > kRoiMaxLevels || C < 1 || R < 1 || pooled_size < 1 || T_live < 1 || T_live > 32 ||
+        (C * pooled_size * pooled_size) % 8 != 0)
+        return fail(SNN_E_ARG, "roi_align_encode: unsupported sizes (levels %d, C %d, R %d, pooled %d, T_live %d)", n_levels, C,
+                    R, pooled_size, T_live);
+    RoiEncParams p;
+    memset(&p, 0, sizeof(p));
+    for (int l = 0; l < n_levels; ++l) {
+        if (!feat_ptrs[l] || H[l] < 1 || W[l] < 1) return fail(SNN_E_ARG, "roi_align_encode: level %d: bad argument", l);
+        p.lv[l].x = reinterpret_cast<const float*>(feat_ptrs[l]); p.lv[l].H = H[l]; p.lv[l].W = W[l]; p.lv[l].scale = scales[l];
+    }
+    p.n_levels = n_levels; p.C = C; p.R = R; p.P = pooled_size; p.sampling = sampling_ratio; p.T_live = T_live;
+    p.wb = word_bytes(T_live);
+    p.rois = rois; p.roi_level = roi_level; p.words = reinterpret_cast<uint8_t*>(words_out); p.pooled = pooled_out;
+    const size_t total8 = static_cast<size_t>(R) * C * pooled_size * pooled_size / 8;
+    const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 32 ? 148 * 32 : (total8 + 255) / 256);
+    roi_align_encode_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
     return SNN_OK;
 }
 

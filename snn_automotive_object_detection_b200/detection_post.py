@@ -201,3 +201,71 @@ def attach_fast_postprocessing(model):
 
 
 BBOX_XFORM_CLIP = math.log(1000.0 / 16)
+
+
+# --------------------------------------------------------------------------- rank 2
+class FusedRoIAlignEncoder(torch.nn.Module):
+    """Drop-in for `RoIHeadsSNN.box_roi_pool` (a torchvision MultiScaleRoIAlign; roi_heads.py:1217) when the box head
+    is the B200 `FastRCNNPredictorSNNFull`: RoIAlign and the head's constant-current encoder run in ONE kernel
+    (csrc/aux_kernels.cuh::roi_align_encode_kernel), so the pooled [R, C, 7, 7] fp32 tensor (50 MB per image written
+    and read back) never exists.  forward(features, proposals, image_shapes) has the pooler's signature and returns
+    `EncodedRoIs` (spike-train words [R, C*7*7] for num_steps - 1 encoder steps), which the head's forward accepts in
+    place of the pooled tensor.  Level assignment and scales are torchvision's own (LevelMapper, _setup_scales)."""
+
+    def __init__(self, featmap_names: Sequence[str], output_size: int, sampling_ratio: int, num_steps: int,
+                 canonical_scale: int = 224, canonical_level: int = 4):
+        super().__init__()
+        self.featmap_names = list(featmap_names)
+        self.output_size = int(output_size[0] if isinstance(output_size, (tuple, list)) else output_size)
+        self.sampling_ratio = int(sampling_ratio)
+        self.num_steps = int(num_steps)
+        self.canonical_scale, self.canonical_level = canonical_scale, canonical_level
+        self.return_pooled = False                      # tests: also keep the RoIAlign values
+        self.last_pooled = None
+
+    @classmethod
+    def from_pooler(cls, pooler, num_steps: int):
+        return cls(pooler.featmap_names, pooler.output_size, pooler.sampling_ratio, num_steps,
+                   getattr(pooler, "canonical_scale", 224), getattr(pooler, "canonical_level", 4))
+
+    @torch.no_grad()
+    def forward(self, features: Dict[str, Tensor], proposals: List[Tensor], image_shapes: List[Tuple[int, int]]):
+        from torchvision.ops.poolers import _setup_scales, _convert_to_roi_format
+        from .heads import EncodedRoIs, _TRAIN_DTYPE
+        lib = _lib.load()
+        feats = [features[k].detach().float().contiguous() for k in self.featmap_names if k in features]
+        if not feats or not feats[0].is_cuda:
+            raise RuntimeError("FusedRoIAlignEncoder: expected CUDA feature maps (B200); there is no CPU fallback")
+        dev = feats[0].device
+        scales, mapper = _setup_scales(feats, image_shapes, self.canonical_scale, self.canonical_level)
+        rois = _convert_to_roi_format(proposals).float().contiguous()              # [R, 5]
+        R, C, P = rois.shape[0], feats[0].shape[1], self.output_size
+        T_live = self.num_steps - 1
+        wb = 1 if T_live <= 8 else 2 if T_live <= 16 else 4
+        words = torch.empty(R, C * P * P, device=dev, dtype=_TRAIN_DTYPE[wb])
+        pooled = torch.empty(R, C * P * P, device=dev, dtype=torch.float32) if self.return_pooled else None
+        if R > 0:
+            levels = (mapper(proposals) if len(feats) > 1 else torch.zeros(R, dtype=torch.int64, device=dev)).to(torch.int32).contiguous()
+            L = len(feats)
+            VP, IA, FA = ctypes.c_void_p * L, ctypes.c_int * L, ctypes.c_float * L
+            with torch.cuda.device(dev):
+                rc = lib.snn_roi_align_encode(
+                    VP(*[f.data_ptr() for f in feats]), IA(*[f.shape[2] for f in feats]), IA(*[f.shape[3] for f in feats]),
+                    FA(*[float(s) for s in scales]), L, C, ctypes.c_void_p(rois.data_ptr()), ctypes.c_void_p(levels.data_ptr()),
+                    R, P, self.sampling_ratio, T_live, ctypes.c_void_p(words.data_ptr()),
+                    ctypes.c_void_p(pooled.data_ptr()) if pooled is not None else None,
+                    ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            _lib.check(rc, "snn_roi_align_encode")
+        self.last_pooled = pooled
+        return EncodedRoIs(words, self.num_steps)
+
+
+def attach_fused_roi_pool(model):
+    """Replace `roi_heads.box_roi_pool` by the fused RoIAlign + encoder (eval only; the reference's RoIHeadsSNN, whose
+    forward hands the pooler's output straight to `box_head_and_predictor`, roi_heads.py:1217-1230)."""
+    rh = model.roi_heads
+    head = getattr(rh, "box_head_and_predictor", None)
+    if head is None:
+        raise RuntimeError("attach_fused_roi_pool: needs the reference's RoIHeadsSNN (box_head_and_predictor)")
+    rh.box_roi_pool = FusedRoIAlignEncoder.from_pooler(rh.box_roi_pool, int(head.num_steps))
+    return model

@@ -86,6 +86,13 @@ def _require_cuda(t: Tensor, what: str):
         raise RuntimeError(f"{what}: expected a CUDA tensor (B200); the spiking heads have no CPU fallback")
 
 
+class EncodedRoIs(NamedTuple):
+    """RoI features that are already the box head's encoder output (detection_post.FusedRoIAlignEncoder):
+    `words` [R, K] spike-train words for num_steps - 1 encoder steps."""
+    words: Tensor
+    num_steps: int
+
+
 class RPNHeadSNN(nn.Module):
     """Spiking RPN head (reference: rpn.py:33-121).
 
@@ -212,9 +219,17 @@ class FastRCNNPredictorSNNFull(nn.Module):
         lib = _lib.load()
         mode = _lib.mode_id(self.mode)
         T = int(self.num_steps)
-        _require_cuda(x, "FastRCNNPredictorSNNFull.forward")
-        x = x.detach().flatten(start_dim=1).float().contiguous()          # faster_rcnn.py:474
-        R, K = x.shape
+        encoded = isinstance(x, EncodedRoIs)
+        if encoded:                      # RoIAlign + encoder already fused upstream
+            if x.num_steps != T:
+                raise RuntimeError(f"FastRCNNPredictorSNNFull.forward: RoIs were encoded for {x.num_steps} steps, head runs {T}")
+            x = x.words
+            _require_cuda(x, "FastRCNNPredictorSNNFull.forward")
+            R, K = x.shape
+        else:
+            _require_cuda(x, "FastRCNNPredictorSNNFull.forward")
+            x = x.detach().flatten(start_dim=1).float().contiguous()          # faster_rcnn.py:474
+            R, K = x.shape
         if K != self.in_channels:
             raise RuntimeError(f"FastRCNNPredictorSNNFull.forward: expected {self.in_channels} features, got {K}")
         dev = x.device
@@ -240,7 +255,8 @@ class FastRCNNPredictorSNNFull(nn.Module):
             tr7 = torch.empty(R, Hd, device=dev, dtype=tdt)
         counts = torch.zeros(2, R, device=dev, dtype=torch.int32) if self.record_rates else None
         with torch.cuda.device(dev):
-            rc = lib.snn_box_head_forward(_ptr(x), R, K, Hd, C, nb, T, mode, _ptr(w6), _ptr(w7), _ptr(w_cls), _ptr(w_box),
+            fwd = lib.snn_box_head_forward_encoded if encoded else lib.snn_box_head_forward
+            rc = fwd(_ptr(x), R, K, Hd, C, nb, T, mode, _ptr(w6), _ptr(w7), _ptr(w_cls), _ptr(w_box),
                                           _ptr(cls), _ptr(box), _ptr(tr6), _ptr(tr7), _ptr(counts), _ptr(ws), ws.numel(),
                                           _stream(dev))
         _lib.check(rc, "snn_box_head_forward")

@@ -120,3 +120,43 @@ def test_ref_index_points_at_the_reference_anchor(golden_dir):
     flat = torch.cat([o.permute(0, 2, 3, 1).reshape(o.shape[0], -1) for o in obj], dim=1)   # (level, h, w, a)
     got = torch.sigmoid(torch.gather(flat, 1, ref_index))
     assert torch.allclose(got, probs, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_fused_roi_align_encoder_matches_torchvision_pool_then_encode():
+    """RoIAlign fused with the box head's encoder against torchvision's MultiScaleRoIAlign followed by
+    the head's own encoder, and the box head outputs on both inputs."""
+    from collections import OrderedDict
+    from torchvision.ops import MultiScaleRoIAlign
+    from oracle import snn_oracle as O
+    import snn_automotive_object_detection_b200 as S
+    torch.manual_seed(3)
+    N, C, T = 2, 256, 12
+    img = (256, 384)
+    feats = OrderedDict((str(i), torch.randn(N, C, img[0] // s, img[1] // s, device="cuda")) for i, s in enumerate((4, 8, 16, 32)))
+    feats["pool"] = torch.randn(N, C, 4, 6, device="cuda")
+    props = []
+    for _ in range(N):
+        xy = torch.rand(60, 2, device="cuda") * torch.tensor([300.0, 200.0], device="cuda")
+        wh = torch.rand(60, 2, device="cuda") ** 2 * torch.tensor([300.0, 220.0], device="cuda") + 2.0
+        props.append(torch.cat([xy, xy + wh], dim=1))
+    props[0][0] = torch.tensor([-20.0, -10.0, 500.0, 300.0], device="cuda")      # sticks out of the image
+    shapes = [img, (240, 360)]
+    pooler = MultiScaleRoIAlign(featmap_names=["0", "1", "2", "3"], output_size=7, sampling_ratio=2)
+    want = pooler(feats, props, shapes)                                           # [R, C, 7, 7]
+    fused = S.FusedRoIAlignEncoder.from_pooler(pooler, T)
+    fused.return_pooled = True
+    enc = fused(feats, props, shapes)
+    torch.cuda.synchronize()
+    got = fused.last_pooled.view_as(want)
+    assert torch.allclose(got, want, atol=2e-5, rtol=1e-5), (got - want).abs().max().item()
+    # the words are the encoder's spike trains of the pooled values (bit-exact w.r.t. the kernel's own pooled values)
+    ref_spk = torch.stack(O.encoder_spikes(fused.last_pooled.cpu(), T - 1))       # [T-1, R, K]
+    from snn_automotive_object_detection_b200.heads import unpack_trains
+    assert torch.equal(unpack_trains(enc.words.cpu(), T - 1).float(), ref_spk)
+    # and the head gives the same outputs from either input (up to near-threshold flips of RoIAlign rounding)
+    head = S.FastRCNNPredictorSNNFull(C * 49, 1024, 9, T).cuda()
+    cls_a, box_a = head(want)
+    cls_b, box_b = head(enc)
+    bad = ((cls_a - cls_b).abs().amax(dim=1) > 1e-3 * cls_a.abs().max()).float().mean().item()
+    assert bad <= 0.05, bad
