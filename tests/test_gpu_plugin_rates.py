@@ -1,11 +1,13 @@
 """Spike-rate report (reference section a8 format), the torchvision plug-in point, full-size parity."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import snn_oracle as O
 import snn_automotive_object_detection_b200 as S
-from tests._util import unpack_trains, flip_mask
+from tests._util import unpack_trains, flip_mask, spike_agreement
 
 pytestmark = pytest.mark.gpu
 
@@ -16,10 +18,11 @@ def test_rpn_spike_rate_report_matches_oracle_format():
     g = torch.Generator().manual_seed(9)
     feats = [torch.randn(2, 256, 10, 14, generator=g), torch.randn(2, 256, 5, 7, generator=g)]
     T = 8
-    m = S.RPNHeadSNN(256, 3, T)
+    m = S.RPNHeadSNN(256, 3, T, mode=mode)
     with torch.no_grad():
         m.shared_conv.weight.copy_(w[0]); m.conv_cls.weight.copy_(w[1]); m.conv_bbox.weight.copy_(w[2])
     m = m.cuda(); m.record_spikes = True
+    stats = {"workload": workload, "mode": mode, "rpn_levels": []}
     m([f.cuda() for f in feats])
     got = S.rpn_spike_rates_and_flops(m)
     want = O.rpn_head_rates(feats, *w, T, 3)
@@ -78,8 +81,9 @@ def test_attach_to_torchvision_faster_rcnn_runs_end_to_end():
         assert bad <= 0.01, (l, bad)
 
 
+@pytest.mark.parametrize("mode", ["fp32_exact", "fp16x2"])
 @pytest.mark.parametrize("workload", ["cityscapes", "bdd"])
-def test_full_size_level_shapes_parity(workload):
+def test_full_size_level_shapes_parity(workload, mode):
     """BASELINE configs 1/2/3 at their real per-image sizes (one image): every FPN level of the
     Cityscapes (768x1536) and BDD (768x1376, ragged widths) shapes against the oracle."""
     levels = O.CITYSCAPES_LEVELS if workload == "cityscapes" else O.BDD_LEVELS
@@ -88,10 +92,11 @@ def test_full_size_level_shapes_parity(workload):
     w = [W["shared_conv"], W["conv_cls"], W["conv_bbox"]]
     feats, rois = O.synthetic_inputs(levels, 1, rois_per_image=300)
     T = 8
-    m = S.RPNHeadSNN(256, 3, T)
+    m = S.RPNHeadSNN(256, 3, T, mode=mode)
     with torch.no_grad():
         m.shared_conv.weight.copy_(w[0]); m.conv_cls.weight.copy_(w[1]); m.conv_bbox.weight.copy_(w[2])
     m = m.cuda(); m.record_spikes = True
+    stats = {"workload": workload, "mode": mode, "rpn_levels": []}
     lo, bb = m([f.cuda() for f in feats])
     torch.cuda.synchronize()
     torch.set_num_threads(max(torch.get_num_threads(), 8))
@@ -99,12 +104,16 @@ def test_full_size_level_shapes_parity(workload):
     for l in range(len(levels)):
         trains = m.last_spike_trains[l].permute(0, 3, 1, 2)
         fm = flip_mask(trains, tr[l]["spk"], T)
+        agree, unexplained = spike_agreement(trains, tr[l]["spk"], tr[l]["v_dec"], T)
+        stats["rpn_levels"].append({"neurons": fm.numel(), "flipped_neurons": int(fm.sum()), "spike_agreement": agree,
+                                    "flips_outside_1e-5_band": unexplained})
+        assert unexplained == 0 and agree >= 0.999
         assert fm.float().mean().item() <= 1e-3, f"level {l}: flipped neurons {fm.float().mean().item()}"
         keep = ~fm.any(dim=1, keepdim=True)
         scale = rlo[l].abs().max().item()
         assert ((lo[l].cpu() - rlo[l]).abs() * keep).max().item() <= 1e-3 * scale
         assert ((bb[l].cpu() - rbb[l]).abs() * keep).max().item() <= 1e-3 * rbb[l].abs().max().item()
-    b = S.FastRCNNPredictorSNNFull(12544, 1024, C, 12)
+    b = S.FastRCNNPredictorSNNFull(12544, 1024, C, 12, mode=mode)
     with torch.no_grad():
         b.fc6.weight.copy_(W["fc6"]); b.fc7.weight.copy_(W["fc7"]); b.cls_score.weight.copy_(W["cls_score"])
         b.bbox_pred.weight.copy_(W["bbox_pred"])
@@ -113,6 +122,12 @@ def test_full_size_level_shapes_parity(workload):
     rc, rd, trb = O.box_head_forward(rois, W["fc6"], W["fc7"], W["cls_score"], W["bbox_pred"], 12, record=True)
     f6 = flip_mask(b.last_spike_trains[0], trb["spk6"], 12); f7 = flip_mask(b.last_spike_trains[1], trb["spk7"], 12)
     assert f6.float().mean().item() <= 1e-3 and f7.float().mean().item() <= 1e-3
+    stats["box"] = {"neurons_per_layer": f6.numel(), "lif6_flipped": int(f6.sum()), "lif7_flipped": int(f7.sum())}
+    out_dir = os.environ.get("SNN_PARITY_STATS_DIR")          # profiles/: measured flip counts of both fp32-grade modes
+    if out_dir:
+        import json
+        with open(os.path.join(out_dir, f"parity_stats_{workload}_{mode}.json"), "w") as f:
+            json.dump(stats, f)
     keep = ~(f6.any(dim=1) | f7.any(dim=1)).unsqueeze(1)
     assert ((cls.cpu() - rc).abs() * keep).max().item() <= 1e-3 * rc.abs().max().item()
     assert ((dl.cpu() - rd).abs() * keep).max().item() <= 1e-3 * rd.abs().max().item()
