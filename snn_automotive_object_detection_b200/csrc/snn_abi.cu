@@ -207,6 +207,21 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
     p.stages_a = kStagesA;
     p.stages_b = kRingBytesB / p.slot_b;
     if (p.stages_b > kMaxStagesB) p.stages_b = kMaxStagesB;
+    if (!p.conv) {
+        // fc: one spike tile per k-block, handed producer -> relay -> MMA -> commit across the CTA pair; that chain
+        // is a few thousand cycles, so the spike ring wants depth more than the weight ring does (4 stages cover
+        // the TMA latency at one 16 KB tile per ~480 cycles)
+        // (measured: 4 weight stages + 7 spike stages beat 6 + 5 with 1-2 pieces per weight; with 3 pieces the
+        // weight ring is the one that must stay deep)
+        const int a_min = p.nsplit >= 3 ? kStagesA : 4;
+        int sb = (ring_total - a_min * kTileBytesA) / p.slot_b;
+        if (sb > kMaxStagesB) sb = kMaxStagesB;
+        if (sb > p.stages_b) {
+            p.stages_b = sb;
+            p.stages_a = (ring_total - sb * p.slot_b) / kTileBytesA;
+            if (p.stages_a > kStagesA) p.stages_a = kStagesA;
+        }
+    }
     if (p.stages_b < 2) {
         p.stages_b = (ring_total - 3 * kTileBytesA) / p.slot_b >= 2 ? 2 : 1;
         p.stages_a = (ring_total - p.stages_b * p.slot_b) / kTileBytesA;

@@ -44,7 +44,7 @@ namespace snn {
 
 constexpr int kMaxLevels = 8;
 constexpr int kStagesA = 6;                 // weight ring: up to 6 stages of 16 KB (p.stages_a; fewer when one spike tile needs > 80 KB)
-constexpr int kMaxStagesB = 6;              // ring of p.stages_b slots of p.slot_b bytes; weight + spike rings share 176 KB
+constexpr int kMaxStagesB = 8;              // ring of p.stages_b slots of p.slot_b bytes; weight + spike rings share 176 KB
 constexpr int kMaxStagesW = 8;              // ring of p.stages_w slots of p.slot_w bytes, 16 KB in total
 constexpr int kTileBytesA = 128 * 128;      // 128 rows x 64 16-bit
 constexpr int kRingBytesB = 80 * 1024;

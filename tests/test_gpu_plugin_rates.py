@@ -18,11 +18,10 @@ def test_rpn_spike_rate_report_matches_oracle_format():
     g = torch.Generator().manual_seed(9)
     feats = [torch.randn(2, 256, 10, 14, generator=g), torch.randn(2, 256, 5, 7, generator=g)]
     T = 8
-    m = S.RPNHeadSNN(256, 3, T, mode=mode)
+    m = S.RPNHeadSNN(256, 3, T)
     with torch.no_grad():
         m.shared_conv.weight.copy_(w[0]); m.conv_cls.weight.copy_(w[1]); m.conv_bbox.weight.copy_(w[2])
     m = m.cuda(); m.record_spikes = True
-    stats = {"workload": workload, "mode": mode, "rpn_levels": []}
     m([f.cuda() for f in feats])
     got = S.rpn_spike_rates_and_flops(m)
     want = O.rpn_head_rates(feats, *w, T, 3)
