@@ -157,7 +157,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.010)        # a 20-step timed region lasts ~55 ms: ~5 samples (a faster poll costs ~1.5 % through the GIL)
 
     def stop(self):
         self._stop_evt.set()
@@ -179,6 +179,19 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device; the spiking heads have no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        # one process per GPU: run (and first-touch the pinned staging buffers) on the CPUs NVML reports as local to
+        # this GPU, so the end-to-end host->device copies of the ranks do not share one socket's memory / PCIe root
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception:
+            pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
