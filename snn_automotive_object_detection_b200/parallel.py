@@ -22,22 +22,48 @@ def shard_images(n_images: int, rank: int, world: int) -> List[int]:
     return list(range(lo, hi))
 
 
-def gather_records(local: torch.Tensor, counts: Sequence[int]) -> torch.Tensor:
-    """All-gather per-image records.  `local` is [n_local, F] on this rank, counts[r] the number of
-    images rank r owns.  Returns [sum(counts), F] in global image order on every rank.  Ragged shards
-    are padded to max(counts) so a single fixed-size all_gather_into_tensor is used."""
+class PendingGather:
+    """Handle of an in-flight record gather (see gather_records_async)."""
+
+    def __init__(self, work, out, counts, feat_shape, world, mx):
+        self.work, self.out, self.counts, self.F, self.world, self.mx = work, out, counts, feat_shape, world, mx
+
+    def result(self) -> torch.Tensor:
+        """Make the current stream wait for the collective and return [sum(counts), F] in global image order."""
+        if self.work is not None:
+            self.work.wait()
+        if self.world == 1:
+            return self.out
+        out = self.out.view(self.world, self.mx, *self.F)
+        return torch.cat([out[r, : self.counts[r]] for r in range(self.world)], dim=0)
+
+
+def gather_records_async(local: torch.Tensor, counts: Sequence[int]) -> PendingGather:
+    """Start the all-gather of per-image records and return immediately: the collective runs on NCCL's own stream
+    behind the kernels that produced `local`, and the caller's stream is NOT made to wait for it until
+    `.result()` -- so the next batch's head kernels overlap the exchange (nothing on the hot path waits on a
+    collective).  `local` is [n_local, F] on this rank, counts[r] the number of images rank r owns; ragged shards
+    are padded to max(counts) so one fixed-size all_gather_into_tensor is used."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return local
+        return PendingGather(None, local, list(counts), tuple(local.shape[1:]), 1, local.shape[0])
     world = dist.get_world_size()
     assert len(counts) == world and local.shape[0] == counts[dist.get_rank()]
     mx = max(counts)
-    F = local.shape[1:]
-    padded = local.new_zeros((mx,) + tuple(F))
-    padded[: local.shape[0]] = local
-    out = local.new_empty((world * mx,) + tuple(F))
-    dist.all_gather_into_tensor(out, padded.contiguous())
-    out = out.view(world, mx, *F)
-    return torch.cat([out[r, : counts[r]] for r in range(world)], dim=0)
+    F = tuple(local.shape[1:])
+    if local.shape[0] == mx:
+        padded = local.contiguous()
+    else:
+        padded = local.new_zeros((mx,) + F)
+        padded[: local.shape[0]] = local
+    out = local.new_empty((world * mx,) + F)
+    work = dist.all_gather_into_tensor(out, padded, async_op=True)
+    return PendingGather(work, out, list(counts), F, world, mx)
+
+
+def gather_records(local: torch.Tensor, counts: Sequence[int]) -> torch.Tensor:
+    """All-gather per-image records (blocking form of gather_records_async).  Returns [sum(counts), F] in global
+    image order on every rank."""
+    return gather_records_async(local, counts).result()
 
 
 _DENOM_CACHE = {}

@@ -28,6 +28,10 @@ def _worker(rank, world, port, n_images, q):
         mine = P.shard_images(n_images, rank, world)
         local = torch.tensor([[float(i), 10.0 * i, -1.0 * i] for i in mine]).view(len(mine), 3)
         full = P.gather_records(local, counts)
+        # the pipelined form used by bench.py: start two exchanges, consume them later, in order
+        h1 = P.gather_records_async(local, counts)
+        h2 = P.gather_records_async(local * 2, counts)
+        assert torch.equal(h1.result(), full) and torch.equal(h2.result(), full * 2)
         q.put((rank, full.tolist()))
     finally:
         dist.destroy_process_group()
