@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 3
+#define SNN_ABI_VERSION 4
 
 #define SNN_MODE_FP32_EXACT 0 /* 3 bf16 pieces per weight (24 mantissa bits): the parity mode          */
 #define SNN_MODE_BF16 1       /* 1 piece: weights rounded to bf16, the throughput mode                 */
@@ -104,6 +104,15 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
  * encoder only: x [R][K] fp32 -> z_words [R][K], words of 1/2/4 bytes for T_live <= 8/16/32, bit t = z_t
  * (Norse lif_current_encoder, faster_rcnn.py:494). */
 int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_words, snn_stream_t stream);
+/* The encoders evaluate lif_current_encoder as a comparator bank: the input current is constant and a spike resets
+ * the membrane to its initial value, so a neuron's train is periodic with period n(x) = its first-spike step, and
+ * n(x) = min{ n : x >= thresholds[n] }.  HOST call: copies the 33-entry tables (index n = 1..32; thresholds[n] =
+ * the smallest fp32 input whose first spike comes at step <= n; deltas[n] = train(n) ^ train(n+1) over 32 steps). */
+void snn_encoder_table(float* thresholds33, unsigned int* deltas33);
+/* Exhaustive device self-test: counts, over ALL 2^32 fp32 bit patterns, the inputs whose comparator-bank word differs
+ * from the step-by-step simulation of lif_current_encoder for T_live steps; *mismatches (device, zeroed by the caller)
+ * must stay 0. */
+int snn_encoder_selftest(int T_live, unsigned long long* mismatches, snn_stream_t stream);
 /* one fully-connected spiking layer: z_words [R][K] input spike-train words of `in_word_bytes` bytes whose
  * bit (in_bit0 + i) is the input spike injected at step t0 + i (i < T_live); w_prep [pieces][M][K] + scales;
  * runs the LIF recurrence for steps 0..T-1 and writes trains [R][M] (words of snn_train_word_bytes(T));

@@ -83,25 +83,90 @@ __device__ __forceinline__ uint32_t encode_train(float x, int T) {
     return w;
 }
 
-// The same for N independent inputs in lock-step: one time loop, the step's bit mask computed once, N
-// dependency chains interleaved (the encoders are instruction-issue bound, not HBM bound).
-template <int N>
-__device__ __forceinline__ void encode_trains(const float (&x)[N], int T, uint32_t (&w)[N]) {
-    float v[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) { v[k] = 0.f; w[k] = 0u; }
-#pragma unroll 2
-    for (int t = 0; t < T; ++t) {
-        const uint32_t bit = 1u << t;
-#pragma unroll
-        for (int k = 0; k < N; ++k) {
-            v[k] = __fadd_rn(v[k], __fmul_rn(0.1f, __fsub_rn(x[k], v[k])));
-            const bool z = v[k] > 0.25f;
-            w[k] = z ? (w[k] | bit) : w[k];
-            v[k] = z ? 0.f : v[k];
+// ---- the encoder as a comparator bank
+// The input current x is constant over the steps and a spike resets v to exactly 0.f = the initial state, so the
+// trajectory repeats: a neuron whose first spike falls on step n (1-based) fires at steps n, 2n, 3n, ... -- its whole
+// train is a function of n(x) alone.  n(x) is non-increasing in x (every op of the update is monotone in x while no
+// spike has occurred; checked for EVERY fp32 input by snn_encoder_selftest), so
+//     n(x) = min { n : x >= thr[n] },   thr[n] = the smallest fp32 x whose first spike comes at step <= n
+// and the train word is a telescoping XOR over the thresholds passed:
+//     word = XOR_{n : x >= thr[n]} (full[n] ^ full[n+1]),   full[n] = bits n-1, 2n-1, 3n-1, ... of a 32-step train
+// (x >= thr[n] implies x >= thr[m] for m > n, so the XOR collapses to full[n(x)]); the caller masks the live steps.
+// 2 instructions per step and neuron (FSETP + predicated LOP3) instead of the 6 of the simulation.  The thresholds
+// are found at COMPILE time by bisection on the simulation itself (constexpr fp32 arithmetic: one IEEE add/sub/mul
+// per op, the same roundings as __fadd_rn/__fmul_rn); NaN compares false everywhere = never spikes, as simulated.
+struct EncTable { float thr[33]; uint32_t delta[33]; };     // index n = 1..32; [0] unused
+
+__host__ __device__ constexpr int enc_first_spike(float x, int nmax) {
+    float v = 0.f;
+    for (int n = 1; n <= nmax; ++n) {
+        const float d = x - v;
+        const float dv = 0.1f * d;
+        v = v + dv;
+        if (v > 0.25f) return n;
+    }
+    return nmax + 1;
+}
+__host__ __device__ constexpr uint32_t enc_full_train(int n) {
+    uint32_t w = 0u;
+    for (int t = n - 1; t < 32; t += n) w |= 1u << t;
+    return n <= 32 ? w : 0u;
+}
+__host__ __device__ constexpr EncTable make_enc_table() {
+    EncTable tb{};
+    for (int n = 1; n <= 32; ++n) {
+        float lo = 0.25f, hi = 4.0f;            // first spike of lo comes after step n (never), of hi at step 1
+        for (int it = 0; it < 64; ++it) {
+            const float mid = 0.5f * (lo + hi);
+            if (!(mid > lo && mid < hi)) break; // lo and hi are adjacent floats
+            if (enc_first_spike(mid, n) <= n) hi = mid; else lo = mid;
         }
+        tb.thr[n] = hi;
+        tb.delta[n] = enc_full_train(n) ^ enc_full_train(n + 1);
+    }
+    tb.thr[0] = 0.f; tb.delta[0] = 0u;
+    return tb;
+}
+constexpr EncTable kEncTableHost = make_enc_table();
+__constant__ EncTable c_enc = make_enc_table();
+
+// NT >= the number of live steps (a compile-time bucket); bits at steps >= T_live are masked by the caller.
+// if (x >= th) w ^= delta: one FSETP + one predicated LOP3
+__device__ __forceinline__ void xor_if_ge(uint32_t& w, float x, float th, uint32_t delta) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p xor.b32 %0, %0, %3;\n\t}" : "+r"(w) : "f"(x), "f"(th), "r"(delta));
+}
+template <int NT>
+__device__ __forceinline__ uint32_t encode_word(float x) {
+    uint32_t w = 0u;
+#pragma unroll
+    for (int n = 1; n <= NT; ++n) xor_if_ge(w, x, c_enc.thr[n], c_enc.delta[n]);
+    return w;
+}
+
+// N inputs at once (independent chains for the scheduler); tmask = the live steps
+template <int NT, int N>
+__device__ __forceinline__ void encode_words(const float (&x)[N], uint32_t tmask, uint32_t (&w)[N]) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) w[k] = 0u;
+#pragma unroll
+    for (int n = 1; n <= NT; ++n) {
+        const float th = c_enc.thr[n];
+        const uint32_t dl = c_enc.delta[n] & tmask;
+#pragma unroll
+        for (int k = 0; k < N; ++k) xor_if_ge(w[k], x[k], th, dl);
     }
 }
+
+// dispatch a kernel template on the bucket of live steps
+#define SNN_ENC_BUCKETS(T_live, ...)                                  \
+    do {                                                                \
+        if ((T_live) <= 4) { constexpr int NT = 4; __VA_ARGS__; }             \
+        else if ((T_live) <= 8) { constexpr int NT = 8; __VA_ARGS__; }         \
+        else if ((T_live) <= 12) { constexpr int NT = 12; __VA_ARGS__; }       \
+        else if ((T_live) <= 16) { constexpr int NT = 16; __VA_ARGS__; }       \
+        else if ((T_live) <= 24) { constexpr int NT = 24; __VA_ARGS__; }       \
+        else { constexpr int NT = 32; __VA_ARGS__; }                           \
+    } while (0)
 
 constexpr int kEncW = 32;        // pixels per block along W
 constexpr int kEncMaxLevels = 8;
@@ -123,6 +188,7 @@ struct EncParams {
 //   phase 2: NHWC words out, 16 bytes per thread: a pixel's C words are contiguous, so the block writes one
 //            contiguous run of 32 * C words.
 // HBM traffic: 4 B read + wb B written per input neuron (the per-timestep planes never exist).
+template <int NT>
 __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant__ EncParams p) {
     extern __shared__ uint32_t s_tr[];            // [kEncW][C * wb / 4 + 1] 32-bit words of packed spike-train words
     int lvl = 0;
@@ -142,12 +208,13 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
     const int gw = 2 * p.wb;                      // 32-bit words per group of 8 channels
     const float* xrow = L.x + (static_cast<size_t>(n) * C * H + h) * W + w;
     const size_t cstride = static_cast<size_t>(H) * W;
+    const uint32_t tmask = (p.T_live >= 32) ? 0xFFFFFFFFu : ((1u << p.T_live) - 1u);
     for (int g = warp; g < C / 8; g += 8) {       // channels 8g .. 8g+7
         float xv[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) xv[k] = (w < W) ? __ldg(xrow + (8 * g + k) * cstride) : 0.f;
         uint32_t tw[8];
-        encode_trains<8>(xv, p.T_live, tw);
+        encode_words<NT, 8>(xv, tmask, tw);
         uint32_t* dst = &s_tr[lane * ld + g * gw];
         if (p.wb == 1) {
             dst[0] = tw[0] | (tw[1] << 8) | (tw[2] << 16) | (tw[3] << 24);
@@ -172,8 +239,10 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
 }
 
 // x [R][K] fp32 -> words [R][K] of `wb` bytes; 8 consecutive k per thread (2 x float4 in, 8 words out)
+template <int NT>
 __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total8, int T_live,
                                                           int wb, uint8_t* __restrict__ z) {
+    const uint32_t tmask = (T_live >= 32) ? 0xFFFFFFFFu : ((1u << T_live) - 1u);
 #pragma unroll 2
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -181,7 +250,7 @@ __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restric
         const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
         const float xs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         uint32_t tr[8];
-        encode_trains<8>(xs, T_live, tr);
+        encode_words<NT, 8>(xs, tmask, tr);
         if (wb == 1) {
             uint2 o;
             o.x = tr[0] | (tr[1] << 8) | (tr[2] << 16) | (tr[3] << 24);
@@ -447,7 +516,9 @@ __device__ __forceinline__ float roi_bilinear(const float* __restrict__ f, int H
     return w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
 }
 
+template <int NT>
 __global__ void __launch_bounds__(256) roi_align_encode_kernel(const __grid_constant__ RoiEncParams p) {
+    const uint32_t tmask = (p.T_live >= 32) ? 0xFFFFFFFFu : ((1u << p.T_live) - 1u);
     const int PP = p.P * p.P;
     const int K = p.C * PP;
     const size_t total8 = static_cast<size_t>(p.R) * K / 8;
@@ -486,7 +557,7 @@ __global__ void __launch_bounds__(256) roi_align_encode_kernel(const __grid_cons
             for (int e = 0; e < 8; ++e) p.pooled[static_cast<size_t>(r) * K + k0 + e] = xv[e];
         }
         uint32_t tr[8];
-        encode_trains<8>(xv, p.T_live, tr);
+        encode_words<NT, 8>(xv, tmask, tr);
         uint8_t* z = p.words;
         if (p.wb == 1) {
             uint2 o;
@@ -501,6 +572,20 @@ __global__ void __launch_bounds__(256) roi_align_encode_kernel(const __grid_cons
             reinterpret_cast<uint4*>(z)[2 * i + 1] = make_uint4(tr[4], tr[5], tr[6], tr[7]);
         }
     }
+}
+
+// Exhaustive check of the comparator bank against the simulation: every one of the 2^32 fp32 bit patterns.
+template <int NT>
+__global__ void __launch_bounds__(256) encoder_selftest_kernel(int T_live, unsigned long long* __restrict__ mismatches) {
+    const uint32_t tmask = (T_live >= 32) ? 0xFFFFFFFFu : ((1u << T_live) - 1u);
+    unsigned int bad = 0;
+    for (unsigned long long b = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; b < (1ull << 32);
+         b += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+        const float x = __uint_as_float(static_cast<uint32_t>(b));
+        bad += (encode_word<NT>(x) & tmask) != encode_train(x, T_live);
+    }
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, static_cast<unsigned long long>(bad));
 }
 
 }  // namespace snn

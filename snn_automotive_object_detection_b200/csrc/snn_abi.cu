@@ -486,9 +486,11 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
             }
             ep.n_levels = n_levels; ep.N = N; ep.C = C_in; ep.T_live = T_live; ep.wb = word_bytes(T_live); ep.total_blocks = blocks;
             const size_t smem = static_cast<size_t>(kEncW) * (C_in * ep.wb / 4 + 1) * 4;
-            if (smem > 48 * 1024)
-                CUDA_TRY(cudaFuncSetAttribute(encode_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            encode_nchw_kernel<<<blocks, 256, smem, st>>>(ep);
+            SNN_ENC_BUCKETS(T_live, {
+                if (smem > 48 * 1024)
+                    CUDA_TRY(cudaFuncSetAttribute(encode_nchw_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                encode_nchw_kernel<NT><<<blocks, 256, smem, st>>>(ep);
+            });
             CUDA_TRY(cudaGetLastError()); ++g_launches;
         }
         phase_end(PH_ENC_RPN, st);
@@ -628,8 +630,8 @@ static int box_head_forward_impl(const void* x, bool x_is_words, int R, int K, i
         const size_t total8 = static_cast<size_t>(R) * K / 8;
         const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
         phase_begin(PH_ENC_BOX, st);
-        encode_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), total8, T_live6, word_bytes(T - 1),
-                                                   wsp + ws.z_off);
+        SNN_ENC_BUCKETS(T_live6, (encode_rows_kernel<NT><<<blocks, 256, 0, st>>>(
+                                      reinterpret_cast<const float*>(x), total8, T_live6, word_bytes(T - 1), wsp + ws.z_off)));
         phase_end(PH_ENC_BOX, st);
         CUDA_TRY(cudaGetLastError()); ++g_launches;
     }
@@ -692,7 +694,7 @@ int snn_roi_align_encode(const void* const* feat_ptrs, const int* H, const int* 
     p.rois = rois; p.roi_level = roi_level; p.words = reinterpret_cast<uint8_t*>(words_out); p.pooled = pooled_out;
     const size_t total8 = static_cast<size_t>(R) * C * pooled_size * pooled_size / 8;
     const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 32 ? 148 * 32 : (total8 + 255) / 256);
-    roi_align_encode_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    SNN_ENC_BUCKETS(T_live, (roi_align_encode_kernel<NT><<<blocks, 256, 0, (cudaStream_t)stream>>>(p)));
     CUDA_TRY(cudaGetLastError());
     return SNN_OK;
 }
@@ -759,8 +761,22 @@ int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_words, snn
         return fail(SNN_E_ARG, "encode_rows: bad argument");
     const size_t total8 = static_cast<size_t>(R) * K / 8;
     const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
-    encode_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, total8, T_live, word_bytes(T_live),
-                                                                 reinterpret_cast<uint8_t*>(z_words));
+    SNN_ENC_BUCKETS(T_live, (encode_rows_kernel<NT><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                                 x, total8, T_live, word_bytes(T_live), reinterpret_cast<uint8_t*>(z_words))));
+    CUDA_TRY(cudaGetLastError());
+    return SNN_OK;
+}
+
+void snn_encoder_table(float* thresholds33, unsigned int* deltas33) {
+    for (int n = 0; n <= 32; ++n) {
+        if (thresholds33) thresholds33[n] = kEncTableHost.thr[n];
+        if (deltas33) deltas33[n] = kEncTableHost.delta[n];
+    }
+}
+
+int snn_encoder_selftest(int T_live, unsigned long long* mismatches, snn_stream_t stream) {
+    if (!mismatches || T_live < 1 || T_live > 32) return fail(SNN_E_ARG, "encoder_selftest: bad argument");
+    SNN_ENC_BUCKETS(T_live, (encoder_selftest_kernel<NT><<<148 * 16, 256, 0, (cudaStream_t)stream>>>(T_live, mismatches)));
     CUDA_TRY(cudaGetLastError());
     return SNN_OK;
 }

@@ -56,3 +56,49 @@ def test_bad_arguments_are_reported_without_touching_a_device(lib):
     assert rc == -1 and b"null" in lib.snn_last_error()
     with pytest.raises(ValueError):
         _lib.mode_id("int8")
+
+
+def test_encoder_comparator_table_against_the_oracle_encoder(lib):
+    """The encoders evaluate lif_current_encoder as a comparator bank (include/snn_heads.h: snn_encoder_table).
+    Its thresholds are pinned here against the oracle's step-by-step encoder: thresholds[n] is the SMALLEST fp32
+    input whose first spike comes at step <= n, the first-spike step is monotone in the input over every fp32
+    value between the smallest and the largest threshold, and the word the table yields equals the simulated
+    train for all those inputs."""
+    import numpy as np
+    import torch
+    from oracle import snn_oracle as O
+    thr = (ctypes.c_float * 33)()
+    dl = (ctypes.c_uint * 33)()
+    lib.snn_encoder_table(thr, dl)
+    thr = np.array(thr[:], dtype=np.float32)
+    dl = np.array(dl[:], dtype=np.uint32)
+    T = 32
+
+    def first_spike(x):
+        z = torch.stack(O.encoder_spikes(torch.from_numpy(x), T)).numpy() > 0       # [T, n]
+        return np.where(z.any(0), z.argmax(0) + 1, T + 1), z
+
+    for n in range(1, 33):
+        x = np.array([np.nextafter(thr[n], np.float32(0)), thr[n]], dtype=np.float32)
+        f, _ = first_spike(x)
+        assert f[0] > n and f[1] <= n, f"threshold {n}: {thr[n]!r} is not the smallest input spiking by step {n}"
+        full = sum(1 << t for t in range(n - 1, 32, n))
+        nxt = sum(1 << t for t in range(n, 32, n + 1)) if n < 32 else 0
+        assert int(dl[n]) == full ^ nxt
+    assert np.all(np.diff(thr[1:]) < 0)
+    # every fp32 value in [just below thr[32], just above thr[1]]: monotone first-spike step, table word == simulation
+    lo = int(np.float32(thr[32]).view(np.uint32)) - 4096
+    hi = int(np.float32(thr[1]).view(np.uint32)) + 4096
+    prev_last = T + 1
+    for s0 in range(lo, hi + 1, 1 << 22):
+        x = np.arange(s0, min(s0 + (1 << 22), hi + 1), dtype=np.uint32).view(np.float32)
+        f, z = first_spike(x)
+        assert f[0] <= prev_last and np.all(np.diff(f) <= 0)
+        prev_last = f[-1]
+        sim = np.zeros(x.shape, dtype=np.uint32)
+        for t in range(T):
+            sim |= z[t].astype(np.uint32) << np.uint32(t)
+        tab = np.zeros(x.shape, dtype=np.uint32)
+        for n in range(1, 33):
+            tab ^= np.where(x >= thr[n], dl[n], np.uint32(0))
+        assert np.array_equal(sim, tab)

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 def test_library_reports_version_and_rejects_bad_args():
     lib = _lib.load()
-    assert lib.snn_version() == 3
+    assert lib.snn_version() == 4
     rc = lib.snn_fc_lif_layer(None, 1, 0, 1, 64, 128, 8, 0, 7, 0, None, None, None, 0, None)
     assert rc == -1 and b"null" in lib.snn_last_error()
 
@@ -44,6 +44,17 @@ def test_encoder_rows_bit_exact(T):
     ref = torch.stack(O.encoder_spikes(x, T))
     assert torch.equal(unpack_trains(z.cpu(), T).float(), ref)
     assert T < 8 or ref.sum() > 0
+
+
+@pytest.mark.parametrize("T", [1, 3, 4, 7, 8, 10, 11, 12, 15, 16, 23, 24, 31, 32])
+def test_encoder_comparator_bank_equals_simulation_for_every_fp32_input(T):
+    """The comparator-bank encoder against the step-by-step lif_current_encoder simulation on the device, over ALL
+    2^32 fp32 bit patterns (NaNs, infinities, subnormals, negatives included)."""
+    lib = _lib.load()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _lib.check(lib.snn_encoder_selftest(T, vp(bad), stream()), "encoder_selftest")
+    torch.cuda.synchronize()
+    assert bad.item() == 0
 
 
 def _fc_case(R, K, M, T, t0, T_live, mode, cg, seed=0, density=0.15, in_bit0=0, in_wb=None):
