@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cta-group", type=int, default=0)
+    ap.add_argument("--fc-dual", type=int, default=0, help="fc tiling experiments: 0 auto, 1 single tiles, 2 dual wherever possible")
+    ap.add_argument("--fc-units", type=int, default=0, help="fc tiling experiments: cap on the units per accumulator tile")
+    ap.add_argument("--fc-no-split", type=int, default=0, help="fc tiling experiments: 1 = never run the tail wave as single tiles")
     return ap.parse_args()
 
 
@@ -204,6 +207,7 @@ def run_ours(args):
         B = args.global_batch // world
     lib = _lib.load()
     lib.snn_set_cta_group(args.cta_group)
+    lib.snn_set_fc_tiling(args.fc_dual, args.fc_units, args.fc_no_split)
 
     # weights: the reference constructors' init (random init; there are no checkpoints offline)
     torch.manual_seed(0)

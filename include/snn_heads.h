@@ -157,6 +157,12 @@ int snn_rpn_decode_selected(const void* const* logits, const void* const* deltas
 int snn_last_launch_count(void);
 /* force cta_group (1 or 2; 0 = auto) for subsequent forward calls on this thread -- tests/profiling only */
 void snn_set_cta_group(int cta_group);
+/* fc tiling of subsequent calls on this thread -- tests/profiling only.  dual: 0 = auto (dual tiles -- 2J units whose
+ * two accumulators share every weight tile -- for K >= 4096), 1 = never, 2 = whenever the tile shape allows it;
+ * max_units > 0 caps the units per accumulator tile (0 = the widest tile without a padding step, else the widest);
+ * tail_split: 0 = auto (a last wave of dual tiles that is less than half full runs as single tiles in a second
+ * launch), 1 = never. */
+void snn_set_fc_tiling(int dual, int max_units, int tail_split);
 
 /* Per-phase device timing for bench.py: when enabled, every forward records CUDA events on its stream
  * around each phase (up to 256 forwards).  snn_profile_read() waits for them, writes the summed

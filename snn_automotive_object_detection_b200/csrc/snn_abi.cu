@@ -21,6 +21,9 @@ namespace {
 thread_local std::string g_err;
 thread_local int g_launches = 0;
 thread_local int g_force_cg = 0;
+thread_local int g_fc_dual = 0;      // 0 auto, 1 never, 2 whenever the tile shape allows it (tests)
+thread_local int g_fc_units = 0;     // > 0: cap on the units per fc tile (experiments)
+thread_local int g_fc_split = 0;     // 1: never run the last partial wave of dual tiles as single tiles (experiments)
 
 // Optional per-phase device timing (CUDA events recorded on the launch stream around each phase).
 enum Phase { PH_ENC_RPN = 0, PH_GEMM_RPN, PH_RO_RPN, PH_ENC_BOX, PH_GEMM_FC6, PH_GEMM_FC7, PH_RO_BOX, PH_COUNT };
@@ -138,7 +141,8 @@ struct TileCfg { int cg, T_box, J, Jh, TW, TH, TWh, THh, dw, dh, CW, n_mma; };
 // Fold time into the MMA N dimension: N = T_box * J <= 256, N % 16 == 0, J units per tile.
 bool pick_tile_cg(int T_live, bool conv, int cg, TileCfg& out) {
     const int step = conv ? 8 * cg : 2 * cg;      // fc: units per CTA a multiple of 2 (epilogue chunks of 2, 4 or 8)
-    const int maxJ = kMaxUnitsPerCta * cg;                        // producers: Jh * 8 pairs <= kMaxPairs x 64 threads
+    int maxJ = kMaxUnitsPerCta * cg;                              // producers: Jh * 8 pairs <= kMaxPairs x 64 threads
+    if (!conv && g_fc_units >= step && g_fc_units < maxJ) maxJ = g_fc_units;
     int bestJ = 0, bestT = 0;
     for (int J = step; J <= maxJ; J += step)
         for (int Tb = T_live; Tb <= T_live + 1; ++Tb) {
@@ -147,6 +151,15 @@ bool pick_tile_cg(int T_live, bool conv, int cg, TileCfg& out) {
             if (J > bestJ) { bestJ = J; bestT = Tb; }
         }
     if (bestJ == 0) return false;
+    // fc: a padding step (T_box = T_live + 1) is tensor work on zero rows.  Prefer the widest tile WITHOUT padding
+    // when it keeps N >= 160 (narrower MMAs are bound by the shared-memory reads of the weight operand); such a
+    // tile runs as a dual tile (two accumulators per weight tile), which restores the weight reuse.
+    if (!conv && cg == 2 && bestT != T_live) {
+        for (int J = bestJ - step; J >= step; J -= step) {
+            const int n = T_live * J;
+            if (n <= 256 && (n % 16) == 0 && n >= 160) { bestJ = J; bestT = T_live; break; }
+        }
+    }
     out.cg = cg; out.T_box = bestT; out.J = bestJ; out.Jh = bestJ / cg; out.n_mma = bestT * bestJ;
     if (conv) {
         out.TW = 8; out.TH = bestJ / 8; out.TWh = 8; out.THh = out.TH / cg; out.dw = 0; out.dh = (cg == 2) ? out.THh : 0;
@@ -182,6 +195,20 @@ cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_
     }
     if (p.conv) {
         if (CW == 8) SNN_LAUNCH(8, true) else SNN_LAUNCH(4, true)
+    } else if (p.dual) {
+        if constexpr (kCG == 2) {
+#define SNN_LAUNCH_DUAL(CWV)                                                                                   \
+    {                                                                                                          \
+        auto kern = spike_gemm_lif_kernel<2, CWV, false, true>;                                                \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes); \
+        if (e != cudaSuccess) return e;                                                                        \
+        return cudaLaunchKernelEx(&cfg, kern, p);                                                              \
+    }
+            if (CW == 8) SNN_LAUNCH_DUAL(8) else if (CW == 4) SNN_LAUNCH_DUAL(4) else SNN_LAUNCH_DUAL(2)
+#undef SNN_LAUNCH_DUAL
+        } else {
+            return cudaErrorInvalidValue;
+        }
     } else {
         if (CW == 8) SNN_LAUNCH(8, false) else if (CW == 4) SNN_LAUNCH(4, false) else SNN_LAUNCH(2, false)
     }
@@ -197,7 +224,7 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
         p.hrows = tc.THh + 2;
         p.slot_b = static_cast<int>(align_up(static_cast<size_t>(p.hrows) * tc.T_box * 10 * 128, 1024));
     } else {
-        p.slot_b = static_cast<int>(align_up(static_cast<size_t>(tc.n_mma / tc.cg) * 128, 1024));
+        p.slot_b = static_cast<int>(align_up(static_cast<size_t>(tc.n_mma / tc.cg) * 128, 1024)) * (p.dual ? 2 : 1);
     }
     // The weight ring (16 KB stages) and the spike-tile ring share 176 KB.  Default: 6 weight stages + 80 KB of
     // spike tiles.  A conv spike tile (one 64-channel block of the halo'd region, read by 9 taps) can be large:
@@ -237,7 +264,7 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
             if (p.stages_b > kMaxStagesB) p.stages_b = kMaxStagesB;
         }
     }
-    p.slot_w = static_cast<int>(align_up(static_cast<size_t>(p.conv ? p.hrows * 10 : tc.Jh) * 64 * p.in_wb, 128));
+    p.slot_w = static_cast<int>(align_up(static_cast<size_t>(p.conv ? p.hrows * 10 : tc.Jh * (p.dual ? 2 : 1)) * 64 * p.in_wb, 128));
     p.stages_w = kRingBytesW / p.slot_w;
     if (p.stages_w > kMaxStagesW) p.stages_w = kMaxStagesW;
     // producer group g starts on stage g of both rings, so there are at most min(stages) groups (1, 2 or 4)
@@ -329,8 +356,10 @@ int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, 
     return SNN_OK;
 }
 
-int fc_layer(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, int R, int K, int M, int T, int t0,
-             int T_live, int mode, const void* w_prep, void* trains, float* dump, const TileCfg& tc, cudaStream_t st) {
+// one launch over the units [0, R) of z_words / trains; dump (debug) is [T_live][dump_rows][M] and already offset
+int fc_launch(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, int R, int K, int M, int T, int t0,
+              int T_live, int mode, const void* w_prep, void* trains, float* dump, int dump_rows, const TileCfg& tc,
+              bool dual, cudaStream_t st) {
     GemmLifParams p;
     memset(&p, 0, sizeof(p));
     const int nsplit = nsplit_of(mode);
@@ -345,19 +374,53 @@ int fc_layer(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, 
     p.n_levels = 1; p.conv = 0; p.n_images = 1;
     p.m_total = M; p.nsplit = nsplit; p.kblocks = K / 64; p.cblocks = 1; p.k_in = K;
     p.T_total = T; p.t0 = t0; p.T_live = T_live;
-    p.rows = R; p.unit_tiles = (R + tc.J - 1) / tc.J;
+    p.dual = dual ? 1 : 0;
+    const int tile_units = tc.J * (p.dual ? 2 : 1);
+    p.rows = R; p.unit_tiles = (R + tile_units - 1) / tile_units;
     p.train_bytes = snn_train_word_bytes(T);
     p.in_wb = in_wb; p.in_bit0 = in_bit0;
     {   // input words [R][K] as a byte tensor
         cuuint64_t dims[2] = {(cuuint64_t)K * in_wb, (cuuint64_t)R};
         cuuint64_t str[1] = {(cuuint64_t)K * in_wb};
-        cuuint32_t box[2] = {(cuuint32_t)(64 * in_wb), (cuuint32_t)tc.Jh};
+        cuuint32_t box[2] = {(cuuint32_t)(64 * in_wb), (cuuint32_t)(tc.Jh * (p.dual ? 2 : 1))};
         int rc = make_tmap(&p.tmW[0], z_words, 2, dims, str, box, true);
         if (rc) return rc;
     }
     p.trains = trains;
-    p.dump = dump;
+    p.dump = dump; p.dump_rows = dump_rows;
     return launch_gemm(p, tc, di, mode, st);
+}
+
+// One fully-connected spiking layer.  Dual tiles (2J units, both accumulator buffers fed from every weight tile) pay
+// off for long contractions: the weight stream from L2 and the cross-CTA hand-offs per FLOP halve; the fc epilogue of
+// a tile is then exposed, so short K stays single.  The persistent grid runs whole waves of tiles; when the last
+// wave of dual tiles would be less than half full, its units are run as single tiles by a second launch (half the
+// time of a dual wave).
+int fc_layer(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, int R, int K, int M, int T, int t0,
+             int T_live, int mode, const void* w_prep, void* trains, float* dump, const TileCfg& tc, cudaStream_t st) {
+    const bool dual_ok = tc.cg == 2 && tc.T_box <= 16 && (tc.n_mma / 2) % 8 == 0;
+    bool dual = dual_ok && g_fc_dual != 1 && (g_fc_dual == 2 || K / 64 >= 64);
+    int R1 = R;                                   // units [0, R1) in the first launch
+    if (dual && g_fc_dual == 0) {
+        const int groups = di.sms / 2, m_tiles = M / 256, U2 = 2 * tc.J;
+        const int ut_total = (R + U2 - 1) / U2;
+        const int full = ut_total * m_tiles / groups;                 // complete waves of dual tiles
+        if (full == 0) {
+            if ((R + tc.J - 1) / tc.J * m_tiles <= groups) dual = false;   // one wave either way: single tiles are half as long
+        } else if (ut_total * m_tiles > full * groups) {
+            const int UT1 = full * groups / m_tiles;
+            const int singles = ((R - UT1 * U2) + tc.J - 1) / tc.J * m_tiles;
+            if (singles <= groups && g_fc_split != 1) R1 = UT1 * U2;
+        }
+    }
+    const size_t tb = snn_train_word_bytes(T);
+    int rc = fc_launch(di, z_words, in_wb, in_bit0, R1, K, M, T, t0, T_live, mode, w_prep, trains, dump, R, tc, dual, st);
+    if (rc || R1 == R) return rc;
+    rc = fc_launch(di, reinterpret_cast<const uint8_t*>(z_words) + static_cast<size_t>(R1) * K * in_wb, in_wb, in_bit0,
+                   R - R1, K, M, T, t0, T_live, mode, w_prep,
+                   reinterpret_cast<uint8_t*>(trains) + static_cast<size_t>(R1) * M * tb,
+                   dump ? dump + static_cast<size_t>(R1) * M : nullptr, R, tc, false, st);
+    return rc;
 }
 
 template <typename T>
@@ -396,6 +459,11 @@ int snn_version(void) { return SNN_ABI_VERSION; }
 const char* snn_last_error(void) { return g_err.c_str(); }
 int snn_last_launch_count(void) { return g_launches; }
 void snn_set_cta_group(int cg) { g_force_cg = (cg == 1 || cg == 2) ? cg : 0; }
+void snn_set_fc_tiling(int dual, int max_units, int tail_split) {
+    g_fc_dual = (dual == 1 || dual == 2) ? dual : 0;
+    g_fc_units = max_units > 0 ? max_units : 0;
+    g_fc_split = tail_split == 1 ? 1 : 0;
+}
 int snn_train_word_bytes(int T) { return T <= 8 ? 1 : T <= 16 ? 2 : 4; }
 int snn_mode_pieces(int mode) { return nsplit_of(mode); }
 

@@ -47,7 +47,7 @@ constexpr int kStagesA = 6;                 // weight ring: up to 6 stages of 16
 constexpr int kMaxStagesB = 8;              // ring of p.stages_b slots of p.slot_b bytes; weight + spike rings share 176 KB
 constexpr int kMaxStagesW = 8;              // ring of p.stages_w slots of p.slot_w bytes, 16 KB in total
 constexpr int kTileBytesA = 128 * 128;      // 128 rows x 64 16-bit
-constexpr int kRingBytesB = 80 * 1024;
+constexpr int kRingBytesB = 97 * 1024;          // weight + spike rings share 193 KB; the whole CTA uses all 227 KB
 constexpr int kRingBytesW = 16 * 1024;
 constexpr int kBarBytes = 512;
 constexpr int kEpiGroups = 1;               // LIF epilogue warp groups (4 warps each): warps 4-7 (+ 16-19)
@@ -91,11 +91,13 @@ struct GemmLifParams {
     int hrows;                // conv: halo rows per CTA = TH / kCG + 2 (halo columns = TWh + 2 = 10)
     int n_pg;                 // producer groups (each owns every n_pg-th k-block): min(4, stages_b, stages_w) rounded to 1/2/4
     int n_mma;                // T_box * J
+    int dual;                 // fc only: one tile = 2J units, BOTH accumulator buffers fed from every weight tile
     uint32_t idesc;
     void* trains;             // fc: [rows][m_total]
     uint32_t spike_one;       // 1.0 as bf16 (0x3F80) or fp16 (0x3C00)
     const float* w_scale;     // [m_total] power of two each accumulator row is multiplied with (1 for bf16 pieces)
-    float* dump;              // debug (fc only): raw currents [T_live][rows][m_total]
+    float* dump;              // debug (fc only): raw currents [T_live][dump_rows][m_total]
+    int dump_rows;
     int dbg_shift, dbg_sbo, dbg_boff;   // swizzle experiment (scratch/swizzle_experiment.py, fc only): row shift, group stride, base-offset field
     // fused leaky-integrator readout (conv, cta_group 2, m_total == 256): mem_{T-1} = W . sum_t kappa_{T-1-t} spk_t
     int fuse_readout, A;
@@ -135,7 +137,11 @@ __device__ __forceinline__ TilePos decode_tile(const GemmLifParams& p, int ut) {
     return tp;
 }
 
-template <int kCG, int CW, bool kConv>
+// kDual (fc only): a tile covers 2J units; the CTA of rank r holds the units [2J*ut + 2Jh*r, +2Jh), the first Jh of
+// them accumulate in TMEM buffer 0, the next Jh in buffer 1, and every weight tile feeds both MMAs -- half the
+// L2 -> SM weight stream and half the producer -> relay -> MMA hand-offs per FLOP; the (short) fc epilogue of a tile
+// then no longer overlaps the next tile's main loop.
+template <int kCG, int CW, bool kConv, bool kDual = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const __grid_constant__ GemmLifParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -216,8 +222,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         if (rank == 0 && elect_one()) {
             uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
             for (int tile = group; tile < p.total_tiles; tile += n_groups, ++it) {
-                const uint32_t buf = it & 1u;
-                mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                const uint32_t buf = kDual ? 0u : (it & 1u);
+                if constexpr (kDual) {
+                    mbar_wait(&acc_empty[0], (it & 1u) ^ 1u);
+                    mbar_wait(&acc_empty[1], (it & 1u) ^ 1u);
+                } else {
+                    mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                }
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 256u;
                 for (int ko = 0; ko < n_outer; ++ko) {
@@ -245,6 +256,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                             for (int k = 0; k < 4; ++k)     // 4 x (K = 16 x 16-bit = 32 B) inside the 128-B swizzle span
                                 umma_f16<kCG>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, p.idesc,
                                               (ko | ki | s | k) != 0 ? 1u : 0u);
+                            if constexpr (kDual) {          // the second half of the slot -> accumulator buffer 1
+                                const uint64_t b_desc1 = umma_desc_sw128(b_slot + static_cast<uint32_t>(n_half) * 128u);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_f16<kCG>(d_tmem + 256u, a_desc + 2u * k, b_desc1 + 2u * k, p.idesc,
+                                                  (ko | s | k) != 0 ? 1u : 0u);
+                            }
                             if constexpr (kCG == 1) umma_commit<1>(&a_empty[sa]);
                             else umma_commit_2sm_mcast(&a_empty[sa], 0b11);
                             if (++sa == static_cast<uint32_t>(stages_a)) { sa = 0; pa ^= 1u; }
@@ -256,6 +274,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 }
                 if constexpr (kCG == 1) umma_commit<1>(&acc_full[buf]);
                 else umma_commit_2sm_mcast(&acc_full[buf], 0b11);
+                if constexpr (kDual) {
+                    if constexpr (kCG == 1) umma_commit<1>(&acc_full[1]);
+                    else umma_commit_2sm_mcast(&acc_full[1], 0b11);
+                }
             }
         } else if (kCG == 2 && rank == 1 && lane < stages_b) {
             // relay (one lane per spike-tile ring stage): tell the leader's MMA thread that this CTA's half
@@ -273,13 +295,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         // ===================================================== TMA producer (input spike-train words)
         if (elect_one()) {
             uint32_t sw = 0, pw = 0;
-            const uint32_t w_bytes = (kConv ? static_cast<uint32_t>(p.hrows) * 10u : static_cast<uint32_t>(p.Jh)) * 64u *
-                                     static_cast<uint32_t>(p.in_wb);
+            const uint32_t w_bytes = (kConv ? static_cast<uint32_t>(p.hrows) * 10u : static_cast<uint32_t>(p.Jh * (kDual ? 2 : 1))) *
+                                     64u * static_cast<uint32_t>(p.in_wb);
             for (int tile = group; tile < p.total_tiles; tile += n_groups) {
                 const int ut = tile / p.m_tiles;
                 const TilePos tp = decode_tile(p, ut);
                 const int h0 = tp.h0 + static_cast<int>(rank) * p.sub_dh, w0 = tp.w0 + static_cast<int>(rank) * p.sub_dw;
-                const int r0 = ut * p.J + static_cast<int>(rank) * p.Jh;
+                const int r0 = (ut * p.J + static_cast<int>(rank) * p.Jh) * (kDual ? 2 : 1);
                 for (int ko = 0; ko < n_outer; ++ko) {
                     mbar_wait_parked(&w_empty[sw], pw ^ 1u);
                     mbar_expect_tx(&w_full[sw], w_bytes);
@@ -325,8 +347,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         // steps of a pair serially: ~5x the latency per stage, which the fc pipeline -- one stage per k-block,
         // handed across the CTA pair -- cannot hide).
         if (!kConv && packed && p.dbg_sbo == 0 && n_pg == 1) {
-            constexpr int kMaxItems = 8;                     // 256 rows x 8 chunks / 256 threads (cta_group 1); 4 with cta_group 2
-            const int n_items = n_pairs * p.T_box;           // <= 128 rows * 8 chunks
+            constexpr int kMaxItems = 8;                     // 256 rows x 8 chunks / 256 threads (cta_group 1, or cta_group 2 dual); 4 with cta_group 2
+            const int n_items = n_pairs * p.T_box * (kDual ? 2 : 1);   // <= 256 rows * 8 chunks
             uint32_t it_src[kMaxItems], it_dst[kMaxItems], it_t[kMaxItems];
             int n_my = 0;
 #pragma unroll
@@ -334,9 +356,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 const int item = ptid + i * (kProducerWarps * 32);
                 it_src[i] = it_dst[i] = 0u; it_t[i] = 0u;
                 if (item < n_items) {
-                    const int t = item / n_pairs, pr = item - t * n_pairs;
-                    const uint32_t j = pr >> 3, q = pr & 7, r = static_cast<uint32_t>(t * p.Jh) + j;
-                    it_src[i] = static_cast<uint32_t>(pr) * 8u * wb;
+                    const int tb = item / n_pairs, pr = item - tb * n_pairs;
+                    const int b = kDual ? tb / p.T_box : 0, t = tb - b * p.T_box;     // b: accumulator buffer (dual)
+                    const uint32_t j = pr >> 3, q = pr & 7, r = static_cast<uint32_t>(b * n_half + t * p.Jh) + j;
+                    it_src[i] = static_cast<uint32_t>(b * n_pairs + pr) * 8u * wb;
                     it_dst[i] = r * 128u + ((q ^ (r & 7u)) << 4);      // slots are 1024-B aligned
                     it_t[i] = (t < p.T_live) ? static_cast<uint32_t>(t) : 32u;     // 32: padding step, zero row
                     n_my = i + 1;
@@ -490,10 +513,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 trains = reinterpret_cast<uint8_t*>(p.lv[lvl].trains);
             }
             const float wscale = __ldg(&p.w_scale[c]);
-            const uint32_t buf = it & 1u;
-            mbar_wait(&acc_full[buf], (it >> 1) & 1u);
+            for (int bi = 0; bi < (kDual ? 2 : 1); ++bi) {      // dual: both buffers belong to this tile
+            const uint32_t buf = kDual ? static_cast<uint32_t>(bi) : (it & 1u);
+            mbar_wait(&acc_full[buf], kDual ? (it & 1u) : ((it >> 1) & 1u));
             tcgen05_fence_after();
             const uint32_t acc = tmem_base + lane_addr + buf * 256u;
+            // first unit of CTA half `sub` of this accumulator (fc)
+            const int unit0 = (ut * p.J) * (kDual ? 2 : 1) + bi * p.Jh;
+            const int sub_units = p.Jh * (kDual ? 2 : 1);
 
             const int chunks_per_sub = p.Jh / CW;
             for (int ch = eg; ch < kCG * chunks_per_sub; ch += kEpiGroups) {
@@ -508,25 +535,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                     // accumulator column of (unit j, step t): fc t * Jh + j; conv (tile row, t, tile column)
                     uint32_t col = acc + static_cast<uint32_t>(sub * n_half + (kConv ? (j0 >> 3) * p.T_box * 8 + (j0 & 7) : j0));
                     const uint32_t col_step = kConv ? 8u : static_cast<uint32_t>(p.Jh);
-                    for (int tl = 0; tl < p.T_live; ++tl, col += col_step) {
-                        float cu[CW];
-                        tmem_ld<CW>(col, reinterpret_cast<uint32_t*>(cu));
+                    // fc: the loads of G steps are issued before one wait (the fc epilogue of a dual tile is not hidden
+                    // behind the next tile's main loop)
+                    constexpr int G = kConv ? 1 : 16 / CW;
+                    for (int tl0 = 0; tl0 < p.T_live; tl0 += G) {
+                        float cu[G][CW];
+#pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            if (tl0 + g < p.T_live) tmem_ld<CW>(col + g * col_step, reinterpret_cast<uint32_t*>(cu[g]));
                         tmem_ld_wait();
-                        const int t = p.t0 + tl;
-                        const float kap = p.kappa[t];
-                        const uint32_t bit = 1u << t;
+                        col += G * col_step;
 #pragma unroll
-                        for (int u = 0; u < CW; ++u) {
-                            cu[u] = __fmul_rn(cu[u], wscale);          // exact: power of two
-                            if (lif_update(v[u], ii[u], cu[u])) { tr[u] |= bit; sk[u] = __fadd_rn(sk[u], kap); }
-                        }
-                        if constexpr (!kConv) {
-                            if (p.dump != nullptr) {
+                        for (int g = 0; g < G; ++g) {
+                            const int tl = tl0 + g;
+                            if (tl >= p.T_live) break;
+                            const int t = p.t0 + tl;
+                            const float kap = p.kappa[t];
+                            const uint32_t bit = 1u << t;
 #pragma unroll
-                                for (int u = 0; u < CW; ++u) {
-                                    const int r = ut * p.J + sub * p.Jh + j0 + u;
-                                    if (r < p.rows)
-                                        p.dump[(static_cast<size_t>(tl) * p.rows + r) * p.m_total + c] = cu[u];
+                            for (int u = 0; u < CW; ++u) {
+                                cu[g][u] = __fmul_rn(cu[g][u], wscale);          // exact: power of two
+                                if (lif_update(v[u], ii[u], cu[g][u])) { tr[u] |= bit; sk[u] = __fadd_rn(sk[u], kap); }
+                            }
+                            if constexpr (!kConv) {
+                                if (p.dump != nullptr) {
+#pragma unroll
+                                    for (int u = 0; u < CW; ++u) {
+                                        const int r = unit0 + sub * sub_units + j0 + u;
+                                        if (r < p.rows)
+                                            p.dump[(static_cast<size_t>(tl) * p.dump_rows + r) * p.m_total + c] = cu[g][u];
+                                    }
                                 }
                             }
                         }
@@ -551,7 +589,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                         lim = W - ww;
                         r0 = (static_cast<size_t>(n) * H + hh) * W + ww;
                     } else {
-                        const int rr = ut * p.J + sub * p.Jh + j0;
+                        const int rr = unit0 + sub * sub_units + j0;
                         row_ok = true;
                         lim = p.rows - rr;
                         r0 = static_cast<size_t>(rr);
@@ -614,6 +652,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 if constexpr (kCG == 1) mbar_arrive(&acc_empty[buf]);
                 else mbar_arrive_cluster(&acc_empty[buf], 0);
             }
+            }   // bi
         }
     }
 

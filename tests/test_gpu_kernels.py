@@ -140,3 +140,59 @@ def test_fc_large_k_many_tiles():
         ref = torch.einsum("trk,mk->trm", z[:, -40:].double(), w_eff.double())
         assert (dump[:, -40:].double() - ref).abs().max().item() < 5e-5
         assert torch.equal(unpack_trains(trains, T), O._lif_unroll(dump, T))
+
+
+@pytest.fixture
+def dual_tiles():
+    """Force dual fc tiles (2J units per tile, both accumulator buffers fed from every weight tile) wherever the
+    tile shape allows it; restore the automatic choice afterwards."""
+    lib = _lib.load()
+    lib.snn_set_fc_tiling(2, 0, 0)
+    yield lib
+    lib.snn_set_fc_tiling(0, 0, 0)
+
+
+@pytest.mark.parametrize("T,t0,T_live,R,K,M,mode", [
+    (8, 0, 6, 50, 192, 256, 0), (12, 1, 10, 77, 128, 512, 3), (16, 0, 15, 33, 64, 256, 0), (5, 0, 4, 130, 256, 256, 3),
+    (12, 0, 11, 41, 320, 256, 3),      # 11 live steps in a 12-step box (a zero padding row per unit)
+    (12, 0, 11, 1, 64, 256, 0),        # a single RoI: buffer 1 and the peer CTA see only zero-filled rows
+    (3, 0, 1, 300, 128, 256, 1),
+])
+def test_fc_dual_tiles_currents_and_spikes(dual_tiles, T, t0, T_live, R, K, M, mode):
+    z, w, trains, dump = _fc_case(R, K, M, T, t0, T_live, mode, 2, seed=T + R)
+    pieces = dual_tiles.snn_mode_pieces(mode)
+    w_eff = split_reconstruct(w, pieces, fp16=mode in _lib.FP16_MODES)
+    ref = torch.einsum("trk,mk->trm", z.double(), w_eff.double())
+    assert not torch.isnan(dump).any(), "some accumulator columns were never written"
+    assert (dump.double() - ref).abs().max().item() < 2e-5
+    assert torch.equal(unpack_trains(trains, T), O._lif_unroll(dump, T, t0=t0))
+
+
+@pytest.mark.parametrize("in_bit0,in_wb,T,t0,T_live", [(1, 1, 8, 1, 6), (1, 2, 12, 1, 10), (5, 4, 12, 0, 3)])
+def test_fc_dual_tiles_word_formats(dual_tiles, in_bit0, in_wb, T, t0, T_live):
+    z, w, trains, dump = _fc_case(45, 128, 256, T, t0, T_live, 0, 2, seed=T + in_bit0, in_bit0=in_bit0, in_wb=in_wb)
+    ref = torch.einsum("trk,mk->trm", z.double(), w.double())
+    assert not torch.isnan(dump).any()
+    assert (dump.double() - ref).abs().max().item() < 2e-5
+    assert torch.equal(unpack_trains(trains, T), O._lif_unroll(dump, T, t0=t0))
+
+
+def test_fc_dual_tiles_are_the_default_for_long_contractions_and_match_single_tiles():
+    # K = 12544: dual tiles by default; the same layer with single tiles must give the same currents and spikes
+    lib = _lib.load()
+    # R = 2500 x M = 512: 79 dual unit tiles x 2 = 158 tiles on 74 CTA pairs = 2 full waves + a tail of 10 tiles,
+    # which the automatic choice runs as single tiles in a second launch
+    R, K, M, T, T_live = 2500, 12544, 512, 12, 11
+    z, w, trains_d, dump_d = _fc_case(R, K, M, T, 0, T_live, 3, 2, seed=11, density=0.05)
+    assert lib.snn_last_launch_count() == 2
+    lib.snn_set_fc_tiling(1, 0, 0)
+    try:
+        _, _, trains_s, dump_s = _fc_case(R, K, M, T, 0, T_live, 3, 2, seed=11, density=0.05)
+    finally:
+        lib.snn_set_fc_tiling(0, 0, 0)
+    assert not torch.isnan(dump_d).any()
+    assert torch.equal(dump_d, dump_s), "same k order per accumulator: the currents are bit-identical"
+    assert torch.equal(trains_d, trains_s)
+    w_eff = split_reconstruct(w, 2, fp16=True)
+    ref = torch.einsum("trk,mk->trm", z[:, -50:].double(), w_eff.double())
+    assert (dump_d[:, -50:].double() - ref).abs().max().item() < 1e-4
