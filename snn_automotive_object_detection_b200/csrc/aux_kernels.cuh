@@ -92,10 +92,17 @@ __device__ __forceinline__ uint32_t encode_train(float x, int T) {
 // and the train word is a telescoping XOR over the thresholds passed:
 //     word = XOR_{n : x >= thr[n]} (full[n] ^ full[n+1]),   full[n] = bits n-1, 2n-1, 3n-1, ... of a 32-step train
 // (x >= thr[n] implies x >= thr[m] for m > n, so the XOR collapses to full[n(x)]); the caller masks the live steps.
-// 2 instructions per step and neuron (FSETP + predicated LOP3) instead of the 6 of the simulation.  The thresholds
-// are found at COMPILE time by bisection on the simulation itself (constexpr fp32 arithmetic: one IEEE add/sub/mul
-// per op, the same roundings as __fadd_rn/__fmul_rn); NaN compares false everywhere = never spikes, as simulated.
-struct EncTable { float thr[33]; uint32_t delta[33]; };     // index n = 1..32; [0] unused
+// 2 instructions per step and neuron instead of the 6 of the simulation.  The thresholds are found at COMPILE time by
+// bisection on the simulation itself (constexpr fp32 arithmetic: one IEEE add/sub/mul per op, the same roundings as
+// __fadd_rn/__fmul_rn); NaN compares false everywhere = never spikes, as simulated.
+// Pipes: FSETP and LOP3 both issue to the ALU pipe (2 cycles per warp instruction), which bounded the first version
+// (ncu r01ab: ALU 73 % busy, FMA 20 %).  For words of <= 16 bits the telescoping sum is therefore taken in fp32 on the
+// FMA pipe: acc = 2^23 + SUM_{n : x >= thr[n]} (full16[n] - full16[n+1]) -- small integers, exact in fp32 -- and the
+// word is the low mantissa bits of acc: one FSETP (ALU) + one predicated FADD (FMA) per step, the pipes in parallel.
+struct EncTable {
+    float thr[33]; uint32_t delta[33];      // index n = 1..32; [0] unused
+    float deltaf[17], lastf[17];            // fp32 path (n <= 16): full16[n] - full16[n+1], and full16[n] for the bucket's last n
+};
 
 __host__ __device__ constexpr int enc_first_spike(float x, int nmax) {
     float v = 0.f;
@@ -125,144 +132,163 @@ __host__ __device__ constexpr EncTable make_enc_table() {
         tb.delta[n] = enc_full_train(n) ^ enc_full_train(n + 1);
     }
     tb.thr[0] = 0.f; tb.delta[0] = 0u;
+    for (int n = 1; n <= 16; ++n) {
+        const int a = static_cast<int>(enc_full_train(n) & 0xFFFFu), b = static_cast<int>(enc_full_train(n + 1) & 0xFFFFu);
+        tb.deltaf[n] = static_cast<float>(a - b);
+        tb.lastf[n] = static_cast<float>(a);
+    }
+    tb.deltaf[0] = 0.f; tb.lastf[0] = 0.f;
     return tb;
 }
 constexpr EncTable kEncTableHost = make_enc_table();
 __constant__ EncTable c_enc = make_enc_table();
 
-// NT >= the number of live steps (a compile-time bucket); bits at steps >= T_live are masked by the caller.
-// if (x >= th) w ^= delta: one FSETP + one predicated LOP3
+// if (x >= th) w ^= delta: one FSETP + one predicated LOP3 (both ALU pipe)
 __device__ __forceinline__ void xor_if_ge(uint32_t& w, float x, float th, uint32_t delta) {
     asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p xor.b32 %0, %0, %3;\n\t}" : "+r"(w) : "f"(x), "f"(th), "r"(delta));
 }
-template <int NT>
-__device__ __forceinline__ uint32_t encode_word(float x) {
-    uint32_t w = 0u;
-#pragma unroll
-    for (int n = 1; n <= NT; ++n) xor_if_ge(w, x, c_enc.thr[n], c_enc.delta[n]);
-    return w;
+// if (x >= th) acc += d: one FSETP (ALU pipe) + one predicated FADD (FMA pipe)
+__device__ __forceinline__ void add_if_ge(float& acc, float x, float th, float d) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p add.rn.f32 %0, %0, %3;\n\t}" : "+f"(acc) : "f"(x), "f"(th), "f"(d));
 }
 
-// N inputs at once (independent chains for the scheduler); tmask = the live steps
+// N inputs at once (independent chains for the scheduler).  NT >= the number of live steps (a compile-time bucket);
+// tmask = the live steps (bits at steps >= T_live come out of the wider bucket and are masked).
 template <int NT, int N>
 __device__ __forceinline__ void encode_words(const float (&x)[N], uint32_t tmask, uint32_t (&w)[N]) {
+    if constexpr (NT <= 16) {
+        float acc[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) w[k] = 0u;
+        for (int k = 0; k < N; ++k) acc[k] = 8388608.f;            // 2^23: integers up to 2^23 on top of it sit in the mantissa
 #pragma unroll
-    for (int n = 1; n <= NT; ++n) {
-        const float th = c_enc.thr[n];
-        const uint32_t dl = c_enc.delta[n] & tmask;
+        for (int n = 1; n <= NT; ++n) {
+            const float th = c_enc.thr[n];
+            const float d = (n == NT) ? c_enc.lastf[n] : c_enc.deltaf[n];
 #pragma unroll
-        for (int k = 0; k < N; ++k) xor_if_ge(w[k], x[k], th, dl);
+            for (int k = 0; k < N; ++k) add_if_ge(acc[k], x[k], th, d);
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) w[k] = __float_as_uint(acc[k]) & tmask;
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) w[k] = 0u;
+#pragma unroll
+        for (int n = 1; n <= NT; ++n) {
+            const float th = c_enc.thr[n];
+            const uint32_t dl = c_enc.delta[n] & tmask;
+#pragma unroll
+            for (int k = 0; k < N; ++k) xor_if_ge(w[k], x[k], th, dl);
+        }
     }
 }
+template <int NT>
+__device__ __forceinline__ uint32_t encode_word(float x, uint32_t tmask) {
+    const float xs[1] = {x};
+    uint32_t w[1];
+    encode_words<NT, 1>(xs, tmask, w);
+    return w[0];
+}
 
-// dispatch a kernel template on the bucket of live steps
-#define SNN_ENC_BUCKETS(T_live, ...)                                  \
-    do {                                                                \
-        if ((T_live) <= 4) { constexpr int NT = 4; __VA_ARGS__; }             \
-        else if ((T_live) <= 8) { constexpr int NT = 8; __VA_ARGS__; }         \
-        else if ((T_live) <= 12) { constexpr int NT = 12; __VA_ARGS__; }       \
-        else if ((T_live) <= 16) { constexpr int NT = 16; __VA_ARGS__; }       \
-        else if ((T_live) <= 24) { constexpr int NT = 24; __VA_ARGS__; }       \
-        else { constexpr int NT = 32; __VA_ARGS__; }                           \
+// dispatch a kernel template on the bucket of live steps (exact for the step counts of the reference's sweeps)
+#define SNN_ENC_BUCKETS(T_live, ...)                                            \
+    do {                                                                        \
+        if ((T_live) <= 4) { constexpr int NT = 4; __VA_ARGS__; }               \
+        else if ((T_live) <= 7) { constexpr int NT = 7; __VA_ARGS__; }          \
+        else if ((T_live) <= 8) { constexpr int NT = 8; __VA_ARGS__; }          \
+        else if ((T_live) <= 10) { constexpr int NT = 10; __VA_ARGS__; }        \
+        else if ((T_live) <= 11) { constexpr int NT = 11; __VA_ARGS__; }        \
+        else if ((T_live) <= 12) { constexpr int NT = 12; __VA_ARGS__; }        \
+        else if ((T_live) <= 16) { constexpr int NT = 16; __VA_ARGS__; }        \
+        else if ((T_live) <= 24) { constexpr int NT = 24; __VA_ARGS__; }        \
+        else { constexpr int NT = 32; __VA_ARGS__; }                            \
     } while (0)
 
-constexpr int kEncW = 32;        // pixels per block along W
+constexpr int kEncPx = 32;       // pixels per work item (one per lane)
+constexpr int kEncCh = 32;       // channels per work item (all held by one thread: a full 32-byte sector of 1-byte words)
 constexpr int kEncMaxLevels = 8;
 
 struct EncLevel {
-    const float* x;             // [N][C][H][W] fp32
-    uint8_t* z;                 // [N][H][W][C] spike-train words of `wb` bytes (bit t = z_t, t < T_live)
-    int H, W, wchunks, block_begin;
+    const float* x;             // [N][C][H*W] fp32 (contiguous NCHW)
+    uint8_t* z;                 // [N][H*W][C] spike-train words of `wb` bytes (bit t = z_t, t < T_live)
+    int HW, chunks, chunk_begin, pad_;   // chunks of 32 consecutive pixels per image (the last one ragged)
 };
 struct EncParams {
     EncLevel lv[kEncMaxLevels];
-    int n_levels, N, C, T_live, wb, total_blocks;
+    int n_levels, N, C, T_live, wb, total_items;
 };
 
-// All FPN levels in one launch.  One block = one (level, n, h, 32-pixel run):
-//   phase 1: thread = pixel (lane) x 8 consecutive channels: 8 coalesced 128-B row reads in flight, the
-//            encoder's T_live steps for the 8 neurons in lock-step, their words packed to shared memory
-//            [px][C words] (row pitch C*wb + 4 bytes: conflict-free 32-bit stores);
-//   phase 2: NHWC words out, 16 bytes per thread: a pixel's C words are contiguous, so the block writes one
-//            contiguous run of 32 * C words.
-// HBM traffic: 4 B read + wb B written per input neuron (the per-timestep planes never exist).
-template <int NT>
-__global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant__ EncParams p) {
-    extern __shared__ uint32_t s_tr[];            // [kEncW][C * wb / 4 + 1] 32-bit words of packed spike-train words
-    int lvl = 0;
-    const int bid = blockIdx.x;
-    while (lvl + 1 < p.n_levels && bid >= p.lv[lvl + 1].block_begin) ++lvl;
-    const EncLevel& L = p.lv[lvl];
-    int local = bid - L.block_begin;
-    const int per_img = L.H * L.wchunks;
-    const int n = local / per_img; local -= n * per_img;
-    const int h = local / L.wchunks;
-    const int w0 = (local - h * L.wchunks) * kEncW;
-    const int C = p.C, H = L.H, W = L.W;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = w0 + lane;
-    const int row_words = C * p.wb / 4;           // 32-bit words per pixel
-    const int ld = row_words + 1;
-    const int gw = 2 * p.wb;                      // 32-bit words per group of 8 channels
-    const float* xrow = L.x + (static_cast<size_t>(n) * C * H + h) * W + w;
-    const size_t cstride = static_cast<size_t>(H) * W;
-    const uint32_t tmask = (p.T_live >= 32) ? 0xFFFFFFFFu : ((1u << p.T_live) - 1u);
-    for (int g = warp; g < C / 8; g += 8) {       // channels 8g .. 8g+7
-        float xv[8];
+template <int WB>
+__device__ __forceinline__ void store_words16(uint8_t* dst, const uint32_t (&w)[16]) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    if constexpr (WB == 1) {
+        d[0] = make_uint4(w[0] | (w[1] << 8) | (w[2] << 16) | (w[3] << 24), w[4] | (w[5] << 8) | (w[6] << 16) | (w[7] << 24),
+                          w[8] | (w[9] << 8) | (w[10] << 16) | (w[11] << 24), w[12] | (w[13] << 8) | (w[14] << 16) | (w[15] << 24));
+    } else if constexpr (WB == 2) {
+        d[0] = make_uint4(w[0] | (w[1] << 16), w[2] | (w[3] << 16), w[4] | (w[5] << 16), w[6] | (w[7] << 16));
+        d[1] = make_uint4(w[8] | (w[9] << 16), w[10] | (w[11] << 16), w[12] | (w[13] << 16), w[14] | (w[15] << 16));
+    } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) xv[k] = (w < W) ? __ldg(xrow + (8 * g + k) * cstride) : 0.f;
-        uint32_t tw[8];
-        encode_words<NT, 8>(xv, tmask, tw);
-        uint32_t* dst = &s_tr[lane * ld + g * gw];
-        if (p.wb == 1) {
-            dst[0] = tw[0] | (tw[1] << 8) | (tw[2] << 16) | (tw[3] << 24);
-            dst[1] = tw[4] | (tw[5] << 8) | (tw[6] << 16) | (tw[7] << 24);
-        } else if (p.wb == 2) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = tw[2 * k] | (tw[2 * k + 1] << 16);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) dst[k] = tw[k];
-        }
-    }
-    __syncthreads();
-    const int npx = min(kEncW, W - w0);
-    const int q16 = row_words / 4;                // 16-byte pieces per pixel
-    uint4* dst0 = reinterpret_cast<uint4*>(L.z + ((static_cast<size_t>(n) * H + h) * W + w0) * C * p.wb);
-    for (int idx = threadIdx.x; idx < npx * q16; idx += blockDim.x) {
-        const int px = idx / q16, k4 = idx - px * q16;
-        const uint32_t* src = &s_tr[px * ld + 4 * k4];
-        dst0[idx] = make_uint4(src[0], src[1], src[2], src[3]);
+        for (int q = 0; q < 4; ++q) d[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
     }
 }
 
-// x [R][K] fp32 -> words [R][K] of `wb` bytes; 8 consecutive k per thread (2 x float4 in, 8 words out)
-template <int NT>
-__global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total8, int T_live,
-                                                          int wb, uint8_t* __restrict__ z) {
-    const uint32_t tmask = (T_live >= 32) ? 0xFFFFFFFFu : ((1u << T_live) - 1u);
-#pragma unroll 2
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
-        const float xs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t tr[8];
-        encode_words<NT, 8>(xs, tmask, tr);
-        if (wb == 1) {
-            uint2 o;
-            o.x = tr[0] | (tr[1] << 8) | (tr[2] << 16) | (tr[3] << 24);
-            o.y = tr[4] | (tr[5] << 8) | (tr[6] << 16) | (tr[7] << 24);
-            reinterpret_cast<uint2*>(z)[i] = o;
-        } else if (wb == 2) {
-            reinterpret_cast<uint4*>(z)[i] =
-                make_uint4(tr[0] | (tr[1] << 16), tr[2] | (tr[3] << 16), tr[4] | (tr[5] << 16), tr[6] | (tr[7] << 16));
-        } else {
-            reinterpret_cast<uint4*>(z)[2 * i] = make_uint4(tr[0], tr[1], tr[2], tr[3]);
-            reinterpret_cast<uint4*>(z)[2 * i + 1] = make_uint4(tr[4], tr[5], tr[6], tr[7]);
+// All FPN levels in one launch, no shared memory.  A level's channel planes and its NHWC output are both contiguous
+// in the flat pixel index, so the work item of a WARP is (32 consecutive flat pixels, 32 consecutive channels):
+//   lane = pixel; its 32 loads (one per channel plane, each a coalesced 128-byte row across the warp) are all issued
+//   before the comparator bank runs, and its 32 words are 32 / 64 / 128 contiguous bytes of the NHWC output -- whole
+//   32-byte sectors, written with 16-byte stores.  Consecutive warps take the channel groups of the same pixels, so a
+//   block completes whole pixel rows.  Grid-stride over the items of all levels and images.
+// HBM traffic: 4 B read + wb B written per input neuron (the per-timestep planes never exist).
+template <int NT, int WB>
+__global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant__ EncParams p) {
+    const int lane = threadIdx.x & 31;
+    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    const int cgroups = p.C / kEncCh;
+    const uint32_t tmask = (p.T_live >= 32) ? 0xFFFFFFFFu : ((1u << p.T_live) - 1u);
+    for (int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < p.total_items; item += n_warps) {
+        const int chunk = item / cgroups, c0 = (item - chunk * cgroups) * kEncCh;
+        int lvl = 0;
+        while (lvl + 1 < p.n_levels && chunk >= p.lv[lvl + 1].chunk_begin) ++lvl;
+        const EncLevel& L = p.lv[lvl];
+        int local = chunk - L.chunk_begin;
+        const int n = local / L.chunks;
+        local -= n * L.chunks;
+        const int px = local * kEncPx + lane;
+        const bool ok = px < L.HW;
+        const size_t hw = static_cast<size_t>(L.HW);
+        // byte pointer of channel c0, then one 32 x 32 -> 64-bit multiply-add per channel plane
+        const char* src = reinterpret_cast<const char*>(L.x + (static_cast<size_t>(n) * p.C + c0) * hw + px);
+        const uint32_t plane = static_cast<uint32_t>(L.HW) * 4u;
+        float xv[kEncCh];
+#pragma unroll
+        for (int k = 0; k < kEncCh; ++k)
+            xv[k] = ok ? __ldg(reinterpret_cast<const float*>(src + static_cast<uint64_t>(plane) * static_cast<uint32_t>(k))) : 0.f;
+        uint8_t* dst = L.z + ((static_cast<size_t>(n) * hw + px) * p.C + c0) * WB;
+#pragma unroll
+        for (int h = 0; h < kEncCh / 16; ++h) {
+            float xs[16];
+            uint32_t w[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) xs[k] = xv[16 * h + k];
+            encode_words<NT, 16>(xs, tmask, w);
+            if (ok) store_words16<WB>(dst + 16 * h * WB, w);
         }
+    }
+}
+
+// x [R][K] fp32 -> words [R][K] of WB bytes; 16 consecutive k per thread and iteration (4 x float4 in flight)
+template <int NT, int WB>
+__global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total16, int T_live,
+                                                          uint8_t* __restrict__ z) {
+    const uint32_t tmask = (T_live >= 32) ? 0xFFFFFFFFu : ((1u << T_live) - 1u);
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total16;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4* src = reinterpret_cast<const float4*>(x) + 4 * i;
+        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
+        const float xs[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+        uint32_t w[16];
+        encode_words<NT, 16>(xs, tmask, w);
+        store_words16<WB>(z + i * 16 * WB, w);
     }
 }
 
@@ -582,7 +608,7 @@ __global__ void __launch_bounds__(256) encoder_selftest_kernel(int T_live, unsig
     for (unsigned long long b = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; b < (1ull << 32);
          b += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
         const float x = __uint_as_float(static_cast<uint32_t>(b));
-        bad += (encode_word<NT>(x) & tmask) != encode_train(x, T_live);
+        bad += encode_word<NT>(x, tmask) != encode_train(x, T_live);
     }
     for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, static_cast<unsigned long long>(bad));

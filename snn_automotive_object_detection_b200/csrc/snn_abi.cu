@@ -304,6 +304,18 @@ __global__ void build_lut_kernel(int T, int nbytes, float* lut) {
 
 int word_bytes(int nbits) { return nbits <= 8 ? 1 : nbits <= 16 ? 2 : 4; }
 
+// x [total] fp32 -> words of wb bytes (total a multiple of 16)
+void launch_encode_rows(const float* x, size_t total, int T_live, int wb, uint8_t* z, int sms, cudaStream_t st) {
+    const size_t total16 = total / 16;
+    const size_t want = (total16 + 255) / 256;
+    const int blocks = static_cast<int>(want > static_cast<size_t>(sms) * 8 ? static_cast<size_t>(sms) * 8 : want);
+    SNN_ENC_BUCKETS(T_live, {
+        if (wb == 1) encode_rows_kernel<NT, 1><<<blocks, 256, 0, st>>>(x, total16, T_live, z);
+        else if (wb == 2) encode_rows_kernel<NT, 2><<<blocks, 256, 0, st>>>(x, total16, T_live, z);
+        else encode_rows_kernel<NT, 4><<<blocks, 256, 0, st>>>(x, total16, T_live, z);
+    });
+}
+
 struct RpnWs { size_t z_off[kMaxLevels], tr_off[kMaxLevels], lut_off, total; };
 
 int rpn_ws_layout(const int* H, const int* W, int L, int N, int C, int T, int mode, RpnWs& ws, TileCfg& tc) {
@@ -544,20 +556,21 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
         {
             EncParams ep;
             memset(&ep, 0, sizeof(ep));
-            int blocks = 0;
+            int chunks = 0;
             for (int l = 0; l < n_levels; ++l) {
                 EncLevel& E = ep.lv[l];
                 E.x = reinterpret_cast<const float*>(feat_ptrs[l]);
                 E.z = wsp + ws.z_off[l];
-                E.H = H[l]; E.W = W[l]; E.wchunks = (W[l] + kEncW - 1) / kEncW; E.block_begin = blocks;
-                blocks += N * H[l] * E.wchunks;
+                E.HW = H[l] * W[l]; E.chunks = (E.HW + kEncPx - 1) / kEncPx; E.chunk_begin = chunks;
+                chunks += N * E.chunks;
             }
-            ep.n_levels = n_levels; ep.N = N; ep.C = C_in; ep.T_live = T_live; ep.wb = word_bytes(T_live); ep.total_blocks = blocks;
-            const size_t smem = static_cast<size_t>(kEncW) * (C_in * ep.wb / 4 + 1) * 4;
+            ep.n_levels = n_levels; ep.N = N; ep.C = C_in; ep.T_live = T_live; ep.wb = word_bytes(T_live);
+            ep.total_items = chunks * (C_in / kEncCh);
+            const int blocks = (ep.total_items + 7) / 8 < di.sms * 8 ? (ep.total_items + 7) / 8 : di.sms * 8;
             SNN_ENC_BUCKETS(T_live, {
-                if (smem > 48 * 1024)
-                    CUDA_TRY(cudaFuncSetAttribute(encode_nchw_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                encode_nchw_kernel<NT><<<blocks, 256, smem, st>>>(ep);
+                if (ep.wb == 1) encode_nchw_kernel<NT, 1><<<blocks, 256, 0, st>>>(ep);
+                else if (ep.wb == 2) encode_nchw_kernel<NT, 2><<<blocks, 256, 0, st>>>(ep);
+                else encode_nchw_kernel<NT, 4><<<blocks, 256, 0, st>>>(ep);
             });
             CUDA_TRY(cudaGetLastError()); ++g_launches;
         }
@@ -695,11 +708,9 @@ static int box_head_forward_impl(const void* x, bool x_is_words, int R, int K, i
     const int T_live6 = stats ? T - 1 : T - 2;
     const int T_live7 = T - 2;
     if (!x_is_words) {
-        const size_t total8 = static_cast<size_t>(R) * K / 8;
-        const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
         phase_begin(PH_ENC_BOX, st);
-        SNN_ENC_BUCKETS(T_live6, (encode_rows_kernel<NT><<<blocks, 256, 0, st>>>(
-                                      reinterpret_cast<const float*>(x), total8, T_live6, word_bytes(T - 1), wsp + ws.z_off)));
+        launch_encode_rows(reinterpret_cast<const float*>(x), static_cast<size_t>(R) * K, T_live6, word_bytes(T - 1),
+                           wsp + ws.z_off, di.sms, st);
         phase_end(PH_ENC_BOX, st);
         CUDA_TRY(cudaGetLastError()); ++g_launches;
     }
@@ -825,12 +836,12 @@ int snn_profile_read(float* ms_out, int* counts_out) {
 }
 
 int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_words, snn_stream_t stream) {
-    if (!x || !z_words || R < 1 || K % 8 != 0 || T_live < 1 || T_live > 32)
+    if (!x || !z_words || R < 1 || K % 16 != 0 || T_live < 1 || T_live > 32)
         return fail(SNN_E_ARG, "encode_rows: bad argument");
-    const size_t total8 = static_cast<size_t>(R) * K / 8;
-    const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 16 ? 148 * 16 : (total8 + 255) / 256);
-    SNN_ENC_BUCKETS(T_live, (encode_rows_kernel<NT><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-                                 x, total8, T_live, word_bytes(T_live), reinterpret_cast<uint8_t*>(z_words))));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    launch_encode_rows(x, static_cast<size_t>(R) * K, T_live, word_bytes(T_live), reinterpret_cast<uint8_t*>(z_words), sms,
+                       (cudaStream_t)stream);
     CUDA_TRY(cudaGetLastError());
     return SNN_OK;
 }
