@@ -160,9 +160,14 @@ void snn_set_cta_group(int cta_group);
 /* fc tiling of subsequent calls on this thread -- tests/profiling only.  dual: 0 = auto (dual tiles -- 2J units whose
  * two accumulators share every weight tile -- for K >= 4096), 1 = never, 2 = whenever the tile shape allows it;
  * max_units > 0 caps the units per accumulator tile (0 = the widest tile without a padding step, else the widest);
- * tail_split: 0 = auto (a last wave of dual tiles that is less than half full runs as single tiles in a second
- * launch), 1 = never. */
+ * tail_split: 0 = auto (the units a last, partly filled wave of dual tiles would cover run in a second launch as one
+ * wave of single tiles), 1 = never, 2 = as one wave of narrower dual tiles when such a shape exists. */
 void snn_set_fc_tiling(int dual, int max_units, int tail_split);
+/* Profiling only: the MMA-issuing thread of every CTA pair of the next spike-GEMM launches of `phase` (0 = RPN conv,
+ * 1 = fc with K >= 4096 in dual tiles, 3 = the same in single tiles, 2 = other fc) on this thread writes 8 counters in SM clock cycles to device_counters
+ * [pairs][8]: [0] whole role, [1] waiting for a free accumulator, [2] for this CTA's half of a spike tile, [3] for the
+ * peer CTA's half, [4] for weight tiles, [5] number of tiles.  NULL switches it off. */
+void snn_set_role_timers(unsigned long long* device_counters, int phase);
 
 /* Per-phase device timing for bench.py: when enabled, every forward records CUDA events on its stream
  * around each phase (up to 256 forwards).  snn_profile_read() waits for them, writes the summed

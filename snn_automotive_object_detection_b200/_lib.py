@@ -23,7 +23,7 @@ EXPORTS = [
     "snn_prepare_conv3x3_weights", "snn_prepare_fc_weights", "snn_rpn_head_workspace_bytes", "snn_rpn_head_forward",
     "snn_box_head_workspace_bytes", "snn_box_head_forward", "snn_fc_lif_layer", "snn_encode_rows",
     "snn_last_launch_count", "snn_set_cta_group", "snn_profile_enable", "snn_profile_read", "snn_rpn_decode_selected",
-    "snn_roi_align_encode", "snn_box_head_forward_encoded", "snn_encoder_table", "snn_encoder_selftest", "snn_set_fc_tiling",
+    "snn_roi_align_encode", "snn_box_head_forward_encoded", "snn_encoder_table", "snn_encoder_selftest", "snn_set_fc_tiling", "snn_set_role_timers",
 ]
 PHASES = ["rpn_encoder", "rpn_conv_lif_gemm", "rpn_readout", "box_encoder", "fc6_lif_gemm", "fc7_lif_gemm", "box_readout"]
 
@@ -62,6 +62,7 @@ def _declare(lib):
     lib.snn_last_launch_count.restype = i
     lib.snn_set_cta_group.argtypes = [i]; lib.snn_set_cta_group.restype = None
     lib.snn_set_fc_tiling.argtypes = [i, i, i]; lib.snn_set_fc_tiling.restype = None
+    lib.snn_set_role_timers.argtypes = [vp, i]; lib.snn_set_role_timers.restype = None
     lib.snn_profile_enable.argtypes = [i]; lib.snn_profile_enable.restype = None
     lib.snn_profile_read.argtypes = [c.POINTER(c.c_float), pi]; lib.snn_profile_read.restype = i
 

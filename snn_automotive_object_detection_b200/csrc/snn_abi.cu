@@ -23,7 +23,9 @@ thread_local int g_launches = 0;
 thread_local int g_force_cg = 0;
 thread_local int g_fc_dual = 0;      // 0 auto, 1 never, 2 whenever the tile shape allows it (tests)
 thread_local int g_fc_units = 0;     // > 0: cap on the units per fc tile (experiments)
-thread_local int g_fc_split = 0;     // 1: never run the last partial wave of dual tiles as single tiles (experiments)
+thread_local int g_fc_split = 0;
+thread_local unsigned long long* g_role_cycles = nullptr;   // profiling: MMA-thread wait counters of the next launches
+thread_local int g_role_phase = -1;                        // which launch gets them: 0 conv, 1 / 3 fc with K >= 4096 in dual / single tiles, 2 other fc     // 1: never run the last partial wave of dual tiles as single tiles (experiments)
 
 // Optional per-phase device timing (CUDA events recorded on the launch stream around each phase).
 enum Phase { PH_ENC_RPN = 0, PH_GEMM_RPN, PH_RO_RPN, PH_ENC_BOX, PH_GEMM_FC6, PH_GEMM_FC7, PH_RO_BOX, PH_COUNT };
@@ -139,10 +141,12 @@ const float* scale_of(const void* w_prep, int rows, int cols, int mode) {
 struct TileCfg { int cg, T_box, J, Jh, TW, TH, TWh, THh, dw, dh, CW, n_mma; };
 
 // Fold time into the MMA N dimension: N = T_box * J <= 256, N % 16 == 0, J units per tile.
-bool pick_tile_cg(int T_live, bool conv, int cg, TileCfg& out) {
+// cap_units > 0: no more than that many units per tile.
+bool pick_tile_cg(int T_live, bool conv, int cg, TileCfg& out, int cap_units = 0) {
     const int step = conv ? 8 * cg : 2 * cg;      // fc: units per CTA a multiple of 2 (epilogue chunks of 2, 4 or 8)
     int maxJ = kMaxUnitsPerCta * cg;                              // producers: Jh * 8 pairs <= kMaxPairs x 64 threads
     if (!conv && g_fc_units >= step && g_fc_units < maxJ) maxJ = g_fc_units;
+    if (cap_units >= step && cap_units < maxJ) maxJ = cap_units;
     int bestJ = 0, bestT = 0;
     for (int J = step; J <= maxJ; J += step)
         for (int Tb = T_live; Tb <= T_live + 1; ++Tb) {
@@ -273,6 +277,17 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
         p.n_pg = m >= 2 ? 2 : 1;      // pair-loop producers: 2 groups x 4 warps beat 4 x 2 (r01h vs r01f)
         if (p.conv) p.n_pg = 1;       // one stage per 64-channel block serves 9 taps: all 8 warps fill it together
         if (!p.conv && tc.T_box <= 16) p.n_pg = 1;   // fc item-parallel producers: all 8 warps fill every stage
+    }
+    if (const char* e = getenv("SNN_DBG_STAGES")) {        // "a,b": ring depths, profiling experiments only
+        int a = 0, b = 0;
+        if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 2 && a <= kStagesA && b >= 1 && b <= kMaxStagesB &&
+            static_cast<size_t>(a) * kTileBytesA + static_cast<size_t>(b) * p.slot_b <= static_cast<size_t>(ring_total) && !p.conv) {
+            p.stages_a = a; p.stages_b = b;
+        }
+    }
+    {
+        const int phase = p.conv ? 0 : (p.kblocks >= 64 ? (p.dual ? 1 : 3) : 2);
+        p.role_cycles = (g_role_cycles != nullptr && phase == g_role_phase) ? g_role_cycles : nullptr;
     }
     p.m_tiles = p.m_total / (128 * tc.cg);
     p.total_tiles = p.unit_tiles * p.m_tiles;
@@ -413,16 +428,29 @@ int fc_layer(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, 
     const bool dual_ok = tc.cg == 2 && tc.T_box <= 16 && (tc.n_mma / 2) % 8 == 0;
     bool dual = dual_ok && g_fc_dual != 1 && (g_fc_dual == 2 || K / 64 >= 64);
     int R1 = R;                                   // units [0, R1) in the first launch
+    TileCfg tail = tc;                            // tile shape of the second launch
+    bool tail_dual = false;
     if (dual && g_fc_dual == 0) {
         const int groups = di.sms / 2, m_tiles = M / 256, U2 = 2 * tc.J;
         const int ut_total = (R + U2 - 1) / U2;
         const int full = ut_total * m_tiles / groups;                 // complete waves of dual tiles
         if (full == 0) {
             if ((R + tc.J - 1) / tc.J * m_tiles <= groups) dual = false;   // one wave either way: single tiles are half as long
-        } else if (ut_total * m_tiles > full * groups) {
+        } else if (ut_total * m_tiles > full * groups && g_fc_split != 1) {
+            // the units left after the full waves fit ONE wave of smaller tiles: single tiles of the same shape
+            // (measured r01ae: 0.622 ms), or -- tail_split 2 -- narrower dual tiles (N = 96: 0.631 ms)
             const int UT1 = full * groups / m_tiles;
-            const int singles = ((R - UT1 * U2) + tc.J - 1) / tc.J * m_tiles;
-            if (singles <= groups && g_fc_split != 1) R1 = UT1 * U2;
+            const int R2 = R - UT1 * U2;
+            const int step = 2 * tc.cg;
+            for (int cap = step; cap < tc.J && g_fc_split == 2; cap += step) {
+                TileCfg t2{};
+                if (!pick_tile_cg(T_live, false, 2, t2, cap) || t2.J != cap) continue;
+                if ((t2.n_mma / 2) % 8 != 0 || t2.n_mma < 96) continue;
+                if ((R2 + 2 * t2.J - 1) / (2 * t2.J) * m_tiles > groups) continue;
+                tail = t2; tail_dual = true; R1 = UT1 * U2;
+                break;
+            }
+            if (R1 == R && (R2 + tc.J - 1) / tc.J * m_tiles <= groups) R1 = UT1 * U2;
         }
     }
     const size_t tb = snn_train_word_bytes(T);
@@ -431,7 +459,7 @@ int fc_layer(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, 
     rc = fc_launch(di, reinterpret_cast<const uint8_t*>(z_words) + static_cast<size_t>(R1) * K * in_wb, in_wb, in_bit0,
                    R - R1, K, M, T, t0, T_live, mode, w_prep,
                    reinterpret_cast<uint8_t*>(trains) + static_cast<size_t>(R1) * M * tb,
-                   dump ? dump + static_cast<size_t>(R1) * M : nullptr, R, tc, false, st);
+                   dump ? dump + static_cast<size_t>(R1) * M : nullptr, R, tail, tail_dual, st);
     return rc;
 }
 
@@ -471,10 +499,14 @@ int snn_version(void) { return SNN_ABI_VERSION; }
 const char* snn_last_error(void) { return g_err.c_str(); }
 int snn_last_launch_count(void) { return g_launches; }
 void snn_set_cta_group(int cg) { g_force_cg = (cg == 1 || cg == 2) ? cg : 0; }
+void snn_set_role_timers(unsigned long long* device_counters, int phase) {
+    g_role_cycles = device_counters;
+    g_role_phase = phase;
+}
 void snn_set_fc_tiling(int dual, int max_units, int tail_split) {
     g_fc_dual = (dual == 1 || dual == 2) ? dual : 0;
     g_fc_units = max_units > 0 ? max_units : 0;
-    g_fc_split = tail_split == 1 ? 1 : 0;
+    g_fc_split = (tail_split == 1 || tail_split == 2) ? tail_split : 0;
 }
 int snn_train_word_bytes(int T) { return T <= 8 ? 1 : T <= 16 ? 2 : 4; }
 int snn_mode_pieces(int mode) { return nsplit_of(mode); }

@@ -98,6 +98,10 @@ struct GemmLifParams {
     const float* w_scale;     // [m_total] power of two each accumulator row is multiplied with (1 for bf16 pieces)
     float* dump;              // debug (fc only): raw currents [T_live][dump_rows][m_total]
     int dump_rows;
+    // profiling only (nullable): per CTA pair 8 counters of the MMA-issuing thread, in SM clock cycles:
+    // [0] whole role, [1] waiting for a free accumulator, [2] for this CTA's spike-tile half, [3] for the peer's
+    // half, [4] for weight tiles, [5] tiles
+    unsigned long long* role_cycles;
     int dbg_shift, dbg_sbo, dbg_boff;   // swizzle experiment (scratch/swizzle_experiment.py, fc only): row shift, group stride, base-offset field
     // fused leaky-integrator readout (conv, cta_group 2, m_total == 256): mem_{T-1} = W . sum_t kappa_{T-1-t} spk_t
     int fuse_readout, A;
@@ -221,19 +225,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         // ======================================================= MMA issuer
         if (rank == 0 && elect_one()) {
             uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+            const bool timed = p.role_cycles != nullptr;
+            long long c_acc = 0, c_b = 0, c_peer = 0, c_a = 0, c0 = 0;
+            const long long c_begin = timed ? clock64() : 0;
             for (int tile = group; tile < p.total_tiles; tile += n_groups, ++it) {
                 const uint32_t buf = kDual ? 0u : (it & 1u);
+                if (timed) c0 = clock64();
                 if constexpr (kDual) {
                     mbar_wait(&acc_empty[0], (it & 1u) ^ 1u);
                     mbar_wait(&acc_empty[1], (it & 1u) ^ 1u);
                 } else {
                     mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);
                 }
+                if (timed) c_acc += clock64() - c0;
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 256u;
                 for (int ko = 0; ko < n_outer; ++ko) {
+                    if (timed) c0 = clock64();
                     mbar_wait(&b_ready[sb], pb);
+                    if (timed) { const long long c1 = clock64(); c_b += c1 - c0; c0 = c1; }
                     if constexpr (kCG == 2) mbar_wait_cluster(&b_peer[sb], pb);
+                    if (timed) c_peer += clock64() - c0;
                     tcgen05_fence_after();
                     const uint32_t b_slot = smem_u32(b_ring + sb * p.slot_b);
                     for (int ki = 0; ki < n_inner; ++ki) {
@@ -249,7 +261,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                                          (static_cast<uint64_t>(p.dbg_boff & 7) << 49);
                         }
                         for (int s = 0; s < p.nsplit; ++s) {
+                            if (timed) c0 = clock64();
                             mbar_wait(&a_full[sa], pa);
+                            if (timed) c_a += clock64() - c0;
                             tcgen05_fence_after();
                             const uint64_t a_desc = umma_desc_sw128(smem_u32(a_ring + sa * kTileBytesA));
 #pragma unroll
@@ -278,6 +292,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                     if constexpr (kCG == 1) umma_commit<1>(&acc_full[1]);
                     else umma_commit_2sm_mcast(&acc_full[1], 0b11);
                 }
+            }
+            if (timed) {
+                unsigned long long* out = p.role_cycles + static_cast<size_t>(group) * 8;
+                out[0] = static_cast<unsigned long long>(clock64() - c_begin);
+                out[1] = static_cast<unsigned long long>(c_acc); out[2] = static_cast<unsigned long long>(c_b);
+                out[3] = static_cast<unsigned long long>(c_peer); out[4] = static_cast<unsigned long long>(c_a);
+                out[5] = it;
             }
         } else if (kCG == 2 && rank == 1 && lane < stages_b) {
             // relay (one lane per spike-tile ring stage): tell the leader's MMA thread that this CTA's half
