@@ -260,7 +260,10 @@ def run_ours(args):
     sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    _lib.profile_enable(True)
+    # inside the timed region only the dominant kernel is bracketed by CUDA events (on the launch stream, by the
+    # library); all seven phases are timed in a second pass of the same step below, so that 14 event records per
+    # step do not sit between the kernels of the headline measurement (r01ag: 2.40 -> 2.37 ms per step)
+    _lib.profile_enable(True, phases=["rpn_conv_lif_gemm"])
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -271,8 +274,16 @@ def run_ours(args):
     sync_all()
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
+    live = _lib.profile_read()
+    _lib.profile_enable(True)
+    for _ in range(args.steps):
+        step_resident()
+    if pending[0] is not None:
+        pending[1] = pending[0].result(); pending[0] = None
+    sync_all()
     phases = _lib.profile_read()
     _lib.profile_enable(False)
+    phases["rpn_conv_lif_gemm"] = live["rpn_conv_lif_gemm"]      # the roofline uses the launch times of the timed region
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     per_rank_ms = [ms_total / args.steps]
     if world > 1:
@@ -432,6 +443,8 @@ def run_ours(args):
                    "parallelism": f"image-sharded dp{world}, no hot-path collective"},
         "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "phase_ms_per_step": phase_ms,
+        "phase_timing": "rpn_conv_lif_gemm: CUDA events on the launch stream inside the timed region; the other phases: "
+                        "a second pass of the same steps with every phase bracketed",
         "other_kernels": extra, "other_modes": other_modes,
         "ms_per_step_by_rank": per_rank_ms,          # value uses the maximum
     }

@@ -101,7 +101,7 @@ int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box
  * Spikes travel between kernels only as time-packed spike-train WORDS: one word per neuron, bit t = spike
  * at step t, 1 / 2 / 4 bytes for up to 8 / 16 / 32 steps.
  *
- * encoder only: x [R][K] fp32 -> z_words [R][K], words of 1/2/4 bytes for T_live <= 8/16/32, bit t = z_t
+ * encoder only: x [R][K] fp32 (K a multiple of 16) -> z_words [R][K], words of 1/2/4 bytes for T_live <= 8/16/32, bit t = z_t
  * (Norse lif_current_encoder, faster_rcnn.py:494). */
 int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_words, snn_stream_t stream);
 /* The encoders evaluate lif_current_encoder as a comparator bank: the input current is constant and a spike resets
@@ -172,7 +172,8 @@ void snn_set_role_timers(unsigned long long* device_counters, int phase);
 /* Per-phase device timing for bench.py: when enabled, every forward records CUDA events on its stream
  * around each phase (up to 256 forwards).  snn_profile_read() waits for them, writes the summed
  * milliseconds and the number of timed forwards per phase, and resets.  Phase order:
- * 0 rpn encoder, 1 rpn conv+LIF GEMM, 2 rpn readout, 3 box encoder, 4 fc6+LIF GEMM, 5 fc7+LIF GEMM, 6 box readout. */
+ * 0 rpn encoder, 1 rpn conv+LIF GEMM, 2 rpn readout, 3 box encoder, 4 fc6+LIF GEMM, 5 fc7+LIF GEMM, 6 box readout.
+ * on: 0 = off, 1 = every phase, else a mask with bit (1 + phase) set for each phase to time (4 = the conv GEMM only). */
 #define SNN_PHASES 7
 void snn_profile_enable(int on);
 int snn_profile_read(float* ms_out, int* counts_out);

@@ -9,8 +9,8 @@ TAG=${1:-r01}
 MODE=${2:-fp16x2}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 3 --mode $MODE --no-e2e --no-cpu-baseline --no-other-modes"
-# per step: rpn {lut, encoder, conv gemm} + box {lut, encoder, fc6 gemm, fc7 gemm, readout} = 8 launches; 2 weight-prep first
+# per step: rpn {encoder, conv gemm} + box {lut, encoder, fc6 gemm (dual tiles), fc6 gemm (tail wave), fc7 gemm, readout} = 8 launches
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${TAG}_launches_${MODE}.csv $CMD > gpurun_out/${TAG}_launches_${MODE}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:spike_gemm_lif -s 9 -c 3 -o gpurun_out/${TAG}_gemm_${MODE} $CMD > gpurun_out/${TAG}_gemm_${MODE}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"encode_|readout_|build_lut" -s 15 -c 5 -o gpurun_out/${TAG}_aux_${MODE} $CMD > gpurun_out/${TAG}_aux_${MODE}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:spike_gemm_lif -s 12 -c 4 -o gpurun_out/${TAG}_gemm_${MODE} $CMD > gpurun_out/${TAG}_gemm_${MODE}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"encode_|readout_|build_lut" -s 12 -c 4 -o gpurun_out/${TAG}_aux_${MODE} $CMD > gpurun_out/${TAG}_aux_${MODE}.log 2>&1
 ls -la gpurun_out | tail -8

@@ -99,8 +99,15 @@ def mode_id(mode):
         raise ValueError(f"unknown mode {mode!r}; expected one of {sorted(MODES)}") from None
 
 
-def profile_enable(on: bool):
-    load().snn_profile_enable(1 if on else 0)
+def profile_enable(on, phases=None):
+    """Per-phase CUDA-event timing inside the library: off, every phase, or only the named `phases`."""
+    if on and phases:
+        mask = 0
+        for name in phases:
+            mask |= 1 << (1 + PHASES.index(name))
+        load().snn_profile_enable(mask)
+    else:
+        load().snn_profile_enable(1 if on else 0)
 
 
 def profile_read():

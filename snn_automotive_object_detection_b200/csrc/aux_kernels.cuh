@@ -387,6 +387,8 @@ constexpr int kRoRows = 8;         // RoIs per block
 // every 8th output row of [w_cls; w_box], streams it once (coalesced) against all 8 RoIs and finishes
 // with a warp-shuffle reduction.  Also per-RoI spike counts of this layer and of an optional
 // second layer `trains_b` (fc6): counts[0][R] = layer b, counts[1][R] = this layer.
+// The kernel is latency-bound (250 blocks, a few KB each), so every global read is a 16-byte vector and all the
+// vectors of a row are requested before the first is used: one memory latency per row instead of one per 32 words.
 template <typename TrainT>
 __global__ void __launch_bounds__(256) readout_rows_kernel(const TrainT* __restrict__ trains,
                                                            const TrainT* __restrict__ trains_b, int R, int Hd,
@@ -397,6 +399,8 @@ __global__ void __launch_bounds__(256) readout_rows_kernel(const TrainT* __restr
                                                            unsigned int* __restrict__ counts) {
     __shared__ float s_lut[256 * sizeof(TrainT)];
     extern __shared__ float s_s[];                 // [kRoRows][Hd]
+    constexpr int kWpv = 16 / static_cast<int>(sizeof(TrainT));      // words per 16-byte vector
+    constexpr int kMaxVec = 8;                                       // vectors per lane and pass (Hd <= 8 * 32 * kWpv per pass)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = blockIdx.x * kRoRows;
     for (int i = threadIdx.x; i < 256 * static_cast<int>(sizeof(TrainT)); i += blockDim.x) s_lut[i] = lut_g[i];
@@ -404,16 +408,33 @@ __global__ void __launch_bounds__(256) readout_rows_kernel(const TrainT* __restr
     {   // warp q stages row r0 + q (8 warps <-> 8 rows) and counts its spikes
         const int r = r0 + warp;
         unsigned int ca = 0, cb = 0;
-        for (int h = lane; h < Hd; h += 32) {
-            float sv = 0.f;
-            if (r < R) {
-                const TrainT tr = trains[static_cast<size_t>(r) * Hd + h];
-                ca += __popc(static_cast<unsigned int>(tr));
-                sv = lut_weight<TrainT>(s_lut, tr);
-                if (trains_b != nullptr)
-                    cb += __popc(static_cast<unsigned int>(trains_b[static_cast<size_t>(r) * Hd + h]));
+        const int n_vec = Hd / kWpv;
+        for (int v0 = 0; v0 < n_vec; v0 += 32 * kMaxVec) {
+            uint4 va[kMaxVec], vb[kMaxVec];
+#pragma unroll
+            for (int i = 0; i < kMaxVec; ++i) {
+                const int v = v0 + lane + 32 * i;
+                va[i] = make_uint4(0u, 0u, 0u, 0u); vb[i] = va[i];
+                if (r < R && v < n_vec) {
+                    va[i] = __ldg(reinterpret_cast<const uint4*>(trains + static_cast<size_t>(r) * Hd) + v);
+                    if (trains_b != nullptr) vb[i] = __ldg(reinterpret_cast<const uint4*>(trains_b + static_cast<size_t>(r) * Hd) + v);
+                }
             }
-            s_s[warp * Hd + h] = sv;
+#pragma unroll
+            for (int i = 0; i < kMaxVec; ++i) {
+                const int v = v0 + lane + 32 * i;
+                if (v >= n_vec) break;
+                ca += __popc(va[i].x) + __popc(va[i].y) + __popc(va[i].z) + __popc(va[i].w);
+                cb += __popc(vb[i].x) + __popc(vb[i].y) + __popc(vb[i].z) + __popc(vb[i].w);
+                const uint32_t w32[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
+                float* dst = &s_s[warp * Hd + v * kWpv];
+#pragma unroll
+                for (int e = 0; e < kWpv; ++e) {
+                    constexpr int per32 = 4 / static_cast<int>(sizeof(TrainT));
+                    const TrainT tr = static_cast<TrainT>(w32[e / per32] >> (8 * static_cast<int>(sizeof(TrainT)) * (e % per32)));
+                    dst[e] = lut_weight<TrainT>(s_lut, tr);
+                }
+            }
         }
         if (counts != nullptr) {
             for (int off = 16; off > 0; off >>= 1) {
@@ -425,16 +446,31 @@ __global__ void __launch_bounds__(256) readout_rows_kernel(const TrainT* __restr
     }
     __syncthreads();
     const int n_out = n_cls + n_box;
+    const int n_v4 = Hd / 4;
     for (int o = warp; o < n_out; o += 8) {
-        const float* wrow = (o < n_cls) ? (w_cls + static_cast<size_t>(o) * Hd) : (w_box + static_cast<size_t>(o - n_cls) * Hd);
+        const float4* wrow = reinterpret_cast<const float4*>((o < n_cls) ? (w_cls + static_cast<size_t>(o) * Hd)
+                                                                         : (w_box + static_cast<size_t>(o - n_cls) * Hd));
         float acc[kRoRows];
 #pragma unroll
         for (int q = 0; q < kRoRows; ++q) acc[q] = 0.f;
-#pragma unroll 4
-        for (int h = lane; h < Hd; h += 32) {
-            const float wv = __ldg(&wrow[h]);
+        for (int v0 = 0; v0 < n_v4; v0 += 32 * kMaxVec) {
+            float4 wv[kMaxVec];
 #pragma unroll
-            for (int q = 0; q < kRoRows; ++q) acc[q] = fmaf(wv, s_s[q * Hd + h], acc[q]);
+            for (int i = 0; i < kMaxVec; ++i) {
+                const int v = v0 + lane + 32 * i;
+                wv[i] = (v < n_v4) ? __ldg(wrow + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < kMaxVec; ++i) {
+                const int v = v0 + lane + 32 * i;
+                if (v >= n_v4) break;
+#pragma unroll
+                for (int q = 0; q < kRoRows; ++q) {
+                    const float4 sv = *reinterpret_cast<const float4*>(&s_s[q * Hd + 4 * v]);
+                    acc[q] = fmaf(wv[i].x, sv.x, acc[q]); acc[q] = fmaf(wv[i].y, sv.y, acc[q]);
+                    acc[q] = fmaf(wv[i].z, sv.z, acc[q]); acc[q] = fmaf(wv[i].w, sv.w, acc[q]);
+                }
+            }
         }
 #pragma unroll
         for (int q = 0; q < kRoRows; ++q) {

@@ -32,10 +32,10 @@ enum Phase { PH_ENC_RPN = 0, PH_GEMM_RPN, PH_RO_RPN, PH_ENC_BOX, PH_GEMM_FC6, PH
 constexpr int kMaxTimed = 256;
 struct PhaseEvents { cudaEvent_t start[kMaxTimed], stop[kMaxTimed]; int created = 0, used = 0; };
 PhaseEvents g_ph[PH_COUNT];
-bool g_profile = false;
+unsigned g_profile = 0;          // bit ph: phase ph is timed
 
 void phase_begin(int ph, cudaStream_t st) {
-    if (!g_profile) return;
+    if (!((g_profile >> ph) & 1u)) return;
     PhaseEvents& e = g_ph[ph];
     if (e.used >= kMaxTimed) return;
     if (e.used >= e.created) {
@@ -45,7 +45,7 @@ void phase_begin(int ph, cudaStream_t st) {
     cudaEventRecord(e.start[e.used], st);
 }
 void phase_end(int ph, cudaStream_t st) {
-    if (!g_profile) return;
+    if (!((g_profile >> ph) & 1u)) return;
     PhaseEvents& e = g_ph[ph];
     if (e.used >= kMaxTimed || e.used >= e.created) return;
     cudaEventRecord(e.stop[e.used], st);
@@ -230,42 +230,37 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
     } else {
         p.slot_b = static_cast<int>(align_up(static_cast<size_t>(tc.n_mma / tc.cg) * 128, 1024)) * (p.dual ? 2 : 1);
     }
-    // The weight ring (16 KB stages) and the spike-tile ring share 176 KB.  Default: 6 weight stages + 80 KB of
-    // spike tiles.  A conv spike tile (one 64-channel block of the halo'd region, read by 9 taps) can be large:
-    // keep two of them in flight when possible (producers refill one while the MMAs read the other) by
-    // borrowing weight stages, down to 3.
-    const int ring_total = kStagesA * kTileBytesA + kRingBytesB;
-    p.stages_a = kStagesA;
-    p.stages_b = kRingBytesB / p.slot_b;
-    if (p.stages_b > kMaxStagesB) p.stages_b = kMaxStagesB;
-    if (!p.conv) {
-        // fc: one spike tile per k-block, handed producer -> relay -> MMA -> commit across the CTA pair; that chain
-        // is a few thousand cycles, so the spike ring wants depth more than the weight ring does (4 stages cover
-        // the TMA latency at one 16 KB tile per ~480 cycles)
-        // (measured: 4 weight stages + 7 spike stages beat 6 + 5 with 1-2 pieces per weight; with 3 pieces the
-        // weight ring is the one that must stay deep)
-        const int a_min = p.nsplit >= 3 ? kStagesA : 4;
-        int sb = (ring_total - a_min * kTileBytesA) / p.slot_b;
-        if (sb > kMaxStagesB) sb = kMaxStagesB;
-        if (sb > p.stages_b) {
-            p.stages_b = sb;
-            p.stages_a = (ring_total - sb * p.slot_b) / kTileBytesA;
-            if (p.stages_a > kStagesA) p.stages_a = kStagesA;
-        }
-    }
-    if (p.stages_b < 2) {
-        p.stages_b = (ring_total - 3 * kTileBytesA) / p.slot_b >= 2 ? 2 : 1;
+    // The weight ring (16 KB stages) and the spike-tile ring share 193 KB.
+    const int ring_total = kRingBytesAB;
+    if (p.conv) {
+        // A conv spike tile (one 64-channel block of the halo'd region, read by 9 taps) is large: two of them in
+        // flight (producers refill one while the MMAs read the other), the rest is weight stages -- the conv's MMA
+        // thread waits mostly for weight tiles (r01ad role counters: 16 % of its time with 6 stages)
+        p.stages_b = 2 * p.slot_b + 3 * kTileBytesA <= ring_total ? 2 : 1;
+        if (p.slot_b <= 16 * 1024 && 3 * p.slot_b + 6 * kTileBytesA <= ring_total) p.stages_b = 3;
         p.stages_a = (ring_total - p.stages_b * p.slot_b) / kTileBytesA;
-        if (p.stages_a > kStagesA) p.stages_a = kStagesA;
-        if (p.stages_a < 2) return fail(SNN_E_ARG, "spike tile of %d bytes does not fit shared memory", p.slot_b);
+    } else {
+        // fc: one spike tile per k-block, handed producer -> relay -> MMA -> commit across the CTA pair; that chain
+        // is a few thousand cycles, so the spike ring wants depth more than the weight ring does (measured r01ad,
+        // dual tiles of 22 KB, 2 pieces: 5 weight + 5 spike stages 0.632 ms, 6 + 4 0.666, 4 + 5 0.645, 3 + 6 0.700);
+        // with 3 pieces per weight the weight ring is the one that must stay deep
+        const int a_min = p.nsplit >= 3 ? 6 : 4;
+        p.stages_b = (ring_total - a_min * kTileBytesA) / p.slot_b;
+        if (p.stages_b > kMaxStagesB) p.stages_b = kMaxStagesB;
+        if (p.stages_b < 1) p.stages_b = 1;
+        p.stages_a = (ring_total - p.stages_b * p.slot_b) / kTileBytesA;
     }
+    if (p.stages_a > kStagesA) p.stages_a = kStagesA;
+    if (p.stages_a < 2 || p.stages_b < 1)
+        return fail(SNN_E_ARG, "spike tile of %d bytes does not fit shared memory", p.slot_b);
     if (const char* e = getenv("SNN_DBG_SWIZZLE")) {       // "shift,sbo,boff" -- scratch/swizzle_experiment.py only
         int a = 0, b = 0, c = 0;
         if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && b >= 1024) {
             p.dbg_shift = a; p.dbg_sbo = b; p.dbg_boff = c;
             p.slot_b = static_cast<int>(align_up(static_cast<size_t>(tc.n_mma / tc.cg + 7) / 8 * b + 2048, 1024));
-            p.stages_b = kRingBytesB / p.slot_b;
+            p.stages_b = (ring_total - 4 * kTileBytesA) / p.slot_b;
             if (p.stages_b > kMaxStagesB) p.stages_b = kMaxStagesB;
+            p.stages_a = 4;
         }
     }
     p.slot_w = static_cast<int>(align_up(static_cast<size_t>(p.conv ? p.hrows * 10 : tc.Jh * (p.dual ? 2 : 1)) * 64 * p.in_wb, 128));
@@ -846,7 +841,7 @@ int snn_rpn_decode_selected(const void* const* logits, const void* const* deltas
 }
 
 void snn_profile_enable(int on) {
-    g_profile = on != 0;
+    g_profile = on == 1 ? 0xFFFFFFFFu : on <= 0 ? 0u : (static_cast<unsigned>(on) >> 1);
     for (int k = 0; k < PH_COUNT; ++k) g_ph[k].used = 0;
 }
 
@@ -870,8 +865,10 @@ int snn_profile_read(float* ms_out, int* counts_out) {
 int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_words, snn_stream_t stream) {
     if (!x || !z_words || R < 1 || K % 16 != 0 || T_live < 1 || T_live > 32)
         return fail(SNN_E_ARG, "encode_rows: bad argument");
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    DeviceInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    const int sms = di.sms;
     launch_encode_rows(x, static_cast<size_t>(R) * K, T_live, word_bytes(T_live), reinterpret_cast<uint8_t*>(z_words), sms,
                        (cudaStream_t)stream);
     CUDA_TRY(cudaGetLastError());

@@ -43,11 +43,11 @@
 namespace snn {
 
 constexpr int kMaxLevels = 8;
-constexpr int kStagesA = 6;                 // weight ring: up to 6 stages of 16 KB (p.stages_a; fewer when one spike tile needs > 80 KB)
+constexpr int kStagesA = 8;                 // weight ring: up to 8 stages of 16 KB (p.stages_a)
 constexpr int kMaxStagesB = 8;              // ring of p.stages_b slots of p.slot_b bytes; weight + spike rings share 176 KB
 constexpr int kMaxStagesW = 8;              // ring of p.stages_w slots of p.slot_w bytes, 16 KB in total
 constexpr int kTileBytesA = 128 * 128;      // 128 rows x 64 16-bit
-constexpr int kRingBytesB = 97 * 1024;          // weight + spike rings share 193 KB; the whole CTA uses all 227 KB
+constexpr int kRingBytesAB = 193 * 1024;        // the weight ring (stages_a x 16 KB) and the spike-tile ring share it; the CTA uses all 227 KB
 constexpr int kRingBytesW = 16 * 1024;
 constexpr int kBarBytes = 512;
 constexpr int kEpiGroups = 1;               // LIF epilogue warp groups (4 warps each): warps 4-7 (+ 16-19)
@@ -59,7 +59,7 @@ constexpr int kRoMaxOut = 16;               // fused readout: objectness + box d
 constexpr int kRoWStride = 132;             // floats per readout-weight row in smem (128 + pad, 16-B aligned)
 constexpr int kRoSmemBytes = kRoMaxOut * kRoWStride * 4 + kEpiGroups * 2 * 8 * kRoWStride * 4;   // weights + per epilogue group 2 x [8 px][128 ch] sums
 constexpr size_t kGemmSmemBytes =
-    1024 /*align slack*/ + kStagesA * kTileBytesA + kRingBytesB + kRingBytesW + kBarBytes + kRoSmemBytes;
+    1024 /*align slack*/ + kRingBytesAB + kRingBytesW + kBarBytes + kRoSmemBytes;
 
 struct LevelDesc {
     int H, W, tiles_w, tiles_h;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
     uint8_t* a_ring = smem;
     const int stages_a = p.stages_a;
     uint8_t* b_ring = smem + stages_a * kTileBytesA;
-    uint8_t* w_ring = smem + kStagesA * kTileBytesA + kRingBytesB;
+    uint8_t* w_ring = smem + kRingBytesAB;
     uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + kRingBytesW);
     uint64_t* a_full = bars;                         // [kStagesA]   weight tile landed (TMA tx, leader CTA)
     uint64_t* a_empty = a_full + kStagesA;           // [kStagesA]   MMAs reading it retired
