@@ -164,9 +164,10 @@ void snn_set_cta_group(int cta_group);
  * wave of single tiles), 1 = never, 2 = as one wave of narrower dual tiles when such a shape exists. */
 void snn_set_fc_tiling(int dual, int max_units, int tail_split);
 /* Profiling only: the MMA-issuing thread of every CTA pair of the next spike-GEMM launches of `phase` (0 = RPN conv,
- * 1 = fc with K >= 4096 in dual tiles, 3 = the same in single tiles, 2 = other fc) on this thread writes 8 counters in SM clock cycles to device_counters
- * [pairs][8]: [0] whole role, [1] waiting for a free accumulator, [2] for this CTA's half of a spike tile, [3] for the
- * peer CTA's half, [4] for weight tiles, [5] number of tiles.  NULL switches it off. */
+ * 1 = fc with K >= 4096 in dual tiles, 3 = the same in single tiles, 2 = other fc) on this thread writes counters in SM clock cycles to device_counters
+ * [pairs][12]: [0] whole role, [1] waiting for a free accumulator, [2] for this CTA's half of a spike tile, [3] for the
+ * peer CTA's half, [4] for weight tiles, [5] number of tiles, [6] the LIF-epilogue role (one warp of the leader CTA),
+ * [7] of which waiting for a full accumulator, [8..11] spare.  NULL switches it off. */
 void snn_set_role_timers(unsigned long long* device_counters, int phase);
 
 /* Per-phase device timing for bench.py: when enabled, every forward records CUDA events on its stream

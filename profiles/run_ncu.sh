@@ -2,7 +2,7 @@
 # Run on the GPU box (via gpurun).  Usage: profiles/run_ncu.sh <tag> [mode]
 # Produces in gpurun_out/:
 #   <tag>_launches_<mode>.csv   every kernel launch of `bench.py --steps 2 --warmup 3` with its device time
-#   <tag>_gemm_<mode>.ncu-rep   --set full (+source) of the three spike GEMM launches of one step
+#   <tag>_gemm_<mode>.ncu-rep   --set full (+source) of the four spike GEMM launches of one step (conv, fc6 dual tiles, fc6 tail wave, fc7)
 #   <tag>_aux_<mode>.ncu-rep    --set full of the encoder / readout / LUT launches of one step
 # Summaries for profiles/ are produced here afterwards with profiles/summarise_ncu.py.
 TAG=${1:-r01}

@@ -18,14 +18,14 @@ box = FastRCNNPredictorSNNFull(12544, 1024, 9, 12, mode=mode).to(dev); box.recor
 for _ in range(3):
     rpn(feats); box(rois)
 torch.cuda.synchronize()
-buf = torch.zeros(74, 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(74, 12, dtype=torch.int64, device=dev)
 lib.snn_set_role_timers(buf.data_ptr(), phase)
 rpn(feats); box(rois)
 torch.cuda.synchronize()
 lib.snn_set_role_timers(None, -1)
 b = buf.cpu().double()
 tot = b[:, 0]
-names = ["total", "acc_empty", "b_ready(local)", "b_peer", "a_full(weights)", "tiles"]
+names = ["total", "acc_empty", "b_ready(local)", "b_peer", "a_full(weights)", "tiles", "epilogue role", "epi wait acc_full"]
 print(f"phase {phase} mode {mode}: pairs with work {(tot > 0).sum().item()}")
 for k, n in enumerate(names):
     col = b[:, k][tot > 0]

@@ -100,7 +100,8 @@ struct GemmLifParams {
     int dump_rows;
     // profiling only (nullable): per CTA pair 8 counters of the MMA-issuing thread, in SM clock cycles:
     // [0] whole role, [1] waiting for a free accumulator, [2] for this CTA's spike-tile half, [3] for the peer's
-    // half, [4] for weight tiles, [5] tiles
+    // half, [4] for weight tiles, [5] tiles; [6] the epilogue role (warp 4 of the leader CTA), [7] of which waiting
+    // for a full accumulator
     unsigned long long* role_cycles;
     int dbg_shift, dbg_sbo, dbg_boff;   // swizzle experiment (scratch/swizzle_experiment.py, fc only): row shift, group stride, base-offset field
     // fused leaky-integrator readout (conv, cta_group 2, m_total == 256): mem_{T-1} = W . sum_t kappa_{T-1-t} spk_t
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 }
             }
             if (timed) {
-                unsigned long long* out = p.role_cycles + static_cast<size_t>(group) * 8;
+                unsigned long long* out = p.role_cycles + static_cast<size_t>(group) * 12;
                 out[0] = static_cast<unsigned long long>(clock64() - c_begin);
                 out[1] = static_cast<unsigned long long>(c_acc); out[2] = static_cast<unsigned long long>(c_b);
                 out[3] = static_cast<unsigned long long>(c_peer); out[4] = static_cast<unsigned long long>(c_a);
@@ -521,6 +522,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         float* ro_sg = ro_s + eg * (2 * 8 * kRoWStride);
         uint32_t chunk_ctr = 0;
         uint32_t it = 0;
+        const bool e_timed = p.role_cycles != nullptr && rank == 0 && warp == 4 && lane == 0;
+        uint32_t e_wait = 0, e_t0 = 0;                 // 32-bit cycle counters: the role is short of registers
+        const uint32_t e_begin = e_timed ? static_cast<uint32_t>(clock()) : 0u;
         for (int tile = group; tile < p.total_tiles; tile += n_groups, ++it) {
             const int ut = tile / p.m_tiles, mt = tile - ut * p.m_tiles;
             const int c = mt * 128 * kCG + static_cast<int>(rank) * 128 + te;
@@ -536,7 +540,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             const float wscale = __ldg(&p.w_scale[c]);
             for (int bi = 0; bi < (kDual ? 2 : 1); ++bi) {      // dual: both buffers belong to this tile
             const uint32_t buf = kDual ? static_cast<uint32_t>(bi) : (it & 1u);
+            if (e_timed) e_t0 = static_cast<uint32_t>(clock());
             mbar_wait(&acc_full[buf], kDual ? (it & 1u) : ((it >> 1) & 1u));
+            if (e_timed) e_wait += static_cast<uint32_t>(clock()) - e_t0;
             tcgen05_fence_after();
             const uint32_t acc = tmem_base + lane_addr + buf * 256u;
             // first unit of CTA half `sub` of this accumulator (fc)
@@ -558,7 +564,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                     const uint32_t col_step = kConv ? 8u : static_cast<uint32_t>(p.Jh);
                     // fc: the loads of G steps are issued before one wait (the fc epilogue of a dual tile is not hidden
                     // behind the next tile's main loop)
-                    constexpr int G = kConv ? 1 : 16 / CW;
+                    constexpr int G = kConv ? (CW == 8 ? 2 : 4) : 16 / CW;
                     for (int tl0 = 0; tl0 < p.T_live; tl0 += G) {
                         float cu[G][CW];
 #pragma unroll
@@ -636,20 +642,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                         if (fused) {
                             float* S = ro_sg + (chunk_ctr & 1u) * (8 * kRoWStride);    // [CW pixels][128 channels + pad]
                             ++chunk_ctr;
+                            {   // explicit shared-space accesses (the generic-pointer form compiled to LD.E / ST.E)
+                                const uint32_t s_dst = smem_u32(S) + static_cast<uint32_t>(te) * 4u;
 #pragma unroll
-                            for (int u = 0; u < CW; ++u) S[u * kRoWStride + te] = sk[u];
+                                for (int u = 0; u < CW; ++u)
+                                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_dst + static_cast<uint32_t>(u * kRoWStride) * 4u), "f"(sk[u]) : "memory");
+                            }
                             asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
                             const int u = te % CW, og = te / CW;            // thread = (pixel u, output og)
                             if (og < kRoMaxOut) {
-                                const float4* s4 = reinterpret_cast<const float4*>(&S[u * kRoWStride]);
-                                const float4* w4 = reinterpret_cast<const float4*>(&ro_w[og * kRoWStride]);
-                                float a = 0.f;
+                                const uint32_t s_a = smem_u32(S) + static_cast<uint32_t>(u * kRoWStride) * 4u;
+                                const uint32_t w_a = smem_u32(ro_w) + static_cast<uint32_t>(og * kRoWStride) * 4u;
+                                // four independent chains (one chain of 128 dependent FMAs was ~500 cycles of latency
+                                // per chunk, r01aj: the readout is 42 % of the epilogue role)
+                                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
                                 for (int cc = 0; cc < 32; ++cc) {
-                                    const float4 sv = s4[cc], wv = w4[cc];
-                                    a = fmaf(wv.x, sv.x, a); a = fmaf(wv.y, sv.y, a);
-                                    a = fmaf(wv.z, sv.z, a); a = fmaf(wv.w, sv.w, a);
+                                    const uint4 sv = lds_v4(s_a + 16u * cc), wv = lds_v4(w_a + 16u * cc);
+                                    a0 = fmaf(__uint_as_float(wv.x), __uint_as_float(sv.x), a0);
+                                    a1 = fmaf(__uint_as_float(wv.y), __uint_as_float(sv.y), a1);
+                                    a2 = fmaf(__uint_as_float(wv.z), __uint_as_float(sv.z), a2);
+                                    a3 = fmaf(__uint_as_float(wv.w), __uint_as_float(sv.w), a3);
                                 }
+                                const float a = (a0 + a1) + (a2 + a3);
                                 if (row_ok && u < lim && og < n_out) {
                                     const LevelDesc& L = p.lv[lvl];
                                     const size_t hw = static_cast<size_t>(H) * W, pix = static_cast<size_t>(hh) * W + ww + u;
@@ -674,6 +689,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 else mbar_arrive_cluster(&acc_empty[buf], 0);
             }
             }   // bi
+        }
+        if (e_timed) {      // [6] the epilogue role of warp 4, [7] of which waiting for a full accumulator
+            p.role_cycles[static_cast<size_t>(group) * 12 + 6] = static_cast<uint32_t>(clock()) - e_begin;
+            p.role_cycles[static_cast<size_t>(group) * 12 + 7] = e_wait;
         }
     }
 
