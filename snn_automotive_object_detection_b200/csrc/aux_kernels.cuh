@@ -299,6 +299,20 @@ __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restric
 // lut[b][256] (b = byte position in the word), built on the host in float64.
 constexpr int kMaxTrainBytes = 4;
 
+// kappa[t] = 0.9^{T-t} - 0.8^{T-t} in float64 (computed on the host), passed by value; each block builds its own
+// byte-indexed tables from it: lut[b][v] = float( sum_{bit j of v} kappa[8b + j] )  (summed in float64)
+struct KappaTable { double k[32]; };
+__device__ __forceinline__ void build_kappa_lut(const KappaTable& kt, int nbytes, float* s_lut) {
+    for (int i = threadIdx.x; i < nbytes * 256; i += blockDim.x) {
+        const int b = i >> 8, v = i & 255;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if ((v >> j) & 1) acc += kt.k[8 * b + j];
+        s_lut[i] = static_cast<float>(acc);
+    }
+}
+
 template <typename TrainT>
 __device__ __forceinline__ float lut_weight(const float* lut, TrainT tr) {
     float s = lut[tr & 0xFFu];
@@ -316,7 +330,7 @@ template <typename TrainT>
 __global__ void __launch_bounds__(kRpnRoPx) readout_rpn_kernel(const TrainT* __restrict__ trains, int C, int HW,
                                                                const float* __restrict__ w_cls,
                                                                const float* __restrict__ w_bbox, int A,
-                                                               const float* __restrict__ lut_g,
+                                                               const __grid_constant__ KappaTable kt,
                                                                float* __restrict__ logits, float* __restrict__ bbox,
                                                                unsigned long long* __restrict__ counts) {
     extern __shared__ uint8_t s_raw[];
@@ -333,7 +347,7 @@ __global__ void __launch_bounds__(kRpnRoPx) readout_rpn_kernel(const TrainT* __r
     if (threadIdx.x == 0) s_cnt = 0;
     for (int i = threadIdx.x; i < n_out * C; i += blockDim.x)
         s_w[i] = (i < A * C) ? w_cls[i] : w_bbox[i - A * C];
-    for (int i = threadIdx.x; i < 256 * static_cast<int>(sizeof(TrainT)); i += blockDim.x) s_lut[i] = lut_g[i];
+    build_kappa_lut(kt, static_cast<int>(sizeof(TrainT)), s_lut);
     // coalesced tile load: npx rows of C*sizeof(TrainT) bytes are contiguous in global memory
     const uint32_t* src = reinterpret_cast<const uint32_t*>(trains + (static_cast<size_t>(n) * HW + p0) * C);
     const int wpr = row_words - 1;
@@ -394,7 +408,7 @@ __global__ void __launch_bounds__(256) readout_rows_kernel(const TrainT* __restr
                                                            const TrainT* __restrict__ trains_b, int R, int Hd,
                                                            const float* __restrict__ w_cls, int n_cls,
                                                            const float* __restrict__ w_box, int n_box,
-                                                           const float* __restrict__ lut_g,
+                                                           const __grid_constant__ KappaTable kt,
                                                            float* __restrict__ out_cls, float* __restrict__ out_box,
                                                            unsigned int* __restrict__ counts) {
     __shared__ float s_lut[256 * sizeof(TrainT)];
@@ -403,7 +417,7 @@ __global__ void __launch_bounds__(256) readout_rows_kernel(const TrainT* __restr
     constexpr int kMaxVec = 8;                                       // vectors per lane and pass (Hd <= 8 * 32 * kWpv per pass)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = blockIdx.x * kRoRows;
-    for (int i = threadIdx.x; i < 256 * static_cast<int>(sizeof(TrainT)); i += blockDim.x) s_lut[i] = lut_g[i];
+    build_kappa_lut(kt, static_cast<int>(sizeof(TrainT)), s_lut);
     __syncthreads();
     {   // warp q stages row r0 + q (8 warps <-> 8 rows) and counts its spikes
         const int r = r0 + warp;

@@ -41,6 +41,20 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// The same with the default (CTA-scope) release.  Used by the relay lane that forwards "this CTA's half of a spike
+// tile is written": the tile data itself was made visible to the tensor core (async proxy) by the producers'
+// fence.proxy.async before they arrived on the local barrier the relay waited on, so the remote arrive only has to
+// carry the signal -- the cluster-scope release costs about a microsecond per stage (SNN_RELAY_CLUSTER_RELEASE
+// restores it for A/B measurements).
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+#ifdef SNN_RELAY_CLUSTER_RELEASE
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#else
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#endif
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

@@ -296,20 +296,11 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
     return SNN_OK;
 }
 
-// LUT of kappa-weighted spike trains: lut[b][v] = sum_{bit j of v} kappa_{T-1-(8b+j)}, kappa_n = .9^{n+1} - .8^{n+1}
-__global__ void build_lut_kernel(int T, int nbytes, float* lut) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nbytes * 256) return;
-    const int b = i >> 8, v = i & 255;
-    double s = 0.0;
-    for (int j = 0; j < 8; ++j) {
-        const int t = 8 * b + j;
-        if (((v >> j) & 1) && t < T) {
-            const int n = T - 1 - t;
-            s += pow(0.9, n + 1) - pow(0.8, n + 1);
-        }
-    }
-    lut[i] = static_cast<float>(s);
+// kappa[t] = weight of a spike at step t in the last leaky-integrator membrane: 0.9^{T-t} - 0.8^{T-t}
+KappaTable kappa_table(int T) {
+    KappaTable kt;
+    for (int t = 0; t < 32; ++t) kt.k[t] = (t < T) ? pow(0.9, T - t) - pow(0.8, T - t) : 0.0;
+    return kt;
 }
 
 int word_bytes(int nbits) { return nbits <= 8 ? 1 : nbits <= 16 ? 2 : 4; }
@@ -460,7 +451,7 @@ int fc_layer(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, 
 
 template <typename T>
 cudaError_t launch_readout_rpn(const void* trains, int C, int HW, int N, const float* wc, const float* wb, int A,
-                               const float* lut, float* lo, float* bo, unsigned long long* counts, cudaStream_t st) {
+                               const KappaTable& lut, float* lo, float* bo, unsigned long long* counts, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(5 * A) * C * 4 + 256 * sizeof(T) * 4 +
                         static_cast<size_t>(kRpnRoPx) * ((C * sizeof(T)) / 4 + 1) * 4;
     auto kern = readout_rpn_kernel<T>;
@@ -473,7 +464,7 @@ cudaError_t launch_readout_rpn(const void* trains, int C, int HW, int N, const f
 
 template <typename T>
 cudaError_t launch_readout_rows(const void* tr7, const void* tr6, int R, int Hd, const float* wc, int nc,
-                                const float* wb, int nb, const float* lut, float* oc, float* ob, unsigned int* counts,
+                                const float* wb, int nb, const KappaTable& lut, float* oc, float* ob, unsigned int* counts,
                                 cudaStream_t st) {
     const size_t smem = static_cast<size_t>(kRoRows) * Hd * 4;
     auto kern = readout_rows_kernel<T>;
@@ -561,16 +552,12 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
     const int tb = snn_train_word_bytes(T);
     const int ns = nsplit_of(mode);
     const int T_live = T - 1;
-    float* lut = reinterpret_cast<float*>(wsp + ws.lut_off);
+    const KappaTable lut = kappa_table(T);
 
     // The LI readout (and the spike counts) are fused into the GEMM epilogue when a CTA pair covers all
     // output channels (cta_group 2, C_in == 256) and the 5A outputs fit one pass; otherwise a separate
     // readout kernel consumes the spike trains (and needs the kappa lookup table).
     const bool fused = T_live > 0 && tc.cg == 2 && C_in == 256 && 5 * A <= kRoMaxOut;
-    if (!fused) {
-        build_lut_kernel<<<(tb * 256 + 255) / 256, 256, 0, st>>>(T, tb, lut);
-        CUDA_TRY(cudaGetLastError()); ++g_launches;
-    }
     void* trains[kMaxLevels];
     for (int l = 0; l < n_levels; ++l) {
         trains[l] = (spike_trains_out && spike_trains_out[l]) ? spike_trains_out[l] : (wsp + ws.tr_off[l]);
@@ -720,15 +707,12 @@ static int box_head_forward_impl(const void* x, bool x_is_words, int R, int K, i
     uint8_t* wsp = reinterpret_cast<uint8_t*>(workspace);
     const int tb = snn_train_word_bytes(T);
     const int ns = nsplit_of(mode);
-    float* lut = reinterpret_cast<float*>(wsp + ws.lut_off);
+    const KappaTable lut = kappa_table(T);
     void* tr6 = spk6_trains ? spk6_trains : (wsp + ws.tr6_off);
     void* tr7 = spk7_trains ? spk7_trains : (wsp + ws.tr7_off);
     // x_is_words: the caller already holds the encoder's spike-train words (snn_roi_align_encode), [R][K] words of
     // word_bytes(T - 1) bytes; bits beyond the live steps are ignored by the producers
     const void* z = x_is_words ? x : static_cast<const void*>(wsp + ws.z_off);
-
-    build_lut_kernel<<<(tb * 256 + 255) / 256, 256, 0, st>>>(T, tb, lut);
-    CUDA_TRY(cudaGetLastError()); ++g_launches;
 
     // fc6 is live for steps 0..T-3 (its last two steps never reach the outputs); one more step when
     // the fc6 spike statistics are wanted.  fc7 is live for steps 1..T-2.

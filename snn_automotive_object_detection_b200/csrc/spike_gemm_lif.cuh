@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             uint32_t pb = 0;
             for (long long i = lane; i < total_kb; i += stages_b, pb ^= 1u) {
                 mbar_wait_parked(&b_ready[lane], pb);
-                mbar_arrive_cluster(&b_peer[lane], 0);
+                mbar_arrive_remote(&b_peer[lane], 0);
             }
         }
     } else if (warp == 3) {
