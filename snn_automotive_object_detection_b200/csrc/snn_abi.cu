@@ -317,7 +317,16 @@ void launch_encode_rows(const float* x, size_t total, int T_live, int wb, uint8_
     });
 }
 
-struct RpnWs { size_t z_off[kMaxLevels], tr_off[kMaxLevels], lut_off, total; };
+// More than kPassSteps live steps run as several launches over the time axis with the neuron state carried in HBM
+constexpr int kPassSteps = 16;
+// steps per pass: the time axis is cut evenly (23 live steps = 12 + 11, not 16 + 7 with nine all-zero rows per unit)
+int pass_steps(int T_live) {
+    if (T_live <= kPassSteps) return T_live;
+    const int n_pass = (T_live + kPassSteps - 1) / kPassSteps;
+    return (T_live + n_pass - 1) / n_pass;
+}
+
+struct RpnWs { size_t z_off[kMaxLevels], tr_off[kMaxLevels], st_off[kMaxLevels], lut_off, total; };
 
 int rpn_ws_layout(const int* H, const int* W, int L, int N, int C, int T, int mode, RpnWs& ws, TileCfg& tc) {
     if (L < 1 || L > kMaxLevels) return fail(SNN_E_ARG, "n_levels %d outside [1,%d]", L, kMaxLevels);
@@ -327,7 +336,7 @@ int rpn_ws_layout(const int* H, const int* W, int L, int N, int C, int T, int mo
     if (N < 1) return fail(SNN_E_ARG, "batch size %d < 1", N);
     const int T_live = T - 1;
     tc = TileCfg{};
-    if (T_live > 0 && !pick_tile(T_live, true, C, g_force_cg, tc)) return fail(SNN_E_ARG, "no tile shape for T=%d", T);
+    if (T_live > 0 && !pick_tile(pass_steps(T_live), true, C, g_force_cg, tc)) return fail(SNN_E_ARG, "no tile shape for T=%d", T);
     const int tb = snn_train_word_bytes(T);
     size_t off = 0;
     for (int l = 0; l < L; ++l) {
@@ -339,13 +348,17 @@ int rpn_ws_layout(const int* H, const int* W, int L, int N, int C, int T, int mo
         ws.tr_off[l] = off;
         off = align_up(off + static_cast<size_t>(N) * H[l] * W[l] * C * tb, 1024);
     }
+    for (int l = 0; l < L; ++l) {       // carried neuron state (v, i, kappa sum, train word), multi-pass only
+        ws.st_off[l] = off;
+        if (T_live > kPassSteps) off = align_up(off + static_cast<size_t>(N) * H[l] * W[l] * C * sizeof(float4), 1024);
+    }
     ws.lut_off = off;
     off += kMaxTrainBytes * 256 * sizeof(float);
     ws.total = align_up(off, 1024);
     return SNN_OK;
 }
 
-struct BoxWs { size_t z_off, tr6_off, tr7_off, lut_off, total; };
+struct BoxWs { size_t z_off, tr6_off, tr7_off, st_off, lut_off, total; };
 
 int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, TileCfg& t6, TileCfg& t7) {
     if (T < 3 || T > 32) return fail(SNN_E_ARG, "num_steps %d outside [3,32]", T);
@@ -355,15 +368,17 @@ int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, 
     if (nsplit_of(mode) == 0) return fail(SNN_E_ARG, "unknown mode %d", mode);
     // worst case over stats on/off so one workspace size serves both
     TileCfg a{}, b{};
-    if (!pick_tile(T - 1, false, Hd, g_force_cg, a) || !pick_tile(T - 2, false, Hd, g_force_cg, b))
+    if (!pick_tile(pass_steps(T - 1), false, Hd, g_force_cg, a) || !pick_tile(pass_steps(T - 2), false, Hd, g_force_cg, b))
         return fail(SNN_E_ARG, "no tile shape for T=%d", T);
     t6 = stats ? a : b;
-    if (!pick_tile(T - 2, false, Hd, g_force_cg, t7)) return fail(SNN_E_ARG, "no tile shape for T=%d", T);
+    if (!pick_tile(pass_steps(T - 2), false, Hd, g_force_cg, t7)) return fail(SNN_E_ARG, "no tile shape for T=%d", T);
     const int tb = snn_train_word_bytes(T);
     size_t off = 0;
     ws.z_off = off; off = align_up(off + static_cast<size_t>(R) * K * word_bytes(T - 1), 1024);   // encoder words
     ws.tr6_off = off; off = align_up(off + static_cast<size_t>(R) * Hd * tb, 1024);
     ws.tr7_off = off; off = align_up(off + static_cast<size_t>(R) * Hd * tb, 1024);
+    ws.st_off = off;                    // carried neuron state, multi-pass only (fc6's passes finish before fc7's start)
+    if (T - 1 > kPassSteps) off = align_up(off + static_cast<size_t>(R) * Hd * sizeof(float4), 1024);
     ws.lut_off = off; off += kMaxTrainBytes * 256 * sizeof(float);
     ws.total = align_up(off, 1024);
     return SNN_OK;
@@ -372,7 +387,7 @@ int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, 
 // one launch over the units [0, R) of z_words / trains; dump (debug) is [T_live][dump_rows][M] and already offset
 int fc_launch(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, int R, int K, int M, int T, int t0,
               int T_live, int mode, const void* w_prep, void* trains, float* dump, int dump_rows, const TileCfg& tc,
-              bool dual, cudaStream_t st) {
+              bool dual, float4* state, int state_load, int state_store, cudaStream_t st) {
     GemmLifParams p;
     memset(&p, 0, sizeof(p));
     const int nsplit = nsplit_of(mode);
@@ -401,6 +416,7 @@ int fc_launch(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0,
     }
     p.trains = trains;
     p.dump = dump; p.dump_rows = dump_rows;
+    p.state = state; p.state_load = state_load; p.state_store = state_store;
     return launch_gemm(p, tc, di, mode, st);
 }
 
@@ -410,7 +426,8 @@ int fc_launch(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0,
 // wave of dual tiles would be less than half full, its units are run as single tiles by a second launch (half the
 // time of a dual wave).
 int fc_layer(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, int R, int K, int M, int T, int t0,
-             int T_live, int mode, const void* w_prep, void* trains, float* dump, const TileCfg& tc, cudaStream_t st) {
+             int T_live, int mode, const void* w_prep, void* trains, float* dump, const TileCfg& tc, cudaStream_t st,
+             float4* state = nullptr, int state_load = 0, int state_store = 0) {
     const bool dual_ok = tc.cg == 2 && tc.T_box <= 16 && (tc.n_mma / 2) % 8 == 0;
     bool dual = dual_ok && g_fc_dual != 1 && (g_fc_dual == 2 || K / 64 >= 64);
     int R1 = R;                                   // units [0, R1) in the first launch
@@ -440,13 +457,32 @@ int fc_layer(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, 
         }
     }
     const size_t tb = snn_train_word_bytes(T);
-    int rc = fc_launch(di, z_words, in_wb, in_bit0, R1, K, M, T, t0, T_live, mode, w_prep, trains, dump, R, tc, dual, st);
+    int rc = fc_launch(di, z_words, in_wb, in_bit0, R1, K, M, T, t0, T_live, mode, w_prep, trains, dump, R, tc, dual,
+                       state, state_load, state_store, st);
     if (rc || R1 == R) return rc;
     rc = fc_launch(di, reinterpret_cast<const uint8_t*>(z_words) + static_cast<size_t>(R1) * K * in_wb, in_wb, in_bit0,
                    R - R1, K, M, T, t0, T_live, mode, w_prep,
                    reinterpret_cast<uint8_t*>(trains) + static_cast<size_t>(R1) * M * tb,
-                   dump ? dump + static_cast<size_t>(R1) * M : nullptr, R, tail, tail_dual, st);
+                   dump ? dump + static_cast<size_t>(R1) * M : nullptr, R, tail, tail_dual,
+                   state ? state + static_cast<size_t>(R1) * M : nullptr, state_load, state_store, st);
     return rc;
+}
+
+// The same over a long time axis: passes of <= kPassSteps live steps, the neuron state carried through `state`
+// ([R][M] float4, caller's workspace) between the launches; only the last pass drains the synapse and emits.
+int fc_layer_passes(const DeviceInfo& di, const void* z_words, int in_wb, int in_bit0, int R, int K, int M, int T, int t0,
+                    int T_live, int mode, const void* w_prep, void* trains, const TileCfg& tc, float4* state,
+                    cudaStream_t st) {
+    if (T_live <= kPassSteps)
+        return fc_layer(di, z_words, in_wb, in_bit0, R, K, M, T, t0, T_live, mode, w_prep, trains, nullptr, tc, st);
+    const int per = pass_steps(T_live);
+    for (int b = 0; b < T_live; b += per) {
+        const int n = T_live - b < per ? T_live - b : per;
+        const int rc = fc_layer(di, z_words, in_wb, in_bit0 + b, R, K, M, T, t0 + b, n, mode, w_prep, trains, nullptr, tc, st,
+                                state, b > 0 ? 1 : 0, b + n < T_live ? 1 : 0);
+        if (rc) return rc;
+    }
+    return SNN_OK;
 }
 
 template <typename T>
@@ -652,7 +688,23 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
         p.rows = 0; p.unit_tiles = tiles; p.train_bytes = tb;
         p.w_scale = scale_of(w_shared_prep, C_in, 9 * C_in, mode);
         phase_begin(PH_GEMM_RPN, st);
-        rc = launch_gemm(p, tc, di, mode, st);
+        if (T_live <= kPassSteps) {
+            rc = launch_gemm(p, tc, di, mode, st);
+        } else {
+            // long time axis: passes of <= 16 live steps, the neuron state carried through the workspace; only the
+            // last pass drains, emits the spike trains and runs the fused readout
+            const int fuse = p.fuse_readout;
+            for (int l = 0; l < n_levels; ++l) p.lv[l].state = reinterpret_cast<float4*>(wsp + ws.st_off[l]);
+            const int per = pass_steps(T_live);
+            for (int b = 0; b < T_live && rc == SNN_OK; b += per) {
+                const int n = T_live - b < per ? T_live - b : per;
+                const bool last = b + n >= T_live;
+                p.t0 = b; p.in_bit0 = b; p.T_live = n;
+                p.state_load = b > 0 ? 1 : 0; p.state_store = last ? 0 : 1;
+                p.fuse_readout = last ? fuse : 0;
+                rc = launch_gemm(p, tc, di, mode, st);
+            }
+        }
         phase_end(PH_GEMM_RPN, st);
         if (rc) return rc;
     } else {
@@ -726,12 +778,13 @@ static int box_head_forward_impl(const void* x, bool x_is_words, int R, int K, i
         CUDA_TRY(cudaGetLastError()); ++g_launches;
     }
     phase_begin(PH_GEMM_FC6, st);
-    rc = fc_layer(di, z, word_bytes(T - 1), 0, R, K, Hdim, T, 0, T_live6, mode, w6_prep, tr6, nullptr, t6, st);
+    float4* carried = reinterpret_cast<float4*>(wsp + ws.st_off);
+    rc = fc_layer_passes(di, z, word_bytes(T - 1), 0, R, K, Hdim, T, 0, T_live6, mode, w6_prep, tr6, t6, carried, st);
     phase_end(PH_GEMM_FC6, st);
     if (rc) return rc;
     phase_begin(PH_GEMM_FC7, st);
     // fc7 contracts lif6's spike-train words directly: its step t0 = 1 is bit 1 of the word
-    rc = fc_layer(di, tr6, tb, 1, R, Hdim, Hdim, T, 1, T_live7, mode, w7_prep, tr7, nullptr, t7, st);
+    rc = fc_layer_passes(di, tr6, tb, 1, R, Hdim, Hdim, T, 1, T_live7, mode, w7_prep, tr7, t7, carried, st);
     phase_end(PH_GEMM_FC7, st);
     if (rc) return rc;
     phase_begin(PH_RO_BOX, st);

@@ -69,6 +69,7 @@ struct LevelDesc {
     float* logits;            // fused readout: [N][A][H][W]   (zero-initialised; 2 CTAs add their channel halves)
     float* bbox;              // fused readout: [N][4A][H][W]
     unsigned long long* counts;   // nullable: [N] spikes per image of this level
+    float4* state;                // multi-pass only: [N][H][W][m_total] (v, i, kappa-weighted spike sum, train word bits)
 };
 
 struct GemmLifParams {
@@ -96,6 +97,12 @@ struct GemmLifParams {
     void* trains;             // fc: [rows][m_total]
     uint32_t spike_one;       // 1.0 as bf16 (0x3F80) or fp16 (0x3C00)
     const float* w_scale;     // [m_total] power of two each accumulator row is multiplied with (1 for bf16 pieces)
+    // More than 16 live steps do not fit one accumulator tile with a useful number of units: the time axis is then cut
+    // into passes of <= 16 steps, one launch each, and the neuron state (v, i, kappa-weighted spike sum, train word)
+    // is carried between the launches through `state` (fc: [rows][m_total]; conv: per level).  A pass with
+    // state_store set stops after its live steps and writes the state; only the last pass drains and emits.
+    int state_load, state_store;
+    float4* state;
     float* dump;              // debug (fc only): raw currents [T_live][dump_rows][m_total]
     int dump_rows;
     // profiling only (nullable): per CTA pair 8 counters of the MMA-issuing thread, in SM clock cycles:
@@ -558,6 +565,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                     uint32_t tr[CW];
 #pragma unroll
                     for (int u = 0; u < CW; ++u) { v[u] = 0.f; ii[u] = 0.f; tr[u] = 0u; sk[u] = 0.f; }
+                    // position of the chunk's units
+                    int hh = 0, ww = 0;
+                    bool row_ok;
+                    size_t r0;
+                    int lim;                                   // units u < lim are inside the image / row range
+                    if constexpr (kConv) {                     // a chunk lies inside one tile row (TWh == 8, CW <= 8)
+                        hh = h0 + sub * p.sub_dh + (j0 >> 3);
+                        ww = w0 + sub * p.sub_dw + (j0 & 7);
+                        row_ok = hh < H;
+                        lim = W - ww;
+                        r0 = (static_cast<size_t>(n) * H + hh) * W + ww;
+                    } else {
+                        const int rr = unit0 + sub * sub_units + j0;
+                        row_ok = true;
+                        lim = p.rows - rr;
+                        r0 = static_cast<size_t>(rr);
+                    }
+                    float4* state = nullptr;
+                    if (p.state_load | p.state_store) {
+                        if constexpr (kConv) state = p.lv[lvl].state; else state = p.state;
+                        state += r0 * p.m_total + c;
+                        if (p.state_load && row_ok) {
+#pragma unroll
+                            for (int u = 0; u < CW; ++u) {
+                                if (u >= lim) break;
+                                const float4 sv = state[static_cast<size_t>(u) * p.m_total];
+                                v[u] = sv.x; ii[u] = sv.y; sk[u] = sv.z; tr[u] = __float_as_uint(sv.w);
+                            }
+                        }
+                    }
                     // ---- steps that receive an input current (the accumulator columns of this unit chunk)
                     // accumulator column of (unit j, step t): fc t * Jh + j; conv (tile row, t, tile column)
                     uint32_t col = acc + static_cast<uint32_t>(sub * n_half + (kConv ? (j0 >> 3) * p.T_box * 8 + (j0 & 7) : j0));
@@ -596,6 +633,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                             }
                         }
                     }
+                    if (p.state_store) {           // not the last pass over the time axis: carry the state, emit nothing
+                        if (row_ok) {
+#pragma unroll
+                            for (int u = 0; u < CW; ++u) {
+                                if (u >= lim) break;
+                                state[static_cast<size_t>(u) * p.m_total] = make_float4(v[u], ii[u], sk[u], __uint_as_float(tr[u]));
+                            }
+                        }
+                        continue;
+                    }
                     // ---- remaining steps: the synapse only drains (no new input reaches an output later)
                     for (int t = p.t0 + p.T_live; t < p.T_total; ++t) {
                         const float kap = p.kappa[t];
@@ -605,22 +652,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                             if (lif_update(v[u], ii[u], 0.0f)) { tr[u] |= bit; sk[u] = __fadd_rn(sk[u], kap); }
                     }
                     // ---- emit the spike-train words of the chunk
-                    int hh = 0, ww = 0;
-                    bool row_ok;
-                    size_t r0;
-                    int lim;                                   // units u < lim are inside the image / row range
-                    if constexpr (kConv) {                     // a chunk lies inside one tile row (TWh == 8, CW <= 8)
-                        hh = h0 + sub * p.sub_dh + (j0 >> 3);
-                        ww = w0 + sub * p.sub_dw + (j0 & 7);
-                        row_ok = hh < H;
-                        lim = W - ww;
-                        r0 = (static_cast<size_t>(n) * H + hh) * W + ww;
-                    } else {
-                        const int rr = unit0 + sub * sub_units + j0;
-                        row_ok = true;
-                        lim = p.rows - rr;
-                        r0 = static_cast<size_t>(rr);
-                    }
                     if (row_ok) {
 #pragma unroll
                         for (int u = 0; u < CW; ++u)
