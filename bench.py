@@ -284,6 +284,25 @@ def run_ours(args):
     phases = _lib.profile_read()
     _lib.profile_enable(False)
     phases["rpn_conv_lif_gemm"] = live["rpn_conv_lif_gemm"]      # the roofline uses the launch times of the timed region
+    # one more (untimed) step with the library's in-kernel counters on the conv launch: SM cycles and globaltimer
+    # nanoseconds between kernel entry and exit of every CTA pair -> the SM clock the kernel really ran at
+    # (nvidia-smi reports the 1965 MHz application clock while the tensor pipe is power-managed to ~1.82 GHz)
+    in_kernel = None
+    try:
+        n_pairs = torch.cuda.get_device_properties(dev).multi_processor_count // 2
+        ctr = torch.zeros(n_pairs, 12, dtype=torch.int64, device=dev)
+        lib.snn_set_role_timers(ctr.data_ptr(), 0)
+        rpn(d_feats)
+        torch.cuda.synchronize(dev)
+        lib.snn_set_role_timers(None, -1)
+        c = ctr.cpu().double()
+        busy = c[:, 9] > 0
+        if busy.any() and (c[busy, 10] > 0).all():
+            in_kernel = {"cycles_entry_to_exit": c[busy, 9].mean().item(), "ns_entry_to_exit": c[busy, 10].mean().item(),
+                         "effective_sm_mhz": (c[busy, 9] / c[busy, 10]).mean().item() * 1e3,
+                         "mma_role_cycles": c[busy, 0].mean().item(), "tiles_per_cta_pair": c[busy, 5].mean().item()}
+    except Exception as e:                     # profiling aid only
+        in_kernel = {"error": str(e)}
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     per_rank_ms = [ms_total / args.steps]
     if world > 1:
@@ -385,6 +404,11 @@ def run_ours(args):
                 "clock_ceiling_tflops": (sm_count * 8192 * (clocks["sm_mhz"] or 0) * 1e6 / 1e12) if clocks.get("sm_mhz") else None}
         if roof["clock_ceiling_tflops"]:
             roof["frac_of_clock_ceiling"] = ach / roof["clock_ceiling_tflops"]
+        if in_kernel and in_kernel.get("effective_sm_mhz"):
+            roof["in_kernel"] = in_kernel
+            eff_ceiling = sm_count * 8192 * in_kernel["effective_sm_mhz"] * 1e6 / 1e12
+            roof["effective_clock_ceiling_tflops"] = eff_ceiling
+            roof["frac_of_effective_clock_ceiling"] = ach / eff_ceiling
     phase_ms = {k: (v[0] / v[1] if v[1] else None) for k, v in phases.items()}
     fc6_flops = 2.0 * B * ROIS * KBOX * HID * (args.t_det - 1) * pieces      # + the step only lif6's spike count needs
     fc7_flops = 2.0 * B * ROIS * HID * HID * (args.t_det - 2) * pieces

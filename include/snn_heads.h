@@ -167,7 +167,8 @@ void snn_set_fc_tiling(int dual, int max_units, int tail_split);
  * 1 = fc with K >= 4096 in dual tiles, 3 = the same in single tiles, 2 = other fc) on this thread writes counters in SM clock cycles to device_counters
  * [pairs][12]: [0] whole role, [1] waiting for a free accumulator, [2] for this CTA's half of a spike tile, [3] for the
  * peer CTA's half, [4] for weight tiles, [5] number of tiles, [6] the LIF-epilogue role (one warp of the leader CTA),
- * [7] of which waiting for a full accumulator, [8..11] spare.  NULL switches it off. */
+ * [7] of which waiting for a full accumulator, [8] kernel entry to the MMA role's start, [9] kernel entry to exit of the
+ * leader CTA, [10] the same in nanoseconds (globaltimer).  NULL switches it off. */
 void snn_set_role_timers(unsigned long long* device_counters, int phase);
 
 /* Per-phase device timing for bench.py: when enabled, every forward records CUDA events on its stream

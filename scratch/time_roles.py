@@ -25,9 +25,12 @@ torch.cuda.synchronize()
 lib.snn_set_role_timers(None, -1)
 b = buf.cpu().double()
 tot = b[:, 0]
-names = ["total", "acc_empty", "b_ready(local)", "b_peer", "a_full(weights)", "tiles", "epilogue role", "epi wait acc_full"]
+names = ["total", "acc_empty", "b_ready(local)", "b_peer", "a_full(weights)", "tiles", "epilogue role", "epi wait acc_full", "entry->first tile", "entry->exit", "entry->exit (ns)"]
 print(f"phase {phase} mode {mode}: pairs with work {(tot > 0).sum().item()}")
 for k, n in enumerate(names):
     col = b[:, k][tot > 0]
     frac = (col / tot[tot > 0]).mean().item() if k not in (0, 5) else float("nan")
     print(f"  {n:18s} mean {col.mean().item():12.0f}  min {col.min().item():12.0f}  max {col.max().item():12.0f}  mean share {frac:.3f}")
+
+eff = (b[:, 9][tot > 0] / b[:, 10][tot > 0].clamp(min=1)).mean().item() * 1e3
+print(f"  effective SM clock inside the kernel: {eff:.0f} MHz (cycles / globaltimer ns)")

@@ -156,6 +156,9 @@ __device__ __forceinline__ TilePos decode_tile(const GemmLifParams& p, int ut) {
 template <int kCG, int CW, bool kConv, bool kDual = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const __grid_constant__ GemmLifParams p) {
     extern __shared__ uint8_t smem_raw[];
+    const long long k_begin = clock64();          // profiling only (role_cycles)
+    unsigned long long k_begin_ns = 0;
+    if (p.role_cycles != nullptr && threadIdx.x == 64) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_begin_ns));
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
     const int stages_a = p.stages_a;
@@ -307,6 +310,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 out[1] = static_cast<unsigned long long>(c_acc); out[2] = static_cast<unsigned long long>(c_b);
                 out[3] = static_cast<unsigned long long>(c_peer); out[4] = static_cast<unsigned long long>(c_a);
                 out[5] = it;
+                out[8] = static_cast<unsigned long long>(c_begin - k_begin);      // kernel entry -> first tile
             }
         } else if (kCG == 2 && rank == 1 && lane < stages_b) {
             // relay (one lane per spike-tile ring stage): tell the leader's MMA thread that this CTA's half
@@ -730,6 +734,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
     tcgen05_fence_before();
     if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 2) tmem_dealloc<kCG>(tmem_base, 512);
+    if (p.role_cycles != nullptr && rank == 0 && threadIdx.x == 64) {             // kernel entry -> exit of the leader CTA:
+        unsigned long long k_end_ns;                                               // [9] in SM cycles, [10] in nanoseconds
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_end_ns));
+        p.role_cycles[static_cast<size_t>(group) * 12 + 9] = static_cast<unsigned long long>(clock64() - k_begin);
+        p.role_cycles[static_cast<size_t>(group) * 12 + 10] = k_end_ns - k_begin_ns;
+    }
 }
 
 }  // namespace snn
