@@ -102,3 +102,25 @@ def test_encoder_comparator_table_against_the_oracle_encoder(lib):
         for n in range(1, 33):
             tab ^= np.where(x >= thr[n], dl[n], np.uint32(0))
         assert np.array_equal(sim, tab)
+
+
+def test_workspace_sizes_are_host_only_and_cover_the_carried_state(lib):
+    """The workspace queries run without a device.  Up to 17 steps a head needs its encoder words and spike trains;
+    beyond that the time axis runs in passes and the workspace also holds the carried neuron state (16 B per neuron)."""
+    H = (ctypes.c_int * 2)(24, 12)
+    W = (ctypes.c_int * 2)(48, 24)
+    neurons = 2 * (24 * 48 + 12 * 24) * 256
+    w8 = lib.snn_rpn_head_workspace_bytes(H, W, 2, 2, 256, 8, 3)
+    w17 = lib.snn_rpn_head_workspace_bytes(H, W, 2, 2, 256, 17, 3)
+    w18 = lib.snn_rpn_head_workspace_bytes(H, W, 2, 2, 256, 18, 3)
+    assert neurons * 2 <= w8 <= neurons * 2 + 16384                 # 1-byte encoder words + 1-byte trains
+    assert neurons * 6 <= w17 <= neurons * 6 + 16384                # 2-byte words (16 live steps) + 4-byte trains
+    assert neurons * (4 + 4 + 16) <= w18 <= neurons * 24 + 16384    # 4-byte words and trains + carried state
+    assert lib.snn_rpn_head_workspace_bytes(H, W, 2, 2, 200, 8, 3) == 0 and b"multiple of 128" in lib.snn_last_error()
+    assert lib.snn_rpn_head_workspace_bytes(H, W, 2, 2, 256, 33, 3) == 0
+    R, K, Hd = 100, 12544, 1024
+    b12 = lib.snn_box_head_workspace_bytes(R, K, Hd, 12, 3)
+    b32 = lib.snn_box_head_workspace_bytes(R, K, Hd, 32, 3)
+    assert R * K * 2 + 2 * R * Hd * 2 <= b12 <= R * K * 2 + 2 * R * Hd * 2 + 16384
+    assert R * K * 4 + 2 * R * Hd * 4 + R * Hd * 16 <= b32 <= R * K * 4 + 2 * R * Hd * 4 + R * Hd * 16 + 16384
+    assert lib.snn_box_head_workspace_bytes(R, K, Hd, 2, 3) == 0
