@@ -382,19 +382,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         if (!kConv && packed && p.dbg_sbo == 0 && n_pg == 1) {
             constexpr int kMaxItems = 8;                     // 256 rows x 8 chunks / 256 threads (cta_group 1, or cta_group 2 dual); 4 with cta_group 2
             const int n_items = n_pairs * p.T_box * (kDual ? 2 : 1);   // <= 256 rows * 8 chunks
-            uint32_t it_src[kMaxItems], it_dst[kMaxItems], it_t[kMaxItems];
+            // expansion of one 32-bit output (two neurons' bits of step t -> two 16-bit ones):
+            //   ((P >> pre) & mask) * mul  with  mask = 0x00010001 << low, mul = one >> low, low = min(shift, ctz(one)),
+            //   pre = shift - low: the bit is multiplied where it stands, so for shift <= ctz(one) (10 for fp16 1.0,
+            //   7 for bf16 1.0) there is no shift instruction at all
+            uint32_t it_src[kMaxItems], it_dst[kMaxItems], it_pre[kMaxItems], it_mask[kMaxItems], it_mul[kMaxItems];
+            const uint32_t one_ctz = static_cast<uint32_t>(__ffs(static_cast<int>(one)) - 1);
             int n_my = 0;
 #pragma unroll
             for (int i = 0; i < kMaxItems; ++i) {
                 const int item = ptid + i * (kProducerWarps * 32);
-                it_src[i] = it_dst[i] = 0u; it_t[i] = 0u;
+                it_src[i] = it_dst[i] = 0u; it_pre[i] = it_mask[i] = it_mul[i] = 0u;
                 if (item < n_items) {
                     const int tb = item / n_pairs, pr = item - tb * n_pairs;
                     const int b = kDual ? tb / p.T_box : 0, t = tb - b * p.T_box;     // b: accumulator buffer (dual)
                     const uint32_t j = pr >> 3, q = pr & 7, r = static_cast<uint32_t>(b * n_half + t * p.Jh) + j;
                     it_src[i] = static_cast<uint32_t>(b * n_pairs + pr) * 8u * wb;
                     it_dst[i] = r * 128u + ((q ^ (r & 7u)) << 4);      // slots are 1024-B aligned
-                    it_t[i] = (t < p.T_live) ? static_cast<uint32_t>(t) : 32u;     // 32: padding step, zero row
+                    if (t < p.T_live) {                                            // else: padding step, zero row (mask 0)
+                        const uint32_t shift = (wb == 4 ? 0u : static_cast<uint32_t>(p.in_bit0)) + static_cast<uint32_t>(t);
+                        const uint32_t low = shift < one_ctz ? shift : one_ctz;
+                        it_pre[i] = shift - low; it_mask[i] = 0x00010001u << low; it_mul[i] = one >> low;
+                    }
                     n_my = i + 1;
                 }
             }
@@ -423,11 +432,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                         P[2] = ((c.x >> p.in_bit0) & tmask) | (((c.y >> p.in_bit0) & tmask) << 16);
                         P[3] = ((c.z >> p.in_bit0) & tmask) | (((c.w >> p.in_bit0) & tmask) << 16);
                     }
-                    const uint32_t sh = (wb == 4 ? 0u : static_cast<uint32_t>(p.in_bit0)) + (it_t[i] & 31u);
-                    const uint32_t m = (it_t[i] < 32u) ? 0x00010001u : 0u;
+                    const uint32_t m = it_mask[i], mu = it_mul[i];
                     uint4 o;
-                    o.x = ((P[0] >> sh) & m) * one; o.y = ((P[1] >> sh) & m) * one;
-                    o.z = ((P[2] >> sh) & m) * one; o.w = ((P[3] >> sh) & m) * one;
+                    if (it_pre[i] == 0u) {
+                        o.x = (P[0] & m) * mu; o.y = (P[1] & m) * mu; o.z = (P[2] & m) * mu; o.w = (P[3] & m) * mu;
+                    } else {
+                        const uint32_t pre = it_pre[i];
+                        o.x = ((P[0] >> pre) & m) * mu; o.y = ((P[1] >> pre) & m) * mu;
+                        o.z = ((P[2] >> pre) & m) * mu; o.w = ((P[3] >> pre) & m) * mu;
+                    }
                     sts_v4(slot + it_dst[i], o);
                 }
                 fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core
