@@ -8,7 +8,7 @@ OUT=gpurun_out/${TAG}_configs.jsonl
 COMMON="--no-cpu-baseline --no-other-modes --steps 10 --warmup 3"
 python bench.py --workload bdd --batch 4 --mode bf16 $COMMON >> $OUT
 python bench.py --workload bdd --batch 4 --mode fp16x2 $COMMON >> $OUT
-for T in 4 8 12 16 32; do
+for T in 4 8 12 16 24 32; do
   python bench.py --t-rpn $T --t-det $T $COMMON --no-e2e >> $OUT
 done
 python bench.py --global-batch 64 $COMMON --no-e2e >> $OUT
