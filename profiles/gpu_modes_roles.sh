@@ -3,7 +3,7 @@ TAG=${1:-r01ai}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_heads.py -m gpu -x -q 2>&1 | tail -3
 for M in bf16 fp16x2; do timeout 200 python scratch/time_roles.py 0 $M 2>&1 | tail -9; done | tee gpurun_out/${TAG}_roles.txt
-COMMON="--steps 20 --warmup 5 --no-cpu-baseline --no-other-modes --no-e2e"
+COMMON="--steps 100 --warmup 10 --no-cpu-baseline --no-other-modes --no-e2e"
 for V in "--mode fp16x2" "--mode bf16" "--mode fp32_exact"; do
   timeout 300 python bench.py $COMMON $V > gpurun_out/${TAG}_bench_v.json 2> gpurun_out/${TAG}_bench_v.err
   python - <<PY
