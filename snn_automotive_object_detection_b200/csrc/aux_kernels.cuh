@@ -6,6 +6,8 @@
 #include <cuda_fp16.h>
 #include <cstdint>
 
+#include "ptx.cuh"
+
 namespace snn {
 
 // ------------------------------------------------------------ weight prep
@@ -241,6 +243,8 @@ __device__ __forceinline__ void store_words16(uint8_t* dst, const uint32_t (&w)[
 // HBM traffic: 4 B read + wb B written per input neuron (the per-timestep planes never exist).
 template <int NT, int WB>
 __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant__ EncParams p) {
+    griddep_launch_dependents();
+    griddep_wait();             // the words buffer may still be read by the previous forward's GEMM
     const int lane = threadIdx.x & 31;
     const int n_warps = gridDim.x * (blockDim.x >> 5);
     const int cgroups = p.C / kEncCh;
@@ -280,6 +284,8 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
 template <int NT, int WB>
 __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total16, int T_live,
                                                           uint8_t* __restrict__ z) {
+    griddep_launch_dependents();
+    griddep_wait();
     const uint32_t tmask = (T_live >= 32) ? 0xFFFFFFFFu : ((1u << T_live) - 1u);
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total16;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -348,6 +354,7 @@ __global__ void __launch_bounds__(kRpnRoPx) readout_rpn_kernel(const TrainT* __r
     for (int i = threadIdx.x; i < n_out * C; i += blockDim.x)
         s_w[i] = (i < A * C) ? w_cls[i] : w_bbox[i - A * C];
     build_kappa_lut(kt, static_cast<int>(sizeof(TrainT)), s_lut);
+    griddep_wait();             // the spike trains of the preceding GEMM (no-op without a programmatic launch)
     // coalesced tile load: npx rows of C*sizeof(TrainT) bytes are contiguous in global memory
     const uint32_t* src = reinterpret_cast<const uint32_t*>(trains + (static_cast<size_t>(n) * HW + p0) * C);
     const int wpr = row_words - 1;
@@ -413,11 +420,13 @@ __global__ void __launch_bounds__(256) readout_rows_kernel(const TrainT* __restr
                                                            unsigned int* __restrict__ counts) {
     __shared__ float s_lut[256 * sizeof(TrainT)];
     extern __shared__ float s_s[];                 // [kRoRows][Hd]
+    griddep_launch_dependents();
     constexpr int kWpv = 16 / static_cast<int>(sizeof(TrainT));      // words per 16-byte vector
     constexpr int kMaxVec = 8;                                       // vectors per lane and pass (Hd <= 8 * 32 * kWpv per pass)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = blockIdx.x * kRoRows;
     build_kappa_lut(kt, static_cast<int>(sizeof(TrainT)), s_lut);
+    griddep_wait();             // the spike trains of the preceding GEMM
     __syncthreads();
     {   // warp q stages row r0 + q (8 warps <-> 8 rows) and counts its spikes
         const int r = r0 + warp;

@@ -35,6 +35,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Programmatic dependent launch (launch attribute cudaLaunchAttributeProgrammaticStreamSerialization): the next
+// kernel of the stream may be scheduled once every CTA of this one has called griddep_launch_dependents() (or
+// exited), and runs its prologue while this kernel drains; it must call griddep_wait() -- which returns when the
+// preceding grid has completed and its writes are visible -- before it touches global memory.  Both are no-ops in a
+// kernel launched without the attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // arrive on the barrier at the same smem offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
     uint32_t remote;

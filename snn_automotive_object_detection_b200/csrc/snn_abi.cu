@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <string>
+#include <utility>
 
 #include "../../include/snn_heads.h"
 #include "aux_kernels.cuh"
@@ -69,6 +70,25 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// With SNN_PDL=1 every kernel of a forward is launched with programmatic stream serialization: it may be scheduled
+// while its predecessor drains and runs its prologue up to griddep_wait() (ptx.cuh).  Off by default: measured r01av
+// (145 GPU tests green with it), sustained 770-791 img/s with vs 790-791 without -- the path is bound by the board's
+// power cap, so the ~15 us of idle time it removes per kernel boundary come back as a lower SM clock.
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SNN_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // --------------------------------------------------------------------------- device / driver
 struct DeviceInfo { int sms = 0; int cc_major = 0; bool ok = false; };
@@ -186,10 +206,12 @@ cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = kGemmSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kCG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
 #define SNN_LAUNCH(CWV, CONV)                                                                                  \
     {                                                                                                          \
         auto kern = spike_gemm_lif_kernel<kCG, CWV, CONV>;                                                     \
@@ -311,9 +333,9 @@ void launch_encode_rows(const float* x, size_t total, int T_live, int wb, uint8_
     const size_t want = (total16 + 255) / 256;
     const int blocks = static_cast<int>(want > static_cast<size_t>(sms) * 8 ? static_cast<size_t>(sms) * 8 : want);
     SNN_ENC_BUCKETS(T_live, {
-        if (wb == 1) encode_rows_kernel<NT, 1><<<blocks, 256, 0, st>>>(x, total16, T_live, z);
-        else if (wb == 2) encode_rows_kernel<NT, 2><<<blocks, 256, 0, st>>>(x, total16, T_live, z);
-        else encode_rows_kernel<NT, 4><<<blocks, 256, 0, st>>>(x, total16, T_live, z);
+        if (wb == 1) launch_pdl(encode_rows_kernel<NT, 1>, dim3(blocks), dim3(256), 0, st, x, total16, T_live, z);
+        else if (wb == 2) launch_pdl(encode_rows_kernel<NT, 2>, dim3(blocks), dim3(256), 0, st, x, total16, T_live, z);
+        else launch_pdl(encode_rows_kernel<NT, 4>, dim3(blocks), dim3(256), 0, st, x, total16, T_live, z);
     });
 }
 
@@ -494,8 +516,7 @@ cudaError_t launch_readout_rpn(const void* trains, int C, int HW, int N, const f
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((HW + kRpnRoPx - 1) / kRpnRoPx, N);
-    kern<<<grid, kRpnRoPx, smem, st>>>(reinterpret_cast<const T*>(trains), C, HW, wc, wb, A, lut, lo, bo, counts);
-    return cudaGetLastError();
+    return launch_pdl(kern, grid, dim3(kRpnRoPx), smem, st, reinterpret_cast<const T*>(trains), C, HW, wc, wb, A, lut, lo, bo, counts);
 }
 
 template <typename T>
@@ -508,9 +529,8 @@ cudaError_t launch_readout_rows(const void* tr7, const void* tr6, int R, int Hd,
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<(R + kRoRows - 1) / kRoRows, 256, smem, st>>>(reinterpret_cast<const T*>(tr7), reinterpret_cast<const T*>(tr6),
-                                                        R, Hd, wc, nc, wb, nb, lut, oc, ob, counts);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3((R + kRoRows - 1) / kRoRows), dim3(256), smem, st, reinterpret_cast<const T*>(tr7),
+                      reinterpret_cast<const T*>(tr6), R, Hd, wc, nc, wb, nb, lut, oc, ob, counts);
 }
 
 }  // namespace
@@ -601,6 +621,27 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
     }
 
     if (T_live > 0) {
+        if (fused) {
+            // The two CTAs of a pair add their channel halves onto zeroed outputs.  Outputs the caller laid out back to
+            // back (logits of all levels, then box deltas of all levels) are cleared with ONE memset -- issued before
+            // the encoder, so that encoder -> GEMM stay adjacent kernels of the stream (programmatic dependent launch).
+            bool adjacent = true;
+            const uint8_t* expect = reinterpret_cast<const uint8_t*>(logits_out[0]);
+            for (int l = 0; l < n_levels && adjacent; ++l) {
+                adjacent = reinterpret_cast<const uint8_t*>(logits_out[l]) == expect;
+                expect += static_cast<size_t>(N) * A * H[l] * W[l] * 4;
+            }
+            for (int l = 0; l < n_levels && adjacent; ++l) {
+                adjacent = reinterpret_cast<const uint8_t*>(bbox_out[l]) == expect;
+                expect += static_cast<size_t>(N) * 4 * A * H[l] * W[l] * 4;
+            }
+            if (adjacent)
+                CUDA_TRY(cudaMemsetAsync(logits_out[0], 0, expect - reinterpret_cast<const uint8_t*>(logits_out[0]), st));
+            for (int l = 0; l < n_levels && !adjacent; ++l) {
+                CUDA_TRY(cudaMemsetAsync(logits_out[l], 0, static_cast<size_t>(N) * A * H[l] * W[l] * 4, st));
+                CUDA_TRY(cudaMemsetAsync(bbox_out[l], 0, static_cast<size_t>(N) * 4 * A * H[l] * W[l] * 4, st));
+            }
+        }
         // 1) encoder: fp32 NCHW features -> NHWC spike-train words (bit t = z_t)
         phase_begin(PH_ENC_RPN, st);
         {
@@ -618,9 +659,9 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
             ep.total_items = chunks * (C_in / kEncCh);
             const int blocks = (ep.total_items + 7) / 8 < di.sms * 8 ? (ep.total_items + 7) / 8 : di.sms * 8;
             SNN_ENC_BUCKETS(T_live, {
-                if (ep.wb == 1) encode_nchw_kernel<NT, 1><<<blocks, 256, 0, st>>>(ep);
-                else if (ep.wb == 2) encode_nchw_kernel<NT, 2><<<blocks, 256, 0, st>>>(ep);
-                else encode_nchw_kernel<NT, 4><<<blocks, 256, 0, st>>>(ep);
+                if (ep.wb == 1) launch_pdl(encode_nchw_kernel<NT, 1>, dim3(blocks), dim3(256), 0, st, ep);
+                else if (ep.wb == 2) launch_pdl(encode_nchw_kernel<NT, 2>, dim3(blocks), dim3(256), 0, st, ep);
+                else launch_pdl(encode_nchw_kernel<NT, 4>, dim3(blocks), dim3(256), 0, st, ep);
             });
             CUDA_TRY(cudaGetLastError()); ++g_launches;
         }
@@ -657,24 +698,9 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
             p.fuse_readout = 1;
             // the two CTAs of a pair add their channel halves onto zeroed outputs.  Outputs the caller laid out
             // back to back (logits of all levels, then box deltas of all levels) are cleared with ONE memset.
-            bool adjacent = true;
-            const uint8_t* expect = reinterpret_cast<const uint8_t*>(logits_out[0]);
-            for (int l = 0; l < n_levels && adjacent; ++l) {
-                adjacent = reinterpret_cast<const uint8_t*>(logits_out[l]) == expect;
-                expect += static_cast<size_t>(N) * A * H[l] * W[l] * 4;
-            }
-            for (int l = 0; l < n_levels && adjacent; ++l) {
-                adjacent = reinterpret_cast<const uint8_t*>(bbox_out[l]) == expect;
-                expect += static_cast<size_t>(N) * 4 * A * H[l] * W[l] * 4;
-            }
-            if (adjacent)
-                CUDA_TRY(cudaMemsetAsync(logits_out[0], 0, expect - reinterpret_cast<const uint8_t*>(logits_out[0]), st));
-            for (int l = 0; l < n_levels; ++l) {
+            // (zeroed before the encoder launch, above)
+            for (int l = 0; l < n_levels; ++l)
                 if (!(spike_trains_out && spike_trains_out[l])) p.lv[l].trains = nullptr;   // nobody reads them
-                if (adjacent) continue;
-                CUDA_TRY(cudaMemsetAsync(logits_out[l], 0, static_cast<size_t>(N) * A * H[l] * W[l] * 4, st));
-                CUDA_TRY(cudaMemsetAsync(bbox_out[l], 0, static_cast<size_t>(N) * 4 * A * H[l] * W[l] * 4, st));
-            }
         } else {
             for (int l = 0; l < n_levels; ++l) p.lv[l].counts = nullptr;   // the readout kernel counts instead
         }

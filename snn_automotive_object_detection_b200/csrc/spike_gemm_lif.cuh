@@ -202,6 +202,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
     if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // barriers, TMEM and descriptor prefetch are set up: let the next kernel of the stream be scheduled as soon as SMs
+    // free up, and wait for the preceding kernel's results (the spike-train words / the carried state) from here on
+    griddep_launch_dependents();
+    griddep_wait();
 
     const int n_half = p.n_mma / kCG;                 // B rows (= accumulator columns) produced per CTA
     // spike-tile ring stages per tile, and MMA k-blocks per stage: fc one k-block per stage; conv one stage per
