@@ -15,7 +15,7 @@
 //    the epilogue multiplies the accumulator row by the inverse scale (exact).
 //  * B operand  = input spikes.  They live in HBM ONLY as time-packed spike-train words (one word
 //    per input neuron, bit t = spike at step t: the encoder's output, or the previous layer's
-//    epilogue output) -- 1-2 bytes per neuron instead of one 16-bit plane per timestep.  Four
+//    epilogue output) -- 1-2 bytes per neuron instead of one 16-bit plane per timestep.  The
 //    producer warps expand the words of a k-block into the 128-byte-swizzled K-major tile the
 //    tensor core reads (rows ordered (t, unit): ALL timesteps of a unit sit in the same
 //    accumulator tile, time folded into the MMA N dimension, N = T_box * J <= 256):
@@ -29,12 +29,19 @@
 //             group stride works with base_offset 0), so the producers swizzle by the absolute row address.
 //    The word tile of a stage is 1-3 KB per CTA, so the L2->SM feed of the kernel is the weight tiles alone,
 //    and the expansion work of the conv is 40/16 halo overhead x 1/9 = 0.28 of expanding every tap.
-//  * accumulators: 2 x 256 TMEM columns (double buffered) -> the MMA of tile i+1 overlaps the
-//    LIF epilogue of tile i.  The LIF state (v, i) never leaves registers; nothing of size
-//    T x state is ever written to HBM.  Output per neuron: one time-packed spike-train word
-//    (bit t = spike at step t; popc = spike count), which is also the next layer's B operand.
+//  * accumulators: 2 x 256 TMEM columns.  conv / short fc: double buffered -> the MMA of tile i+1 overlaps
+//    the LIF epilogue of tile i.  Long fc (kDual): one tile = 2J units, both buffers fed from every weight
+//    tile (half the L2 -> SM weight stream and half the cross-CTA hand-offs per FLOP).
+//    The LIF state (v, i) never leaves registers; nothing of size T x state is ever written to HBM.
+//    Output per neuron: one time-packed spike-train word (bit t = spike at step t; popc = spike count),
+//    which is also the next layer's B operand.
+//  * More than 16 live steps: the host cuts the time axis into passes (one launch each) and the neuron
+//    state is carried between them as one float4 per neuron (GemmLifParams::state).
 //  * kCG = 2 pairs two SMs (cta_group::2, UMMA M = 256): each CTA owns 128 output channels and
 //    produces half of the unit tile.
+//  * Profiling: GemmLifParams::role_cycles (snn_set_role_timers) collects, per CTA pair, where the
+//    MMA-issuing thread and one epilogue warp spend their cycles and the kernel's entry-to-exit time in
+//    SM cycles and nanoseconds.
 #pragma once
 #include <cuda_bf16.h>
 
