@@ -601,16 +601,49 @@ __device__ __forceinline__ float roi_bilinear(const float* __restrict__ f, int H
     return w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
 }
 
+// One bilinear sample of a bin, prepared once and applied to every channel: corner offsets inside a channel plane and
+// corner weights (all zero for a sample outside the map, as roi_bilinear returns 0 there).
+struct RoiSample { int o1, o2, o3, o4; float w1, w2, w3, w4; };
+
+__device__ __forceinline__ RoiSample roi_prepare(int H, int W, float y, float x) {
+    RoiSample s{0, 0, 0, 0, 0.f, 0.f, 0.f, 0.f};
+    if (y < -1.0f || y > static_cast<float>(H) || x < -1.0f || x > static_cast<float>(W)) return s;
+    if (y <= 0.f) y = 0.f;
+    if (x <= 0.f) x = 0.f;
+    int y_low = static_cast<int>(y), x_low = static_cast<int>(x);
+    int y_high, x_high;
+    if (y_low >= H - 1) { y_high = y_low = H - 1; y = static_cast<float>(y_low); } else { y_high = y_low + 1; }
+    if (x_low >= W - 1) { x_high = x_low = W - 1; x = static_cast<float>(x_low); } else { x_high = x_low + 1; }
+    const float ly = y - y_low, lx = x - x_low, hy = 1.f - ly, hx = 1.f - lx;
+    s.o1 = y_low * W + x_low; s.o2 = y_low * W + x_high; s.o3 = y_high * W + x_low; s.o4 = y_high * W + x_high;
+    s.w1 = hy * hx; s.w2 = hy * lx; s.w3 = ly * hx; s.w4 = ly * lx;
+    return s;
+}
+
+constexpr int kRoiChPerThread = 64;
+
+// Thread = (RoI, bin (ph, pw), group of 64 channels).  The sampling grid of a bin -- positions, border rules and the
+// four bilinear weights of each sample -- depends on the RoI and the bin only, so it is prepared ONCE (up to 2 x 2
+// samples, torchvision's sampling_ratio = 2 of Faster R-CNN) and applied to the thread's 64 channel planes: 16 loads
+// + 16 multiply-adds + the comparator-bank encoder per output instead of re-deriving the grid for every channel
+// (the first version: 8 consecutive k = c*PP + bin per thread).  Consecutive threads are consecutive bins of a RoI, so
+// a warp's loads fall into a few rows of one channel plane and its stores are consecutive words.
+// Other sampling grids (adaptive, or more than 4 samples per bin) take the per-channel path.
 template <int NT>
 __global__ void __launch_bounds__(256) roi_align_encode_kernel(const __grid_constant__ RoiEncParams p) {
     const uint32_t tmask = (p.T_live >= 32) ? 0xFFFFFFFFu : ((1u << p.T_live) - 1u);
     const int PP = p.P * p.P;
     const int K = p.C * PP;
-    const size_t total8 = static_cast<size_t>(p.R) * K / 8;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
+    const int groups = (p.C + kRoiChPerThread - 1) / kRoiChPerThread;
+    const size_t bins = static_cast<size_t>(p.R) * PP;
+    const size_t total = bins * groups;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int r = static_cast<int>(i / (K / 8));
-        const int k0 = static_cast<int>(i - static_cast<size_t>(r) * (K / 8)) * 8;
+        const int g = static_cast<int>(i / bins);
+        const size_t rb = i - static_cast<size_t>(g) * bins;
+        const int r = static_cast<int>(rb / PP);
+        const int bin = static_cast<int>(rb - static_cast<size_t>(r) * PP);
+        const int ph = bin / p.P, pw = bin - ph * p.P;
         const float* roi = p.rois + 5 * static_cast<size_t>(r);
         const RoiLevel& L = p.lv[p.roi_level[r]];
         const int b = static_cast<int>(roi[0]);
@@ -620,41 +653,46 @@ __global__ void __launch_bounds__(256) roi_align_encode_kernel(const __grid_cons
         const int gh = p.sampling > 0 ? p.sampling : static_cast<int>(ceilf(roi_h / p.P));
         const int gw = p.sampling > 0 ? p.sampling : static_cast<int>(ceilf(roi_w / p.P));
         const float count = fmaxf(static_cast<float>(gh * gw), 1.f);
-        float xv[8];
+        const int c0 = g * kRoiChPerThread, c1 = min(p.C, c0 + kRoiChPerThread);
+        const size_t plane = static_cast<size_t>(L.H) * L.W;
+        const float* f = L.x + (static_cast<size_t>(b) * p.C + c0) * plane;
+        const size_t out0 = static_cast<size_t>(r) * K + static_cast<size_t>(c0) * PP + bin;
+        const bool fast = gh <= 2 && gw <= 2;
+        RoiSample sm[4];
+        if (fast) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int k = k0 + e;
-            const int c = k / PP, rem = k - c * PP;
-            const int ph = rem / p.P, pw = rem - ph * p.P;
-            const float* f = L.x + (static_cast<size_t>(b) * p.C + c) * L.H * L.W;
-            float acc = 0.f;
-            for (int iy = 0; iy < gh; ++iy) {
-                const float y = rsh + ph * bin_h + static_cast<float>(iy + .5f) * bin_h / static_cast<float>(gh);
-                for (int ix = 0; ix < gw; ++ix) {
+            for (int iy = 0; iy < 2; ++iy)
+#pragma unroll
+                for (int ix = 0; ix < 2; ++ix) {
+                    const float y = rsh + ph * bin_h + static_cast<float>(iy + .5f) * bin_h / static_cast<float>(gh);
                     const float x = rsw + pw * bin_w + static_cast<float>(ix + .5f) * bin_w / static_cast<float>(gw);
-                    acc += roi_bilinear(f, L.H, L.W, y, x);
+                    sm[iy * 2 + ix] = (iy < gh && ix < gw) ? roi_prepare(L.H, L.W, y, x) : RoiSample{0, 0, 0, 0, 0.f, 0.f, 0.f, 0.f};
+                }
+        }
+        size_t out = out0;
+        for (int c = c0; c < c1; ++c, f += plane, out += PP) {
+            float acc = 0.f;
+            if (fast) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const RoiSample& s4 = sm[q];
+                    acc += s4.w1 * __ldg(f + s4.o1) + s4.w2 * __ldg(f + s4.o2) + s4.w3 * __ldg(f + s4.o3) + s4.w4 * __ldg(f + s4.o4);
+                }
+            } else {
+                for (int iy = 0; iy < gh; ++iy) {
+                    const float y = rsh + ph * bin_h + static_cast<float>(iy + .5f) * bin_h / static_cast<float>(gh);
+                    for (int ix = 0; ix < gw; ++ix) {
+                        const float x = rsw + pw * bin_w + static_cast<float>(ix + .5f) * bin_w / static_cast<float>(gw);
+                        acc += roi_bilinear(f, L.H, L.W, y, x);
+                    }
                 }
             }
-            xv[e] = acc / count;
-        }
-        if (p.pooled != nullptr) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) p.pooled[static_cast<size_t>(r) * K + k0 + e] = xv[e];
-        }
-        uint32_t tr[8];
-        encode_words<NT, 8>(xv, tmask, tr);
-        uint8_t* z = p.words;
-        if (p.wb == 1) {
-            uint2 o;
-            o.x = tr[0] | (tr[1] << 8) | (tr[2] << 16) | (tr[3] << 24);
-            o.y = tr[4] | (tr[5] << 8) | (tr[6] << 16) | (tr[7] << 24);
-            reinterpret_cast<uint2*>(z)[i] = o;
-        } else if (p.wb == 2) {
-            reinterpret_cast<uint4*>(z)[i] =
-                make_uint4(tr[0] | (tr[1] << 16), tr[2] | (tr[3] << 16), tr[4] | (tr[5] << 16), tr[6] | (tr[7] << 16));
-        } else {
-            reinterpret_cast<uint4*>(z)[2 * i] = make_uint4(tr[0], tr[1], tr[2], tr[3]);
-            reinterpret_cast<uint4*>(z)[2 * i + 1] = make_uint4(tr[4], tr[5], tr[6], tr[7]);
+            const float val = acc / count;
+            if (p.pooled != nullptr) p.pooled[out] = val;
+            const uint32_t w = encode_word<NT>(val, tmask);
+            if (p.wb == 1) p.words[out] = static_cast<uint8_t>(w);
+            else if (p.wb == 2) reinterpret_cast<uint16_t*>(p.words)[out] = static_cast<uint16_t>(w);
+            else reinterpret_cast<uint32_t*>(p.words)[out] = w;
         }
     }
 }

@@ -861,8 +861,8 @@ int snn_roi_align_encode(const void* const* feat_ptrs, const int* H, const int* 
     p.n_levels = n_levels; p.C = C; p.R = R; p.P = pooled_size; p.sampling = sampling_ratio; p.T_live = T_live;
     p.wb = word_bytes(T_live);
     p.rois = rois; p.roi_level = roi_level; p.words = reinterpret_cast<uint8_t*>(words_out); p.pooled = pooled_out;
-    const size_t total8 = static_cast<size_t>(R) * C * pooled_size * pooled_size / 8;
-    const int blocks = static_cast<int>((total8 + 255) / 256 > 148 * 32 ? 148 * 32 : (total8 + 255) / 256);
+    const size_t items = static_cast<size_t>(R) * pooled_size * pooled_size * ((C + kRoiChPerThread - 1) / kRoiChPerThread);
+    const int blocks = static_cast<int>((items + 255) / 256 > 148 * 32 ? 148 * 32 : (items + 255) / 256);
     SNN_ENC_BUCKETS(T_live, (roi_align_encode_kernel<NT><<<blocks, 256, 0, (cudaStream_t)stream>>>(p)));
     CUDA_TRY(cudaGetLastError());
     return SNN_OK;
