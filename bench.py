@@ -132,6 +132,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.power_mw, self.power_limit_mw = [], None
         self._stop_evt = threading.Event()
         try:
             import pynvml
@@ -139,6 +140,10 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            try:
+                self.power_limit_mw = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.h)
+            except Exception:
+                pass
         except Exception:
             self.nv = None
 
@@ -156,6 +161,7 @@ class ClockSampler(threading.Thread):
         while not self._stop_evt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power_mw.append(nv.nvmlDeviceGetPowerUsage(self.h))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for bit, name in names.items():
                     if r & bit:
@@ -168,7 +174,11 @@ class ClockSampler(threading.Thread):
         self._stop_evt.set()
         self.join(timeout=2)
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                # NVML's board power is a trailing average (about a second), so over a 0.25 s timed region that follows
+                # an idle period it lags far behind the instantaneous draw that trips sw_power_cap
+                "power_w_nvml_trailing_avg": statistics.median(self.power_mw) / 1e3 if self.power_mw else None,
+                "power_limit_w": self.power_limit_mw / 1e3 if self.power_limit_mw else None}
 
 
 # ----------------------------------------------------------------------------- our arm
