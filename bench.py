@@ -6,21 +6,29 @@ RPNHeadSNN.forward on the 5 Cityscapes-shaped FPN levels (768x1536 after the ref
 transform: 192x384 ... 12x24, 256 channels) + FastRCNNPredictorSNNFull.forward on 1000 RoIs
 per image, T_rpn = 8 / T_det = 12, 9 classes, random-init weights (reference constructors).
 
-  value : whole-job images/s with the step's inputs already resident in HBM (CUDA events).
+  value : whole-job images/s with the step's inputs already resident in HBM (CUDA events, max over ranks).
+          The path is bound by the board's 1000 W cap: for ~50 ms after an idle period the SM clock is the
+          1965 MHz application clock, then sw_power_cap settles it near 1.75 GHz.  So that every N and every
+          --steps is measured in the SAME (sustained) regime, the warm-up is followed by an un-reported
+          pre-conditioning loop of >= --precondition-s seconds of the same steps; `first_20_steps` keeps the
+          burst figure (measured from idle, before the pre-conditioning).
   e2e   : same metric through the public modules with HOST (pinned) inputs: every step's features
           and RoI features are copied host->device and its outputs device->host inside the timed
           region (double-buffered on side streams so copies overlap the kernels).
+          e2e_fused_roi_pool: the same with the module boundary one row earlier: host FPN features
+          + proposal boxes in, RoIAlign+encoder fused on the device (no RoI feature tensor crosses PCIe).
   roofline : the dominant kernel (rpn conv+LIF spike GEMM): executed tensor FLOPs per launch /
-          its CUDA-event duration (events recorded by the library on the launch stream) against
-          the measured bf16 peak in MEASURED_PEAKS.json; `traffic` = DRAM bytes of that launch from the
-          committed ncu capture (profiles/roofline_traffic.json).
-  other_kernels : fc6/fc7 spike GEMMs (tensor) and the two encoders (HBM GB/s vs the measured copy peak).
-  other_modes : short device-resident runs of the other weight modes (default headline mode: fp16x2).
-  cpu_baseline : the oracle port of the reference's torch+Norse path timed on the host cores,
-          on a bounded sample (N = 1, rank 0 only).
+          its CUDA-event duration (events recorded by the library on the launch stream inside the timed
+          region) against the measured cuBLAS bf16 peaks of MEASURED_PEAKS.json -- `frac` against the
+          SUSTAINED peak (the timed region is pre-conditioned into that regime), `frac_of_burst_peak`
+          beside it -- and against the dense clock ceiling 148 x 8192 x f with f measured INSIDE the same
+          launches (snn_set_clock_probe).  `canonical` = img/s x the reference's own FLOP count per image.
+  verify : the outputs of one step at the bench shape against the CPU oracle on the same inputs (N = 1).
+  cpu_baseline : the oracle port of the reference's torch+Norse path timed on the host cores on ONE WHOLE
+          image of the same configuration (rank 0, N = 1 only).
 
-`--impl reference` times that CPU port alone (the Norse package is not installable offline and
-/root/reference is absent on the GPU box, so the reference arm is the oracle port: kind "port").
+`--impl reference` times that CPU port alone, one whole image per step (the Norse package is not installable
+offline and /root/reference is absent on the GPU box, so the reference arm is the oracle port: kind "port").
 """
 import argparse
 import json
@@ -37,8 +45,9 @@ if ROOT not in sys.path:
 CITYSCAPES_LEVELS = [(192, 384), (96, 192), (48, 96), (24, 48), (12, 24)]
 BDD_LEVELS = [(192, 344), (96, 172), (48, 86), (24, 43), (12, 22)]
 WORKLOADS = {
-    "cityscapes": dict(levels=CITYSCAPES_LEVELS, classes=9, name="cityscapes-1024x2048(heads see 768x1536)"),
-    "bdd": dict(levels=BDD_LEVELS, classes=5, name="bdd-720x1280(heads see 768x1376)"),
+    "cityscapes": dict(levels=CITYSCAPES_LEVELS, classes=9, name="cityscapes-1024x2048(heads see 768x1536)",
+                       image_size=(768, 1536)),
+    "bdd": dict(levels=BDD_LEVELS, classes=5, name="bdd-720x1280(heads see 768x1376)", image_size=(768, 1376)),
 }
 T_RPN, T_DET, ROIS, CH, HID, KBOX = 8, 12, 1000, 256, 1024, 12544
 METRIC = "SNN-head images/sec (1024x2048, Trpn8/Tdet12)"
@@ -49,11 +58,9 @@ DTYPE_OF_MODE = {"fp32_exact": "bf16x3 (fp32 weights exactly, fp32 accumulate)",
                  "bf16x2": "bf16x2", "bf16": "bf16", "fp16": "fp16"}
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    # 100 steps = 0.25 s: long enough for the board's power management to settle (the first ~20 steps after an idle
-    # period run at the 1965 MHz application clock, the sustained clock under this load is ~1.76-1.81 GHz, sw_power_cap)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -66,65 +73,149 @@ def parse():
                     help="strong-scaling variant (BASELINE configs[4]): this many images per step in total, split over the ranks")
     ap.add_argument("--t-rpn", type=int, default=T_RPN)
     ap.add_argument("--t-det", type=int, default=T_DET)
+    ap.add_argument("--precondition-s", type=float, default=1.0,
+                    help="seconds of un-reported steps between the warm-up and the timed region (power-cap regime)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of one step's outputs (N = 1)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cta-group", type=int, default=0)
     ap.add_argument("--fc-dual", type=int, default=0, help="fc tiling experiments: 0 auto, 1 single tiles, 2 dual wherever possible")
     ap.add_argument("--fc-units", type=int, default=0, help="fc tiling experiments: cap on the units per accumulator tile")
     ap.add_argument("--fc-no-split", type=int, default=0, help="fc tiling experiments: 1 = never run the tail wave as single tiles")
-    return ap.parse_args()
+    return ap.parse_args(argv)
+
+
+def canonical_gflop_per_image(workload, t_rpn, t_det):
+    """The reference's own count: every layer executed at all T steps, 1 MAC = 2 FLOP."""
+    wl = WORKLOADS[workload]
+    P = sum(h * w for (h, w) in wl["levels"])
+    C = wl["classes"]
+    f = 2.0 * P * (9 * CH) * CH * t_rpn + 2.0 * P * CH * 15 * t_rpn
+    f += 2.0 * ROIS * KBOX * HID * t_det + 2.0 * ROIS * HID * HID * t_det + 2.0 * ROIS * HID * 5 * C * t_det
+    return f / 1e9
 
 
 # ----------------------------------------------------------------------------- CPU port (oracle) timing
-def cpu_port_step_fn(workload, t_rpn, t_det, frac_den=4):
-    """Returns (fn, images_per_call, description).  The sample is 1/frac_den of an image: every FPN
-    level cropped to H/frac_den rows and ROIS/frac_den RoIs (both heads are linear in these units)."""
+def bench_inputs(workload, image_index):
+    """The synthetic input of one global image index (seeded per image so shards are reproducible):
+    its 5 FPN levels [CH, h, w] and its RoI features [ROIS, CH, 7, 7].  Shared by the GPU arm, the verify leg and the
+    CPU arm, so all three see the same tensors."""
+    import torch
+    g = torch.Generator().manual_seed(1234 + image_index)
+    feats = [torch.randn(CH, h, w, generator=g) for (h, w) in WORKLOADS[workload]["levels"]]
+    rois = torch.randn(ROIS, CH, 7, 7, generator=g)
+    return feats, rois
+
+
+def cpu_port_step_fn(workload, t_rpn, t_det):
+    """Returns (fn, images_per_call, description): the oracle port on ONE WHOLE image of the configuration (all five
+    FPN levels at full size + its 1000 RoIs) with all host threads."""
     import torch
     from oracle import snn_oracle as O                       # CPU baseline leg only
     torch.set_num_threads(os.cpu_count() or 1)
     W = O.reference_weights(num_classes=WORKLOADS[workload]["classes"], seed=0)
-    g = torch.Generator().manual_seed(1234)
-    levels = [(max(h // frac_den, 1), w) for (h, w) in WORKLOADS[workload]["levels"]]
-    feats = [torch.randn(1, CH, h, w, generator=g) for (h, w) in levels]
-    rois = torch.randn(ROIS // frac_den, CH, 7, 7, generator=g)
+    f, rois = bench_inputs(workload, 0)
+    feats = [x.unsqueeze(0) for x in f]
 
     def fn():
         O.rpn_head_forward(feats, W["shared_conv"], W["conv_cls"], W["conv_bbox"], t_rpn)
         O.box_head_forward(rois, W["fc6"], W["fc7"], W["cls_score"], W["bbox_pred"], t_det)
 
-    desc = (f"1/{frac_den} image per step: 5 FPN levels cropped to H/{frac_den} rows + {ROIS // frac_den} RoIs, "
-            f"T {t_rpn}/{t_det}, torch CPU fp32 port of the reference's torch+Norse path")
-    return fn, 1.0 / frac_den, desc
+    desc = (f"1 whole image per step (5 FPN levels at full size + {ROIS} RoIs, T {t_rpn}/{t_det}), "
+            f"torch CPU fp32 port of the reference's torch+Norse path, {os.cpu_count() or 1} threads")
+    return fn, 1.0, desc
 
 
-def time_cpu_port(workload, t_rpn, t_det, steps, warmup):
+def time_cpu_port(workload, t_rpn, t_det, steps, warmup, budget_s=90.0):
+    """Times at most `steps` whole-image steps, stopping early once `budget_s` seconds of timed work are spent."""
     fn, imgs, desc = cpu_port_step_fn(workload, t_rpn, t_det)
     for _ in range(warmup):
         fn()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    done, t0 = 0, time.perf_counter()
+    while done < max(steps, 1):
         fn()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return imgs / dt, dt * 1e3, desc
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
+    return imgs / dt, dt * 1e3, desc, done
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, ms, desc = time_cpu_port(args.workload, args.t_rpn, args.t_det, args.steps, args.warmup)
+    val, ms, desc, done = time_cpu_port(args.workload, args.t_rpn, args.t_det, args.steps, min(args.warmup, 1))
     cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload]["name"], "T_rpn": args.t_rpn, "T_det": args.t_det,
-                   "rois_per_image": ROIS, "classes": WORKLOADS[args.workload]["classes"]},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc},
+                   "rois_per_image": ROIS, "classes": WORKLOADS[args.workload]["classes"], "images_per_step": 1,
+                   "same_config": True, "cpu_steps_timed": done, "cpu_warmup_steps": min(args.warmup, 1)},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc,
+                         "steps_timed": done},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- verify leg (oracle as the checker)
+def verify_step(workload, B, rank, t_rpn, t_det, rpn, box, d_feats, d_rois):
+    """One step at the bench shape with the spike trains recorded, against the oracle port on the same inputs:
+    the parity bar of oracle/parity.py (spike agreement, flips inside the 1e-5 band, every logit within 1e-3 of its
+    scale plus the exact bound of the flipped neurons feeding it)."""
+    import torch
+    from oracle import snn_oracle as O, parity as P           # checker only
+    torch.set_num_threads(os.cpu_count() or 1)
+    W = {k: v.detach().cpu() for k, v in (("shared_conv", rpn.shared_conv.weight), ("conv_cls", rpn.conv_cls.weight),
+                                          ("conv_bbox", rpn.conv_bbox.weight), ("fc6", box.fc6.weight),
+                                          ("fc7", box.fc7.weight), ("cls_score", box.cls_score.weight),
+                                          ("bbox_pred", box.bbox_pred.weight))}
+    keep = (rpn.record_spikes, box.record_spikes)
+    rpn.record_spikes = box.record_spikes = True
+    try:
+        lo, bb = rpn(d_feats)
+        cls, dl = box(d_rois)
+        torch.cuda.synchronize()
+        trains = [t.permute(0, 3, 1, 2).cpu() for t in rpn.last_spike_trains]
+        t6, t7 = (t.cpu() for t in box.last_spike_trains)
+    finally:
+        rpn.record_spikes, box.record_spikes = keep
+        rpn.last_spike_trains = box.last_spike_trains = None
+    feats = [f.cpu() for f in d_feats]
+    rois = d_rois.cpu()
+    t0 = time.perf_counter()
+    rlo, rbb, tr = O.rpn_head_forward(feats, W["shared_conv"], W["conv_cls"], W["conv_bbox"], t_rpn, record=True)
+    rc, rd, trb = O.box_head_forward(rois, W["fc6"], W["fc7"], W["cls_score"], W["bbox_pred"], t_det, record=True)
+    oracle_s = time.perf_counter() - t0
+    out = {"images": B, "rois": rois.shape[0], "oracle_seconds": oracle_s, "levels": [], "ok": True}
+    worst_agree, unexplained, flipped, neurons = 1.0, 0, 0, 0
+    for l in range(len(feats)):
+        st = P.rpn_level_parity(lo[l], bb[l], trains[l], rlo[l], rbb[l], tr[l], W["conv_cls"], W["conv_bbox"], t_rpn)
+        ok = st["agreement"] >= 0.999 and st["unexplained"] == 0 and st["logits"]["ok"] and st["bbox"]["ok"]
+        out["levels"].append({"agreement": st["agreement"], "flipped_neurons": st["flipped_neurons"],
+                              "outside_band": st["unexplained"], "logits_ok": st["logits"]["ok"],
+                              "bbox_ok": st["bbox"]["ok"],
+                              "max_logit_err_unflipped_rel": st["logits"]["max_err_unflipped"] / st["logits"]["scale"]})
+        out["ok"] = out["ok"] and ok
+        worst_agree = min(worst_agree, st["agreement"]); unexplained += st["unexplained"]
+        flipped += st["flipped_neurons"]; neurons += trains[l].numel()
+    sb = P.box_parity(cls, dl, t6, t7, rc, rd, trb, W["cls_score"], W["bbox_pred"], t_det)
+    ok = (sb["lif6"]["agreement"] >= 0.999 and sb["lif7"]["agreement"] >= 0.999 and sb["lif6"]["unexplained"] == 0 and
+          sb["lif7"]["unexplained"] == 0 and sb["cls"]["ok"] and sb["bbox"]["ok"])
+    out["box"] = {"lif6_agreement": sb["lif6"]["agreement"], "lif7_agreement": sb["lif7"]["agreement"],
+                  "lif6_flipped": sb["lif6"]["flipped_neurons"], "lif7_flipped": sb["lif7"]["flipped_neurons"],
+                  "outside_band": sb["lif6"]["unexplained"] + sb["lif7"]["unexplained"],
+                  "rows_with_flip": sb["rows_with_flip"], "cls_ok": sb["cls"]["ok"], "bbox_ok": sb["bbox"]["ok"],
+                  "max_cls_err_unflipped_rel": sb["cls"]["max_err_unflipped"] / sb["cls"]["scale"]}
+    out["ok"] = out["ok"] and ok
+    out["rpn_min_spike_agreement"] = worst_agree
+    out["rpn_flipped_neurons"] = flipped; out["rpn_neurons"] = neurons; out["rpn_outside_band"] = unexplained
+    out["bar"] = ">= 99.9 % spike agreement, flips only within 1e-5 of threshold, logits within 1e-3 of scale + flip bound"
+    return out
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -175,8 +266,8 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
-                # NVML's board power is a trailing average (about a second), so over a 0.25 s timed region that follows
-                # an idle period it lags far behind the instantaneous draw that trips sw_power_cap
+                # NVML's board power is a trailing average (about a second); the timed region follows >= 1 s of the
+                # same load (pre-conditioning), so the reading describes it
                 "power_w_nvml_trailing_avg": statistics.median(self.power_mw) / 1e3 if self.power_mw else None,
                 "power_limit_w": self.power_limit_mw / 1e3 if self.power_limit_mw else None}
 
@@ -185,7 +276,8 @@ class ClockSampler(threading.Thread):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from snn_automotive_object_detection_b200 import RPNHeadSNN, FastRCNNPredictorSNNFull, _lib, parallel
+    from snn_automotive_object_detection_b200 import (RPNHeadSNN, FastRCNNPredictorSNNFull, FusedRoIAlignEncoder, _lib,
+                                                      parallel)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,6 +286,7 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device; the spiking heads have no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
         # one process per GPU: run (and first-touch the pinned staging buffers) on the CPUs NVML reports as local to
         # this GPU, so the end-to-end host->device copies of the ranks do not share one socket's memory / PCIe root
@@ -205,6 +298,7 @@ def run_ours(args):
             cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
             if cpus:
                 os.sched_setaffinity(0, cpus)
+                numa = {"cpus_local_to_gpu": len(cpus), "first_cpu": cpus[0]}
         except Exception:
             pass
     if world > 1:
@@ -223,8 +317,8 @@ def run_ours(args):
 
     # weights: the reference constructors' init (random init; there are no checkpoints offline)
     torch.manual_seed(0)
-    rpn = RPNHeadSNN(CH, 3, args.t_rpn, mode=args.mode).to(dev)
-    box = FastRCNNPredictorSNNFull(KBOX, HID, C, args.t_det, mode=args.mode).to(dev)
+    rpn = RPNHeadSNN(CH, 3, args.t_rpn, mode=args.mode).to(dev).eval()
+    box = FastRCNNPredictorSNNFull(KBOX, HID, C, args.t_det, mode=args.mode).to(dev).eval()
     # spike-rate statistics are part of every step at every N (they are what the ranks gather), so the
     # per-GPU work is identical in the 1/2/4/8-GPU runs
     rpn.record_rates = box.record_rates = True
@@ -234,10 +328,10 @@ def run_ours(args):
         feats = [torch.empty(B, CH, h, w, pin_memory=pin) for (h, w) in levels]
         rois = torch.empty(B * ROIS, CH, 7, 7, pin_memory=pin)
         for b in range(B):
-            g = torch.Generator().manual_seed(1234 + rank * B + b)
-            for l, (h, w) in enumerate(levels):
-                feats[l][b] = torch.randn(CH, h, w, generator=g)
-            rois[b * ROIS:(b + 1) * ROIS] = torch.randn(ROIS, CH, 7, 7, generator=g)
+            f, r = bench_inputs(args.workload, rank * B + b)
+            for l in range(len(levels)):
+                feats[l][b] = f[l]
+            rois[b * ROIS:(b + 1) * ROIS] = r
         return feats, rois
 
     h_feats, h_rois = make_inputs(pin=True)
@@ -247,9 +341,7 @@ def run_ours(args):
 
     pending = [None, None]          # in-flight gather of the previous step, last gathered records
 
-    def step_resident():
-        lo, bb = rpn(d_feats)
-        cls, dl = box(d_rois)
+    def records():
         rec = parallel.spike_rate_records(rpn.last_spike_counts, levels, CH, args.t_rpn, box.last_spike_counts,
                                           ROIS, HID, args.t_det)
         # NCCL all-gather of the records when world > 1: started here, consumed one step later, so the next batch's
@@ -257,6 +349,15 @@ def run_ours(args):
         if pending[0] is not None:
             pending[1] = pending[0].result()
         pending[0] = parallel.gather_records_async(rec, [B] * world)
+
+    def drain():
+        if pending[0] is not None:
+            pending[1] = pending[0].result(); pending[0] = None
+
+    def step_resident():
+        lo, bb = rpn(d_feats)
+        cls, dl = box(d_rois)
+        records()
         return lo, bb, cls, dl
 
     def sync_all():
@@ -265,68 +366,96 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    # ---------------- device-resident timing
+    def run_for(seconds):
+        """Un-reported steps for at least `seconds` of wall time: puts the board into its sustained power state."""
+        n = 0
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(10):
+                step_resident()
+            n += 10
+            torch.cuda.synchronize(dev)
+        drain()
+        return n
+
+    # ---------------- warm-up, burst figure (from idle), pre-conditioning
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    drain()
     launches_per_step = rpn.last_launch_count + box.last_launch_count
     sync_all()
+    burst = None
+    pre_steps = 0
+    if args.precondition_s > 0:
+        time.sleep(0.25)                       # idle: the first steps then run at the application clock
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(20):
+            step_resident()
+        drain()
+        b1.record()
+        sync_all()
+        bms = torch.tensor([b0.elapsed_time(b1) / 20], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(bms, op=dist.ReduceOp.MAX)
+        burst = {"steps": 20, "ms_per_step": bms.item(), "value": world * B / (bms.item() * 1e-3), "unit": "images/s",
+                 "note": "20 steps timed from idle (max over ranks), before the power cap settles the SM clock; "
+                         "NOT the headline"}
+        pre_steps = run_for(args.precondition_s)
+    sync_all()
+
+    # ---------------- device-resident timing (sustained regime)
     sampler = ClockSampler(local_rank)
     sampler.start()
     # inside the timed region only the dominant kernel is bracketed by CUDA events (on the launch stream, by the
     # library); all seven phases are timed in a second pass of the same step below, so that 14 event records per
-    # step do not sit between the kernels of the headline measurement (r01ag: 2.40 -> 2.37 ms per step)
+    # step do not sit between the kernels of the headline measurement (r01ag: 2.40 -> 2.37 ms per step).  The same
+    # launches carry the in-kernel clock probe (two timer reads per CTA pair).
+    n_pairs = torch.cuda.get_device_properties(dev).multi_processor_count // 2
+    probe = torch.zeros(n_pairs, 2, dtype=torch.int64, device=dev)
+    lib.snn_set_clock_probe(probe.data_ptr())
     _lib.profile_enable(True, phases=["rpn_conv_lif_gemm"])
+    tm_h0, tm_m0 = _lib.host_cache_stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    ev_burst = None
+    # host time of enqueueing a step, over the first steps only: the host runs ahead of the device and would later
+    # block on the driver's launch queue, which is device time, not host time
+    n_host = min(args.steps, 24)
+    host_t0 = time.perf_counter()
+    host_issue_s = 0.0
     for k in range(args.steps):
         step_resident()
-        if k == 19 and args.steps > 20:          # the first 20 steps, reported beside the sustained figure
-            ev_burst = torch.cuda.Event(enable_timing=True)
-            ev_burst.record()
-    if pending[0] is not None:
-        pending[1] = pending[0].result(); pending[0] = None      # the last exchange is inside the timed region
+        if k == n_host - 1:
+            host_issue_s = time.perf_counter() - host_t0
+    drain()                                               # the last exchange is inside the timed region
     ev1.record()
     sync_all()
     clocks = sampler.stop()
+    lib.snn_set_clock_probe(None)
+    tm_h1, tm_m1 = _lib.host_cache_stats()
     ms_total = ev0.elapsed_time(ev1)
-    burst = None
-    if ev_burst is not None:
-        burst = {"steps": 20, "ms_per_step": ev0.elapsed_time(ev_burst) / 20,
-                 "value": world * B / (ev0.elapsed_time(ev_burst) / 20 * 1e-3), "unit": "images/s",
-                 "note": "first 20 timed steps of this rank, before the power cap settles the SM clock"}
     live = _lib.profile_read()
+    in_kernel = None
+    c = probe.cpu().double()
+    busy = c[:, 0] > 0
+    n_conv = max(live["rpn_conv_lif_gemm"][1], 1)
+    if busy.any() and (c[busy, 1] > 0).all():
+        in_kernel = {"cycles_entry_to_exit_per_launch": (c[busy, 0] / n_conv).mean().item(),
+                     "ns_entry_to_exit_per_launch": (c[busy, 1] / n_conv).mean().item(),
+                     "effective_sm_mhz": (c[busy, 0].sum() / c[busy, 1].sum()).item() * 1e3,
+                     "launches": live["rpn_conv_lif_gemm"][1],
+                     "how": "SM cycles / globaltimer ns between kernel entry and exit of every CTA pair, summed over "
+                            "the conv launches of the timed region (the launches the CUDA events bracket; the library "
+                            "keeps at most 256 event pairs, the probe covers all launches)"}
+    # second pass: every phase bracketed
     _lib.profile_enable(True)
-    for _ in range(args.steps):
+    for _ in range(min(args.steps, 100)):
         step_resident()
-    if pending[0] is not None:
-        pending[1] = pending[0].result(); pending[0] = None
+    drain()
     sync_all()
     phases = _lib.profile_read()
     _lib.profile_enable(False)
     phases["rpn_conv_lif_gemm"] = live["rpn_conv_lif_gemm"]      # the roofline uses the launch times of the timed region
-    # a few more (untimed) steps with the library's in-kernel counters on the conv launch (the last one is read): SM cycles and globaltimer
-    # nanoseconds between kernel entry and exit of every CTA pair -> the SM clock the kernel really ran at
-    # (nvidia-smi reports the 1965 MHz application clock while the tensor pipe is power-managed to ~1.82 GHz)
-    in_kernel = None
-    try:
-        n_pairs = torch.cuda.get_device_properties(dev).multi_processor_count // 2
-        ctr = torch.zeros(n_pairs, 12, dtype=torch.int64, device=dev)
-        lib.snn_set_role_timers(ctr.data_ptr(), 0)
-        for _ in range(6):                     # back-to-back steps: the last conv launch runs at the loaded clock
-            step_resident()
-        if pending[0] is not None:
-            pending[1] = pending[0].result(); pending[0] = None
-        torch.cuda.synchronize(dev)
-        lib.snn_set_role_timers(None, -1)
-        c = ctr.cpu().double()
-        busy = c[:, 9] > 0
-        if busy.any() and (c[busy, 10] > 0).all():
-            in_kernel = {"cycles_entry_to_exit": c[busy, 9].mean().item(), "ns_entry_to_exit": c[busy, 10].mean().item(),
-                         "effective_sm_mhz": (c[busy, 9] / c[busy, 10]).mean().item() * 1e3,
-                         "mma_role_cycles": c[busy, 0].mean().item(), "tiles_per_cta_pair": c[busy, 5].mean().item()}
-    except Exception as e:                     # profiling aid only
-        in_kernel = {"error": str(e)}
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     per_rank_ms = [ms_total / args.steps]
     if world > 1:
@@ -338,7 +467,7 @@ def run_ours(args):
     value = world * B / (ms_step * 1e-3)
 
     # ---------------- end-to-end timing: host (pinned) inputs in, host outputs out, every step
-    e2e = None
+    e2e = e2e_fused = None
     if not args.no_e2e:
         cs_in, cs_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         main = torch.cuda.current_stream(dev)
@@ -351,6 +480,38 @@ def run_ours(args):
         comp_done = [torch.cuda.Event() for _ in range(2)]
         out_done = [torch.cuda.Event() for _ in range(2)]
 
+        def e2e_run(step_fn, n_in_bytes, extra):
+            for s in range(max(args.warmup, 3)):
+                step_fn(s)
+            drain()
+            sync_all()
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            t0.record(main)
+            for s in range(args.steps):
+                step_fn(s)
+            drain()
+            main.wait_stream(cs_in); main.wait_stream(cs_out)
+            t1.record(main)
+            sync_all()
+            te = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            d = {"value": world * B / (te.item() / args.steps * 1e-3), "unit": "images/s",
+                 "h2d_bytes_per_step": n_in_bytes, "d2h_bytes_per_step": out_bytes,
+                 "ms_per_step": te.item() / args.steps, "overlap": "copies double-buffered on side streams"}
+            d.update(extra)
+            return d
+
+        def copy_out(k, outs):
+            comp_done[k].record(main)
+            with torch.cuda.stream(cs_out):
+                cs_out.wait_event(comp_done[k])
+                cs_out.wait_event(out_done[k])               # pinned output buffer k free again
+                for dst, src in zip(h_out[k], outs):
+                    dst.copy_(src, non_blocking=True)
+                    src.record_stream(cs_out)
+                out_done[k].record(cs_out)
+
         def e2e_step(s):
             k = s & 1
             with torch.cuda.stream(cs_in):
@@ -362,88 +523,126 @@ def run_ours(args):
             main.wait_event(in_done[k])
             lo, bb = rpn(bufs[k][0])
             cls, dl = box(bufs[k][1])
-            rec = parallel.spike_rate_records(rpn.last_spike_counts, levels, CH, args.t_rpn,
-                                              box.last_spike_counts, ROIS, HID, args.t_det)
-            if pending[0] is not None:
-                pending[1] = pending[0].result()
-            pending[0] = parallel.gather_records_async(rec, [B] * world)
-            comp_done[k].record(main)
-            with torch.cuda.stream(cs_out):
-                cs_out.wait_event(comp_done[k])
-                cs_out.wait_event(out_done[k])               # pinned output buffer k free again
-                for dst, src in zip(h_out[k], list(lo) + list(bb) + [cls, dl]):
-                    dst.copy_(src, non_blocking=True)
-                    src.record_stream(cs_out)
-                out_done[k].record(cs_out)
+            records()
+            copy_out(k, list(lo) + list(bb) + [cls, dl])
 
-        for s in range(max(args.warmup, 3)):
-            e2e_step(s)
-        sync_all()
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        t0.record(main)
-        for s in range(args.steps):
-            e2e_step(s)
-        if pending[0] is not None:
-            pending[1] = pending[0].result(); pending[0] = None
-        main.wait_stream(cs_in); main.wait_stream(cs_out)
-        t1.record(main)
-        sync_all()
-        te = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B / (te.item() / args.steps * 1e-3), "unit": "images/s",
-               "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-               "ms_per_step": te.item() / args.steps, "overlap": "copies double-buffered on side streams"}
+        e2e = e2e_run(e2e_step, in_bytes, {"boundary": "the two head modules: FPN features + RoI features in"})
+
+        # the boundary one row earlier: FPN features + proposal boxes in; RoIAlign + encoder fused on the
+        # device, the [R,256,7,7] fp32 RoI feature tensor (a third of the bytes above) never exists
+        try:
+            names = ["0", "1", "2", "3"]
+            pool = FusedRoIAlignEncoder(names, 7, 2, args.t_det)
+            gb = torch.Generator().manual_seed(4321 + rank)
+            ih, iw = wl["image_size"]
+            h_props = []
+            for b in range(B):
+                xy = torch.rand(ROIS, 2, generator=gb) * torch.tensor([iw * 0.9, ih * 0.9])
+                wh = torch.rand(ROIS, 2, generator=gb) ** 2 * torch.tensor([iw * 0.5, ih * 0.5]) + 8.0
+                h_props.append(torch.cat([xy, xy + wh], dim=1).clamp_(min=0.0).pin_memory())
+            d_props = [[torch.empty_like(p, device=dev) for p in h_props] for _ in range(2)]
+            shapes = [(ih, iw)] * B
+            prop_bytes = sum(p.numel() for p in h_props) * 4
+            feat_bytes = sum(f.numel() for f in h_feats) * 4
+
+            def e2e_step_fused(s):
+                k = s & 1
+                with torch.cuda.stream(cs_in):
+                    cs_in.wait_event(comp_done[k])
+                    for dst, src in zip(bufs[k][0], h_feats):
+                        dst.copy_(src, non_blocking=True)
+                    for dst, src in zip(d_props[k], h_props):
+                        dst.copy_(src, non_blocking=True)
+                    in_done[k].record(cs_in)
+                main.wait_event(in_done[k])
+                lo, bb = rpn(bufs[k][0])
+                enc = pool({n: f for n, f in zip(names, bufs[k][0])}, d_props[k], shapes)
+                cls, dl = box(enc)
+                records()
+                copy_out(k, list(lo) + list(bb) + [cls, dl])
+
+            e2e_fused = e2e_run(e2e_step_fused, feat_bytes + prop_bytes,
+                                {"boundary": "FPN features + 1000 proposal boxes per image in; fused RoIAlign+encoder "
+                                             "(snn_roi_align_encode) feeds the box head on the device"})
+        except Exception as e:                       # an extra line; never takes the bench down
+            e2e_fused = {"error": f"{type(e).__name__}: {e}"}
 
     # ---------------- roofline of the dominant kernel (rpn conv + LIF spike GEMM)
-    peaks, peak_src = None, "fallback"
+    peaks, peak_src = None, "fallback (B200_PROFILING.md)"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             peaks = json.load(f)
-            peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+            peak_src = "measured (MEASURED_PEAKS.json)"
     except Exception:
         pass
-    peak_tf = peaks["bf16_tflops_sustained"] if peaks else 1400.0
-    hbm_gbs = peaks["hbm_gbs"] if peaks else 6500.0
+    peak_sus = peaks["bf16_tflops_sustained"] if peaks else 1400.0
+    peak_burst = peaks["bf16_tflops"] if peaks else 1590.0
+    hbm_gbs = peaks["hbm_gbs"] if peaks else 6650.0
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     pieces = PIECES[args.mode]
     pix = sum(h * w for (h, w) in levels) * B
     conv_flops = 2.0 * pix * (9 * CH) * CH * (args.t_rpn - 1) * pieces        # executed (dead last step skipped)
     g_ms, g_n = phases["rpn_conv_lif_gemm"]
+    preconditioned = args.precondition_s > 0
+
+    def wbytes(nbits):
+        return 1 if nbits <= 8 else 2 if nbits <= 16 else 4
+
+    eff_ceiling = None
+    if in_kernel and in_kernel.get("effective_sm_mhz"):
+        eff_ceiling = sm_count * 8192 * in_kernel["effective_sm_mhz"] * 1e6 / 1e12
     roof = None
     if g_n > 0:
         ach = conv_flops / (g_ms / g_n * 1e-3) / 1e12
-        traffic = None
+        traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                traffic = json.load(f).get(f"rpn_conv_lif_gemm:{args.mode}:b{B}")
+                tj = json.load(f)
+                traffic = tj.get(f"rpn_conv_lif_gemm:{args.mode}:b{B}")
+                traffic_src = tj.get("source", "committed ncu --set full capture under profiles/, NOT measured in this run")
         except Exception:
             pass
+        # the timed region follows >= precondition_s seconds of the same load -> sustained regime -> sustained peak;
+        # without pre-conditioning a region shorter than 1 s is a burst and is judged against the burst peak
+        use_sus = preconditioned or ms_total >= 1000.0
+        peak_tf = peak_sus if use_sus else peak_burst
         roof = {"bound": "tensor", "kernel": "spike_gemm_lif_kernel (rpn 3x3 conv + LIF, all levels, one launch)",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-                "peak_source": peak_src, "flops_per_launch": conv_flops, "ms_per_launch": g_ms / g_n,
-                # the measured peak is cuBLAS on dense random data, power-capped near 1335 MHz; this kernel's B
-                # operand is >= 80 % zeros and holds the full clock, so it can exceed it.  Second yardstick:
-                # the dense 16-bit tensor ceiling at the SM clock sampled during this run.
-                "clock_ceiling_tflops": (sm_count * 8192 * (clocks["sm_mhz"] or 0) * 1e6 / 1e12) if clocks.get("sm_mhz") else None}
-        if roof["clock_ceiling_tflops"]:
-            roof["frac_of_clock_ceiling"] = ach / roof["clock_ceiling_tflops"]
-        if in_kernel and in_kernel.get("effective_sm_mhz"):
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "regime": "sustained" if use_sus else "burst",
+                "peak_source": f"{peak_src}: {'bf16_tflops_sustained' if use_sus else 'bf16_tflops'}",
+                "frac_of_sustained_peak": ach / peak_sus, "frac_of_burst_peak": ach / peak_burst,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": pix * CH * wbytes(args.t_rpn - 1) + pix * 15 * 4 + pieces * 9 * CH * CH * 2,
+                "flops_per_launch": conv_flops, "ms_per_launch": g_ms / g_n,
+                # the measured peaks are cuBLAS on dense random data, power-capped near 1335 MHz; this kernel's B
+                # operand is >= 80 % zeros and holds a higher clock under the same cap, so frac can exceed 1.  Second
+                # yardstick: the dense 16-bit tensor ceiling 148 x 8192 x f at the clock f measured inside these launches.
+                "note": "frac > 1 is possible: the cuBLAS peak was measured on dense data at ~1335 MHz under the power cap"}
+        if eff_ceiling:
             roof["in_kernel"] = in_kernel
-            eff_ceiling = sm_count * 8192 * in_kernel["effective_sm_mhz"] * 1e6 / 1e12
             roof["effective_clock_ceiling_tflops"] = eff_ceiling
             roof["frac_of_effective_clock_ceiling"] = ach / eff_ceiling
+        if clocks.get("sm_max_mhz"):
+            roof["max_clock_ceiling_tflops"] = sm_count * 8192 * clocks["sm_max_mhz"] * 1e6 / 1e12
+            roof["frac_of_max_clock_ceiling"] = ach / roof["max_clock_ceiling_tflops"]
+    gflop_img = canonical_gflop_per_image(args.workload, args.t_rpn, args.t_det)
+    canon_tf = value / world * gflop_img / 1e3                      # per GPU
+    canonical = {"gflop_per_image": gflop_img, "tflops_per_gpu": canon_tf,
+                 "frac_of_sustained_peak": canon_tf / peak_sus, "frac_of_burst_peak": canon_tf / peak_burst,
+                 "frac_of_nominal_2250": canon_tf / 2250.0,
+                 "note": "img/s x the reference's FLOP count per image (all layers at all T steps); the executed count is "
+                         f"lower by the dead steps and higher by the {pieces} pieces per weight"}
     phase_ms = {k: (v[0] / v[1] if v[1] else None) for k, v in phases.items()}
     fc6_flops = 2.0 * B * ROIS * KBOX * HID * (args.t_det - 1) * pieces      # + the step only lif6's spike count needs
     fc7_flops = 2.0 * B * ROIS * HID * HID * (args.t_det - 2) * pieces
     extra = {}
     for name, fl in (("fc6_lif_gemm", fc6_flops), ("fc7_lif_gemm", fc7_flops)):
         if phase_ms.get(name):
-            extra[name] = {"bound": "tensor", "tflops": fl / (phase_ms[name] * 1e-3) / 1e12,
-                           "frac": fl / (phase_ms[name] * 1e-3) / 1e12 / peak_tf}
+            tf = fl / (phase_ms[name] * 1e-3) / 1e12
+            extra[name] = {"bound": "tensor", "tflops": tf, "frac": tf / peak_sus, "frac_of_burst_peak": tf / peak_burst}
+            if eff_ceiling:
+                extra[name]["frac_of_effective_clock_ceiling"] = tf / eff_ceiling
     # HBM-bound companions: algorithmic bytes = fp32 inputs read once + spike-train words written once
-    def wbytes(nbits):
-        return 1 if nbits <= 8 else 2 if nbits <= 16 else 4
     enc_bytes = {"rpn_encoder": pix * CH * (4 + wbytes(args.t_rpn - 1)),
                  "box_encoder": B * ROIS * KBOX * (4 + wbytes(args.t_det - 1))}
     for name, nbytes in enc_bytes.items():
@@ -463,13 +662,19 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
-            for _ in range(10):
+            for _ in range(20):
                 step_resident()
             a1.record()
             torch.cuda.synchronize(dev)
-            other_modes[om] = {"value": B / (a0.elapsed_time(a1) / 10 * 1e-3), "unit": "images/s", "steps": 10,
+            other_modes[om] = {"value": B / (a0.elapsed_time(a1) / 20 * 1e-3), "unit": "images/s", "steps": 20,
                                "pieces_per_weight": PIECES[om]}
         rpn.mode = box.mode = args.mode
+        drain()
+
+    # ---------------- verify: one step at this shape against the oracle (rank 0, N = 1)
+    verify = None
+    if world == 1 and not args.no_verify and B <= 4:
+        verify = verify_step(args.workload, B, rank, args.t_rpn, args.t_det, rpn, box, d_feats, d_rois)
 
     if rank != 0:
         if world > 1:
@@ -477,9 +682,9 @@ def run_ours(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, ms, desc = time_cpu_port(args.workload, args.t_rpn, args.t_det, steps=3, warmup=1)
+        v, ms, desc, done = time_cpu_port(args.workload, args.t_rpn, args.t_det, steps=3, warmup=1, budget_s=30.0)
         cpu = {"value": v, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc,
-               "ms_per_sample": ms}
+               "ms_per_sample": ms, "steps_timed": done, "same_config": True}
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
@@ -488,9 +693,20 @@ def run_ours(args):
                    "T_rpn": args.t_rpn, "T_det": args.t_det, "rois_per_image": ROIS, "classes": C,
                    "weight_mode": args.mode, "pieces_per_weight": pieces,
                    "l2": f"inputs {in_bytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
-                   "parallelism": f"image-sharded dp{world}, no hot-path collective"},
-        "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "phase_ms_per_step": phase_ms,
+                   "parallelism": f"image-sharded dp{world}, no hot-path collective",
+                   "regime": ("sustained: warm-up, then %.1f s = %d un-reported steps of the same load before the timed region"
+                              % (args.precondition_s, pre_steps)) if preconditioned else "as found (no pre-conditioning)"},
+        "e2e": e2e, "e2e_fused_roi_pool": e2e_fused,
+        "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+        "host_us_per_step": host_issue_s / max(n_host, 1) * 1e6,
+        "host": {"issue_us_per_step": host_issue_s / max(n_host, 1) * 1e6, "steps_measured": n_host,
+                 "device_us_per_step": ms_step * 1e3,
+                 "tensor_map_cache_hits_per_step": (tm_h1 - tm_h0) / max(args.steps, 1),
+                 "tensor_maps_encoded_in_timed_region": tm_m1 - tm_m0, "numa": numa,
+                 "note": "wall time of enqueueing one step (both module forwards + the record gather) while the device "
+                         "runs behind; host-bound only if it exceeds device_us_per_step"},
+        "clocks": clocks, "roofline": roof, "canonical": canonical, "cpu_baseline": cpu, "verify": verify,
+        "phase_ms_per_step": phase_ms,
         "phase_timing": "rpn_conv_lif_gemm: CUDA events on the launch stream inside the timed region; the other phases: "
                         "a second pass of the same steps with every phase bracketed",
         "other_kernels": extra, "other_modes": other_modes,
@@ -500,6 +716,8 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if verify is not None and not verify["ok"]:
+        raise SystemExit("bench.py: the outputs at the bench shape FAILED the oracle check (see \"verify\" in the line above)")
 
 
 def main():

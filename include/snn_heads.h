@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 4
+#define SNN_ABI_VERSION 5
 
 #define SNN_MODE_FP32_EXACT 0 /* 3 bf16 pieces per weight (24 mantissa bits): the parity mode          */
 #define SNN_MODE_BF16 1       /* 1 piece: weights rounded to bf16, the throughput mode                 */
@@ -89,7 +89,10 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
  * spk6_trains, spk7_trains (nullable): [R][Hdim] spike-train words of lif6 / lif7 (faster_rcnn.py:499,501)
  * spike_counts_out (nullable): unsigned [2][R] spikes per RoI of lif6 and lif7 over all T steps.  When
  *              it or spk6_trains is given, fc6 is also evaluated for the one step whose spikes no output needs.
- * K multiple of 64, Hdim multiple of 256, 3 <= T <= 32, R >= 1 (ragged R is handled by TMA zero fill). */
+ * K multiple of 64, Hdim multiple of 256, 1 <= T <= 32, R >= 1 (ragged R is handled by TMA zero fill).
+ * T = 1 or 2: no fc6 current reaches lif_cls / lif_bbox before the last step, the outputs are exactly zero as in the
+ * reference (faster_rcnn.py:492-516).  T > 32 is not supported (the reference's own sweeps stop at 12 / 16,
+ * metrics_for_different_timesteps.py:30-33). */
 size_t snn_box_head_workspace_bytes(int R, int K, int Hdim, int T, int mode);
 int snn_box_head_forward(const void* x, int R, int K, int Hdim, int C, int n_box_out, int T, int mode,
                          const void* w6_prep, const void* w7_prep, const float* w_cls, const float* w_bbox,
@@ -153,6 +156,13 @@ int snn_rpn_decode_selected(const void* const* logits, const void* const* deltas
                             int n_levels, int N, int A, const long long* idx, float* boxes_out, float* scores_out,
                             float* logits_out, long long* ref_index_out, snn_stream_t stream);
 
+/* Sort keys for that per-level top-k: keys_out[l] [N][A*H*W] int64, key = (order-preserving integer image of the fp32
+ * logit) << 32 | (2^32 - 1 - the anchor's index in the reference's (H, W, A) flattening, rpn.py:248-259).  top-k on the
+ * keys selects the largest logits and breaks ties -- e.g. the exactly-zero membranes of pixels without a spike -- by
+ * the lowest reference index, whatever the top-k implementation does with equal elements. */
+int snn_rpn_topk_keys(const void* const* logits, const int* H, const int* W, int n_levels, int N, int A,
+                      long long* const* keys_out, snn_stream_t stream);
+
 /* number of kernels the last forward call on this thread enqueued (for bench accounting) */
 int snn_last_launch_count(void);
 /* force cta_group (1 or 2; 0 = auto) for subsequent forward calls on this thread -- tests/profiling only */
@@ -170,6 +180,14 @@ void snn_set_fc_tiling(int dual, int max_units, int tail_split);
  * [7] of which waiting for a full accumulator, [8] kernel entry to the MMA role's start, [9] kernel entry to exit of the
  * leader CTA, [10] the same in nanoseconds (globaltimer).  NULL switches it off. */
 void snn_set_role_timers(unsigned long long* device_counters, int phase);
+
+/* Measurement only: every RPN conv+LIF launch of this thread ADDS, per CTA pair, its kernel entry-to-exit time in SM
+ * cycles and in globaltimer nanoseconds to device_counters [pairs][2] (zeroed by the caller; NULL = off): the SM clock
+ * the kernel really ran at, measured on the same launches a bench times with CUDA events. */
+void snn_set_clock_probe(unsigned long long* device_counters);
+/* Host-side descriptor cache of this thread: TMA tensor maps served from the cache / encoded (immutable-
+ * after-init cache keyed by address, shape and box). */
+void snn_host_cache_stats(unsigned long long* hits, unsigned long long* misses);
 
 /* Per-phase device timing for bench.py: when enabled, every forward records CUDA events on its stream
  * around each phase (up to 256 forwards).  snn_profile_read() waits for them, writes the summed

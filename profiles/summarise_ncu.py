@@ -30,7 +30,9 @@ def main():
         name = os.path.splitext(os.path.basename(rep))[0] + "_summary.csv"
         with open(os.path.join(here, name), "w", newline="") as f:
             w = csv.writer(f)
-            keep = ["Kernel Name"] + [m for m in METRICS if m in col]
+            # every tensor-pipe counter the capture holds (the guide's sm__pipe_tensor_cycles_active among them)
+            tensor = [h for h in hdr if h.startswith("sm__pipe_tensor") or h.startswith("sm__inst_executed_pipe_tensor")]
+            keep = ["Kernel Name"] + [m for m in METRICS if m in col] + [h for h in tensor if h not in METRICS]
             w.writerow(keep)
             w.writerow([units[col[k]] for k in keep])
             for r in rows[2:]:

@@ -13,8 +13,8 @@ dev = "cuda"
 shapes = [(192, 384), (96, 192), (48, 96), (24, 48), (12, 24)]
 feats = [torch.randn(2, 256, h, w, device=dev) for h, w in shapes]
 rois = torch.randn(2000, 256, 7, 7, device=dev)
-rpn = RPNHeadSNN(256, 3, 8, mode=mode).to(dev); rpn.record_rates = True
-box = FastRCNNPredictorSNNFull(12544, 1024, 9, 12, mode=mode).to(dev); box.record_rates = True
+rpn = RPNHeadSNN(256, 3, 8, mode=mode).to(dev).eval(); rpn.record_rates = True
+box = FastRCNNPredictorSNNFull(12544, 1024, 9, 12, mode=mode).to(dev).eval(); box.record_rates = True
 for _ in range(3):
     rpn(feats); box(rois)
 torch.cuda.synchronize()

@@ -24,7 +24,10 @@ EXPORTS = [
     "snn_box_head_workspace_bytes", "snn_box_head_forward", "snn_fc_lif_layer", "snn_encode_rows",
     "snn_last_launch_count", "snn_set_cta_group", "snn_profile_enable", "snn_profile_read", "snn_rpn_decode_selected",
     "snn_roi_align_encode", "snn_box_head_forward_encoded", "snn_encoder_table", "snn_encoder_selftest", "snn_set_fc_tiling", "snn_set_role_timers",
+    "snn_set_clock_probe", "snn_host_cache_stats", "snn_rpn_topk_keys",
 ]
+# the ABI the argtypes below describe (include/snn_heads.h SNN_ABI_VERSION); a library of another version is refused
+EXPECTED_ABI = 5
 PHASES = ["rpn_encoder", "rpn_conv_lif_gemm", "rpn_readout", "box_encoder", "fc6_lif_gemm", "fc7_lif_gemm", "box_readout"]
 
 _lock = threading.Lock()
@@ -53,6 +56,7 @@ def _declare(lib):
     lib.snn_encode_rows.argtypes = [vp, i, i, i, vp, vp]; lib.snn_encode_rows.restype = i
     lib.snn_rpn_decode_selected.argtypes = [pvp, pvp, pvp, pi, pi, pi, pi, pi, i, i, i, vp, vp, vp, vp, vp, vp]
     lib.snn_rpn_decode_selected.restype = i
+    lib.snn_rpn_topk_keys.argtypes = [pvp, pi, pi, i, i, i, pvp, vp]; lib.snn_rpn_topk_keys.restype = i
     lib.snn_box_head_forward_encoded.argtypes = lib.snn_box_head_forward.argtypes
     lib.snn_box_head_forward_encoded.restype = i
     lib.snn_roi_align_encode.argtypes = [pvp, pi, pi, c.POINTER(c.c_float), i, i, vp, vp, i, i, i, i, vp, vp, vp]
@@ -63,6 +67,9 @@ def _declare(lib):
     lib.snn_set_cta_group.argtypes = [i]; lib.snn_set_cta_group.restype = None
     lib.snn_set_fc_tiling.argtypes = [i, i, i]; lib.snn_set_fc_tiling.restype = None
     lib.snn_set_role_timers.argtypes = [vp, i]; lib.snn_set_role_timers.restype = None
+    lib.snn_set_clock_probe.argtypes = [vp]; lib.snn_set_clock_probe.restype = None
+    ull = c.POINTER(c.c_ulonglong)
+    lib.snn_host_cache_stats.argtypes = [ull, ull]; lib.snn_host_cache_stats.restype = None
     lib.snn_profile_enable.argtypes = [i]; lib.snn_profile_enable.restype = None
     lib.snn_profile_read.argtypes = [c.POINTER(c.c_float), pi]; lib.snn_profile_read.restype = i
 
@@ -77,6 +84,12 @@ def load():
                     f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
                     "(nvcc, sm_100a).  There is no CPU / eager fallback for the spiking heads.")
             lib = ctypes.CDLL(LIB_PATH)
+            lib.snn_version.restype = ctypes.c_int
+            have = lib.snn_version()
+            if have != EXPECTED_ABI:
+                raise RuntimeError(
+                    f"{LIB_PATH} has ABI version {have}, this package binds version {EXPECTED_ABI}: the library is "
+                    "stale -- rebuild it with `python __graft_entry__.py build`")
             _declare(lib)
             _lib = lib
     return _lib
@@ -97,6 +110,13 @@ def mode_id(mode):
         return MODES[str(mode).lower()]
     except KeyError:
         raise ValueError(f"unknown mode {mode!r}; expected one of {sorted(MODES)}") from None
+
+
+def host_cache_stats():
+    """(hits, misses) of this thread's TMA tensor-map cache."""
+    h, m = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    load().snn_host_cache_stats(ctypes.byref(h), ctypes.byref(m))
+    return h.value, m.value
 
 
 def profile_enable(on, phases=None):

@@ -569,6 +569,32 @@ __global__ void __launch_bounds__(256) rpn_decode_selected_kernel(const __grid_c
     if (p.ref_index != nullptr) p.ref_index[i] = L.anchor_begin + (static_cast<long long>(h) * L.W + w) * p.A + a;
 }
 
+// Sort keys for the per-level top-k that precedes the decode: the reference takes top-k on the (H, W, A)-flattened
+// logits (rpn.py:248-259, 468-472); taking it on the head's NCHW tensor picks the same VALUES but may break ties --
+// e.g. the exactly-zero membranes of pixels where no shared_lif neuron spiked -- in another order.  The key is unique
+// per anchor: (order-preserving integer image of the fp32 logit) << 32 | (2^32 - 1 - index in the reference's order),
+// so top-k on the keys = "largest logit first, ties by the lowest reference index", independent of how the top-k
+// implementation treats equal elements, and still without the permute / reshape copy of the logits.
+struct KeyLevel { const float* logits; long long* keys; int A, HW; long long begin; };   // begin: first flat item of the level
+struct KeyParams { KeyLevel lv[kPropMaxLevels]; int n_levels, N; long long total; };
+
+__global__ void __launch_bounds__(256) rpn_topk_keys_kernel(const __grid_constant__ KeyParams p) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < p.total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        int l = 0;
+        while (l + 1 < p.n_levels && i >= p.lv[l + 1].begin) ++l;
+        const KeyLevel& L = p.lv[l];
+        const long long local = i - L.begin;                       // n * (A * HW) + a * HW + rem
+        const int per = L.A * L.HW;
+        const int pos = static_cast<int>(local % per);
+        const int a = pos / L.HW, rem = pos - a * L.HW;
+        const int b = __float_as_int(__fadd_rn(L.logits[local], 0.0f));          // -0 -> +0
+        const int k32 = b ^ ((b >> 31) & 0x7FFFFFFF);                            // integer order == float order
+        const unsigned int ref = static_cast<unsigned int>(rem) * L.A + a;
+        L.keys[local] = (static_cast<long long>(k32) << 32) | static_cast<long long>(0xFFFFFFFFu - ref);
+    }
+}
+
 // ------------------------------------------------- RoIAlign fused with the encoder
 // The step before FastRCNNPredictorSNNFull in RoIHeadsSNN.forward (roi_heads.py:1217 -> faster_rcnn.py:474-494):
 // MultiScaleRoIAlign writes [R][C][7][7] fp32 only for the encoder to threshold it into spikes.  Here one thread

@@ -8,8 +8,11 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <utility>
+#include <vector>
 
 #include "../../include/snn_heads.h"
 #include "aux_kernels.cuh"
@@ -31,13 +34,23 @@ thread_local int g_role_phase = -1;                        // which launch gets 
 // Optional per-phase device timing (CUDA events recorded on the launch stream around each phase).
 enum Phase { PH_ENC_RPN = 0, PH_GEMM_RPN, PH_RO_RPN, PH_ENC_BOX, PH_GEMM_FC6, PH_GEMM_FC7, PH_RO_BOX, PH_COUNT };
 constexpr int kMaxTimed = 256;
-struct PhaseEvents { cudaEvent_t start[kMaxTimed], stop[kMaxTimed]; int created = 0, used = 0; };
-PhaseEvents g_ph[PH_COUNT];
-unsigned g_profile = 0;          // bit ph: phase ph is timed
+// Thread-local like every other knob of this file (one host thread drives one device at a time); the events belong to
+// the device that was current when they were created and are re-created when the thread has moved to another device.
+struct PhaseEvents { cudaEvent_t start[kMaxTimed], stop[kMaxTimed]; int created = 0, used = 0, device = -1; };
+thread_local PhaseEvents g_ph[PH_COUNT];
+thread_local unsigned g_profile = 0;          // bit ph: phase ph is timed
+thread_local unsigned long long* g_clock_probe = nullptr;   // [pairs][2]: SM cycles / ns summed over the conv launches
 
 void phase_begin(int ph, cudaStream_t st) {
     if (!((g_profile >> ph) & 1u)) return;
     PhaseEvents& e = g_ph[ph];
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    if (e.device != dev) {
+        if (e.used > 0) return;                  // unread records of another device: do not mix
+        for (int i = 0; i < e.created; ++i) { cudaEventDestroy(e.start[i]); cudaEventDestroy(e.stop[i]); }
+        e.created = 0; e.device = dev;
+    }
     if (e.used >= kMaxTimed) return;
     if (e.used >= e.created) {
         if (cudaEventCreate(&e.start[e.created]) != cudaSuccess || cudaEventCreate(&e.stop[e.created]) != cudaSuccess) return;
@@ -91,18 +104,49 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 
 // --------------------------------------------------------------------------- device / driver
-struct DeviceInfo { int sms = 0; int cc_major = 0; bool ok = false; };
+// Host-side state that is immutable after first use is cached: device attributes per device, the
+// max-dynamic-shared-memory attribute per (kernel, device), and encoded TMA tensor maps keyed by everything
+// cuTensorMapEncodeTiled takes.  A forward then makes no driver query and no descriptor encode in steady state.
+struct DeviceInfo { int sms = 0; int cc_major = 0; int dev = -1; bool ok = false; };
+constexpr int kMaxDevices = 64;
+std::mutex g_host_mutex;
+DeviceInfo g_dev_info[kMaxDevices];
 
 int device_info(DeviceInfo& di) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < kMaxDevices) {
+        std::lock_guard<std::mutex> lk(g_host_mutex);
+        if (g_dev_info[dev].ok) { di = g_dev_info[dev]; return SNN_OK; }
+    }
     CUDA_TRY(cudaDeviceGetAttribute(&di.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
     CUDA_TRY(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev));
     if (di.cc_major != 10)
         return fail(SNN_E_ARCH, "device compute capability %d.x is not sm_100 (B200); there is no fallback path",
                     di.cc_major);
-    di.ok = true;
+    di.dev = dev; di.ok = true;
+    if (dev >= 0 && dev < kMaxDevices) {
+        std::lock_guard<std::mutex> lk(g_host_mutex);
+        g_dev_info[dev] = di;
+    }
     return SNN_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel instantiation, device)
+cudaError_t ensure_dyn_smem(const void* kern, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    static std::vector<std::pair<const void*, int>> done;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mutex);
+        for (const auto& d : done) if (d.first == kern && d.second == dev) return cudaSuccess;
+    }
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_host_mutex);
+    done.emplace_back(kern, dev);
+    return cudaSuccess;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -121,10 +165,38 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
+// Tensor-map cache (thread-local: no lock on the forward path).  The key holds every input of the encode, so a hit
+// returns a byte-identical descriptor; the map is a pure function of the key (it holds the address, not the data).
+struct TmapKey {
+    const void* base; int rank; int words;
+    cuuint64_t dims[4]; cuuint64_t strides[3]; cuuint32_t box[4];
+    bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+        uint64_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+        return static_cast<size_t>(h);
+    }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "TmapKey is hashed as 64-bit words");
+constexpr size_t kTmapCacheMax = 1024;
+thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+thread_local unsigned long long g_tmap_hits = 0, g_tmap_misses = 0;
+
 // innermost dim contiguous, zero fill out of bounds.  words = false: 16-bit weight tensor, 128-byte swizzle
 // (tensor-core operand tiles); words = true: byte tensor of spike-train words, no swizzle (dense box).
 int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
               const cuuint32_t* box, bool words = false) {
+    TmapKey key;
+    memset(&key, 0, sizeof(key));
+    key.base = base; key.rank = rank; key.words = words ? 1 : 0;
+    for (int i = 0; i < rank && i < 4; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+    for (int i = 0; i + 1 < rank && i < 3; ++i) key.strides[i] = strides_bytes[i];
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) { *m = it->second; ++g_tmap_hits; return SNN_OK; }
+    ++g_tmap_misses;
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) return fail(SNN_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -135,6 +207,8 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims
     if (r != CUDA_SUCCESS)
         return fail(SNN_E_CUDA, "cuTensorMapEncodeTiled failed (%d), rank %d dims %llu %llu box %u %u", (int)r, rank,
                     (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    if (g_tmaps.size() >= kTmapCacheMax) g_tmaps.clear();      // shapes / addresses keep changing: start over
+    g_tmaps.emplace(key, *m);
     return SNN_OK;
 }
 
@@ -215,7 +289,7 @@ cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_
 #define SNN_LAUNCH(CWV, CONV)                                                                                  \
     {                                                                                                          \
         auto kern = spike_gemm_lif_kernel<kCG, CWV, CONV>;                                                     \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes); \
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)kGemmSmemBytes);             \
         if (e != cudaSuccess) return e;                                                                        \
         return cudaLaunchKernelEx(&cfg, kern, p);                                                              \
     }
@@ -226,7 +300,7 @@ cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_
 #define SNN_LAUNCH_DUAL(CWV)                                                                                   \
     {                                                                                                          \
         auto kern = spike_gemm_lif_kernel<2, CWV, false, true>;                                                \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes); \
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)kGemmSmemBytes);             \
         if (e != cudaSuccess) return e;                                                                        \
         return cudaLaunchKernelEx(&cfg, kern, p);                                                              \
     }
@@ -305,6 +379,7 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
     {
         const int phase = p.conv ? 0 : (p.kblocks >= 64 ? (p.dual ? 1 : 3) : 2);
         p.role_cycles = (g_role_cycles != nullptr && phase == g_role_phase) ? g_role_cycles : nullptr;
+        p.clock_probe = (phase == 0) ? g_clock_probe : nullptr;
     }
     p.m_tiles = p.m_total / (128 * tc.cg);
     p.total_tiles = p.unit_tiles * p.m_tiles;
@@ -328,15 +403,17 @@ KappaTable kappa_table(int T) {
 int word_bytes(int nbits) { return nbits <= 8 ? 1 : nbits <= 16 ? 2 : 4; }
 
 // x [total] fp32 -> words of wb bytes (total a multiple of 16)
-void launch_encode_rows(const float* x, size_t total, int T_live, int wb, uint8_t* z, int sms, cudaStream_t st) {
+cudaError_t launch_encode_rows(const float* x, size_t total, int T_live, int wb, uint8_t* z, int sms, cudaStream_t st) {
     const size_t total16 = total / 16;
     const size_t want = (total16 + 255) / 256;
     const int blocks = static_cast<int>(want > static_cast<size_t>(sms) * 8 ? static_cast<size_t>(sms) * 8 : want);
+    cudaError_t e = cudaSuccess;
     SNN_ENC_BUCKETS(T_live, {
-        if (wb == 1) launch_pdl(encode_rows_kernel<NT, 1>, dim3(blocks), dim3(256), 0, st, x, total16, T_live, z);
-        else if (wb == 2) launch_pdl(encode_rows_kernel<NT, 2>, dim3(blocks), dim3(256), 0, st, x, total16, T_live, z);
-        else launch_pdl(encode_rows_kernel<NT, 4>, dim3(blocks), dim3(256), 0, st, x, total16, T_live, z);
+        if (wb == 1) e = launch_pdl(encode_rows_kernel<NT, 1>, dim3(blocks), dim3(256), 0, st, x, total16, T_live, z);
+        else if (wb == 2) e = launch_pdl(encode_rows_kernel<NT, 2>, dim3(blocks), dim3(256), 0, st, x, total16, T_live, z);
+        else e = launch_pdl(encode_rows_kernel<NT, 4>, dim3(blocks), dim3(256), 0, st, x, total16, T_live, z);
     });
+    return e;
 }
 
 // More than kPassSteps live steps run as several launches over the time axis with the neuron state carried in HBM
@@ -383,17 +460,19 @@ int rpn_ws_layout(const int* H, const int* W, int L, int N, int C, int T, int mo
 struct BoxWs { size_t z_off, tr6_off, tr7_off, st_off, lut_off, total; };
 
 int box_ws_layout(int R, int K, int Hd, int T, int mode, bool stats, BoxWs& ws, TileCfg& t6, TileCfg& t7) {
-    if (T < 3 || T > 32) return fail(SNN_E_ARG, "num_steps %d outside [3,32]", T);
+    if (T < 1 || T > 32) return fail(SNN_E_ARG, "num_steps %d outside [1,32]", T);
     if (R < 1) return fail(SNN_E_ARG, "R %d < 1", R);
     if (K % 64 != 0) return fail(SNN_E_ARG, "in_channels %d must be a multiple of 64", K);
     if (Hd % 128 != 0) return fail(SNN_E_ARG, "representation_size %d must be a multiple of 128", Hd);
     if (nsplit_of(mode) == 0) return fail(SNN_E_ARG, "unknown mode %d", mode);
-    // worst case over stats on/off so one workspace size serves both
+    // worst case over stats on/off so one workspace size serves both.  T < 3: no fc6 current reaches an output (the
+    // reference's membranes are all zero there); fc6 still runs for T = 2 when its spikes are asked for.
     TileCfg a{}, b{};
-    if (!pick_tile(pass_steps(T - 1), false, Hd, g_force_cg, a) || !pick_tile(pass_steps(T - 2), false, Hd, g_force_cg, b))
+    t6 = TileCfg{}; t7 = TileCfg{};
+    if (T >= 2 && !pick_tile(pass_steps(T - 1), false, Hd, g_force_cg, a)) return fail(SNN_E_ARG, "no tile shape for T=%d", T);
+    if (T >= 3 && (!pick_tile(pass_steps(T - 2), false, Hd, g_force_cg, b) || !pick_tile(pass_steps(T - 2), false, Hd, g_force_cg, t7)))
         return fail(SNN_E_ARG, "no tile shape for T=%d", T);
     t6 = stats ? a : b;
-    if (!pick_tile(pass_steps(T - 2), false, Hd, g_force_cg, t7)) return fail(SNN_E_ARG, "no tile shape for T=%d", T);
     const int tb = snn_train_word_bytes(T);
     size_t off = 0;
     ws.z_off = off; off = align_up(off + static_cast<size_t>(R) * K * word_bytes(T - 1), 1024);   // encoder words
@@ -513,7 +592,7 @@ cudaError_t launch_readout_rpn(const void* trains, int C, int HW, int N, const f
     const size_t smem = static_cast<size_t>(5 * A) * C * 4 + 256 * sizeof(T) * 4 +
                         static_cast<size_t>(kRpnRoPx) * ((C * sizeof(T)) / 4 + 1) * 4;
     auto kern = readout_rpn_kernel<T>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // size varies with C / A
     if (e != cudaSuccess) return e;
     dim3 grid((HW + kRpnRoPx - 1) / kRpnRoPx, N);
     return launch_pdl(kern, grid, dim3(kRpnRoPx), smem, st, reinterpret_cast<const T*>(trains), C, HW, wc, wb, A, lut, lo, bo, counts);
@@ -544,6 +623,11 @@ void snn_set_cta_group(int cg) { g_force_cg = (cg == 1 || cg == 2) ? cg : 0; }
 void snn_set_role_timers(unsigned long long* device_counters, int phase) {
     g_role_cycles = device_counters;
     g_role_phase = phase;
+}
+void snn_set_clock_probe(unsigned long long* device_counters) { g_clock_probe = device_counters; }
+void snn_host_cache_stats(unsigned long long* hits, unsigned long long* misses) {
+    if (hits) *hits = g_tmap_hits;
+    if (misses) *misses = g_tmap_misses;
 }
 void snn_set_fc_tiling(int dual, int max_units, int tail_split) {
     g_fc_dual = (dual == 1 || dual == 2) ? dual : 0;
@@ -658,12 +742,14 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
             ep.n_levels = n_levels; ep.N = N; ep.C = C_in; ep.T_live = T_live; ep.wb = word_bytes(T_live);
             ep.total_items = chunks * (C_in / kEncCh);
             const int blocks = (ep.total_items + 7) / 8 < di.sms * 8 ? (ep.total_items + 7) / 8 : di.sms * 8;
+            cudaError_t le = cudaSuccess;
             SNN_ENC_BUCKETS(T_live, {
-                if (ep.wb == 1) launch_pdl(encode_nchw_kernel<NT, 1>, dim3(blocks), dim3(256), 0, st, ep);
-                else if (ep.wb == 2) launch_pdl(encode_nchw_kernel<NT, 2>, dim3(blocks), dim3(256), 0, st, ep);
-                else launch_pdl(encode_nchw_kernel<NT, 4>, dim3(blocks), dim3(256), 0, st, ep);
+                if (ep.wb == 1) le = launch_pdl(encode_nchw_kernel<NT, 1>, dim3(blocks), dim3(256), 0, st, ep);
+                else if (ep.wb == 2) le = launch_pdl(encode_nchw_kernel<NT, 2>, dim3(blocks), dim3(256), 0, st, ep);
+                else le = launch_pdl(encode_nchw_kernel<NT, 4>, dim3(blocks), dim3(256), 0, st, ep);
             });
-            CUDA_TRY(cudaGetLastError()); ++g_launches;
+            if (le != cudaSuccess) return fail(SNN_E_CUDA, "encode_nchw launch failed: %s", cudaGetErrorString(le));
+            ++g_launches;
         }
         phase_end(PH_ENC_RPN, st);
         // 2) all levels, all images: implicit-GEMM 3x3 conv + LIF recurrence in one persistent launch
@@ -796,23 +882,36 @@ static int box_head_forward_impl(const void* x, bool x_is_words, int R, int K, i
     // the fc6 spike statistics are wanted.  fc7 is live for steps 1..T-2.
     const int T_live6 = stats ? T - 1 : T - 2;
     const int T_live7 = T - 2;
-    if (!x_is_words) {
-        phase_begin(PH_ENC_BOX, st);
-        launch_encode_rows(reinterpret_cast<const float*>(x), static_cast<size_t>(R) * K, T_live6, word_bytes(T - 1),
-                           wsp + ws.z_off, di.sms, st);
-        phase_end(PH_ENC_BOX, st);
-        CUDA_TRY(cudaGetLastError()); ++g_launches;
-    }
-    phase_begin(PH_GEMM_FC6, st);
+    const size_t tr_bytes = static_cast<size_t>(R) * Hdim * tb;
     float4* carried = reinterpret_cast<float4*>(wsp + ws.st_off);
-    rc = fc_layer_passes(di, z, word_bytes(T - 1), 0, R, K, Hdim, T, 0, T_live6, mode, w6_prep, tr6, t6, carried, st);
-    phase_end(PH_GEMM_FC6, st);
-    if (rc) return rc;
-    phase_begin(PH_GEMM_FC7, st);
-    // fc7 contracts lif6's spike-train words directly: its step t0 = 1 is bit 1 of the word
-    rc = fc_layer_passes(di, tr6, tb, 1, R, Hdim, Hdim, T, 1, T_live7, mode, w7_prep, tr7, t7, carried, st);
-    phase_end(PH_GEMM_FC7, st);
-    if (rc) return rc;
+    if (T_live6 >= 1) {
+        if (!x_is_words) {
+            phase_begin(PH_ENC_BOX, st);
+            cudaError_t le = launch_encode_rows(reinterpret_cast<const float*>(x), static_cast<size_t>(R) * K, T_live6,
+                                                word_bytes(T - 1), wsp + ws.z_off, di.sms, st);
+            phase_end(PH_ENC_BOX, st);
+            if (le != cudaSuccess) return fail(SNN_E_CUDA, "encode_rows launch failed: %s", cudaGetErrorString(le));
+            ++g_launches;
+        }
+        phase_begin(PH_GEMM_FC6, st);
+        rc = fc_layer_passes(di, z, word_bytes(T - 1), 0, R, K, Hdim, T, 0, T_live6, mode, w6_prep, tr6, t6, carried, st);
+        phase_end(PH_GEMM_FC6, st);
+        if (rc) return rc;
+    } else {
+        CUDA_TRY(cudaMemsetAsync(tr6, 0, tr_bytes, st));           // T = 1 (or T = 2 without statistics): lif6 never spikes
+    }
+    if (T_live7 >= 1) {
+        phase_begin(PH_GEMM_FC7, st);
+        // fc7 contracts lif6's spike-train words directly: its step t0 = 1 is bit 1 of the word
+        rc = fc_layer_passes(di, tr6, tb, 1, R, Hdim, Hdim, T, 1, T_live7, mode, w7_prep, tr7, t7, carried, st);
+        phase_end(PH_GEMM_FC7, st);
+        if (rc) return rc;
+    } else {
+        // T < 3: a lif6 spike (step 1 at the earliest) reaches lif7's membrane at step 2 -- after the last step; the
+        // reference's membranes are exactly zero (faster_rcnn.py:492-516 with num_steps 1 or 2), and so is the readout
+        // of all-zero lif7 trains below
+        CUDA_TRY(cudaMemsetAsync(tr7, 0, tr_bytes, st));
+    }
     phase_begin(PH_RO_BOX, st);
     cudaError_t e;
     const void* tr6_for_counts = spike_counts_out ? tr6 : nullptr;
@@ -903,6 +1002,27 @@ int snn_rpn_decode_selected(const void* const* logits, const void* const* deltas
     return SNN_OK;
 }
 
+int snn_rpn_topk_keys(const void* const* logits, const int* H, const int* W, int n_levels, int N, int A,
+                      long long* const* keys_out, snn_stream_t stream) {
+    if (!logits || !H || !W || !keys_out) return fail(SNN_E_ARG, "rpn_topk_keys: null argument");
+    if (n_levels < 1 || n_levels > kPropMaxLevels || N < 1 || A < 1)
+        return fail(SNN_E_ARG, "rpn_topk_keys: bad sizes (levels %d, N %d, A %d)", n_levels, N, A);
+    KeyParams p;
+    memset(&p, 0, sizeof(p));
+    long long total = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        if (!logits[l] || !keys_out[l] || H[l] < 1 || W[l] < 1) return fail(SNN_E_ARG, "rpn_topk_keys: level %d: bad argument", l);
+        p.lv[l].logits = reinterpret_cast<const float*>(logits[l]); p.lv[l].keys = keys_out[l];
+        p.lv[l].A = A; p.lv[l].HW = H[l] * W[l]; p.lv[l].begin = total;
+        total += static_cast<long long>(N) * A * H[l] * W[l];
+    }
+    p.n_levels = n_levels; p.N = N; p.total = total;
+    const long long want = (total + 255) / 256;
+    rpn_topk_keys_kernel<<<static_cast<int>(want < 148 * 8 ? want : 148 * 8), 256, 0, (cudaStream_t)stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return SNN_OK;
+}
+
 void snn_profile_enable(int on) {
     g_profile = on == 1 ? 0xFFFFFFFFu : on <= 0 ? 0u : (static_cast<unsigned>(on) >> 1);
     for (int k = 0; k < PH_COUNT; ++k) g_ph[k].used = 0;
@@ -931,10 +1051,8 @@ int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_words, snn
     DeviceInfo di;
     int rc = device_info(di);
     if (rc) return rc;
-    const int sms = di.sms;
-    launch_encode_rows(x, static_cast<size_t>(R) * K, T_live, word_bytes(T_live), reinterpret_cast<uint8_t*>(z_words), sms,
-                       (cudaStream_t)stream);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_encode_rows(x, static_cast<size_t>(R) * K, T_live, word_bytes(T_live),
+                                reinterpret_cast<uint8_t*>(z_words), di.sms, (cudaStream_t)stream));
     return SNN_OK;
 }
 

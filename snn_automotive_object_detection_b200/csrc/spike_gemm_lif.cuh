@@ -117,6 +117,10 @@ struct GemmLifParams {
     // half, [4] for weight tiles, [5] tiles; [6] the epilogue role (warp 4 of the leader CTA), [7] of which waiting
     // for a full accumulator
     unsigned long long* role_cycles;
+    // measurement only (nullable): [pairs][2]; every launch ADDS the leader CTA's kernel entry-to-exit time in SM
+    // cycles ([0]) and in globaltimer nanoseconds ([1]) -> the SM clock the kernel really ran at, taken on the very
+    // launches a bench times with CUDA events (two timer reads per CTA pair: no effect on the measurement)
+    unsigned long long* clock_probe;
     int dbg_shift, dbg_sbo, dbg_boff;   // swizzle experiment (scratch/swizzle_experiment.py, fc only): row shift, group stride, base-offset field
     // fused leaky-integrator readout (conv, cta_group 2, m_total == 256): mem_{T-1} = W . sum_t kappa_{T-1-t} spk_t
     int fuse_readout, A;
@@ -165,7 +169,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
     extern __shared__ uint8_t smem_raw[];
     const long long k_begin = clock64();          // profiling only (role_cycles)
     unsigned long long k_begin_ns = 0;
-    if (p.role_cycles != nullptr && threadIdx.x == 64) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_begin_ns));
+    if ((p.role_cycles != nullptr || p.clock_probe != nullptr) && threadIdx.x == 64)
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_begin_ns));
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
     const int stages_a = p.stages_a;
@@ -758,11 +763,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
     tcgen05_fence_before();
     if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 2) tmem_dealloc<kCG>(tmem_base, 512);
-    if (p.role_cycles != nullptr && rank == 0 && threadIdx.x == 64) {             // kernel entry -> exit of the leader CTA:
-        unsigned long long k_end_ns;                                               // [9] in SM cycles, [10] in nanoseconds
+    if ((p.role_cycles != nullptr || p.clock_probe != nullptr) && rank == 0 && threadIdx.x == 64) {
+        unsigned long long k_end_ns;                       // kernel entry -> exit of the leader CTA
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_end_ns));
-        p.role_cycles[static_cast<size_t>(group) * 12 + 9] = static_cast<unsigned long long>(clock64() - k_begin);
-        p.role_cycles[static_cast<size_t>(group) * 12 + 10] = k_end_ns - k_begin_ns;
+        const unsigned long long cyc = static_cast<unsigned long long>(clock64() - k_begin);
+        if (p.role_cycles != nullptr) {                    // [9] in SM cycles, [10] in nanoseconds
+            p.role_cycles[static_cast<size_t>(group) * 12 + 9] = cyc;
+            p.role_cycles[static_cast<size_t>(group) * 12 + 10] = k_end_ns - k_begin_ns;
+        }
+        if (p.clock_probe != nullptr) {
+            atomicAdd(&p.clock_probe[static_cast<size_t>(group) * 2], cyc);
+            atomicAdd(&p.clock_probe[static_cast<size_t>(group) * 2 + 1], k_end_ns - k_begin_ns);
+        }
     }
 }
 

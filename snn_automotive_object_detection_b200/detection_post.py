@@ -122,11 +122,25 @@ def rpn_select_proposals(objectness: Sequence[Tensor], pred_bbox_deltas: Sequenc
     logits = [o.detach().float().contiguous() for o in objectness]
     deltas = [d.detach().float().contiguous() for d in pred_bbox_deltas]
     bases = [c.detach().to(device=dev, dtype=torch.float32).contiguous() for c in cell_anchors]
+    VP = ctypes.c_void_p * L
+    IA = ctypes.c_int * L
+    # top-k on unique integer keys (logit, then lowest index in the reference's (H, W, A) order): the same selection and
+    # order as the reference's top-k on its permuted tensor, ties included -- pixels where no shared_lif neuron spiked
+    # have exactly-zero membranes for every anchor, so tie groups at the k boundary are real
+    sizes = [o[0].numel() for o in logits]
+    keys_flat = torch.empty(N * sum(sizes), dtype=torch.int64, device=dev)
+    keys, off = [], 0
+    for n_anchors in sizes:
+        keys.append(keys_flat[off:off + N * n_anchors].view(N, n_anchors)); off += N * n_anchors
+    with torch.cuda.device(dev):
+        rc = lib.snn_rpn_topk_keys(VP(*[t.data_ptr() for t in logits]), IA(*[t.shape[2] for t in logits]),
+                                   IA(*[t.shape[3] for t in logits]), L, N, A, VP(*[t.data_ptr() for t in keys]),
+                                   ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "snn_rpn_topk_keys")
     ks, idxs, lvls = [], [], []
-    for l, o in enumerate(logits):
-        n_anchors = o[0].numel()
-        k = min(int(pre_nms_top_n), n_anchors)
-        _, top = o.view(N, -1).topk(k, dim=1)                      # NCHW order: no permute / reshape copy
+    for l, kt in enumerate(keys):
+        k = min(int(pre_nms_top_n), sizes[l])
+        _, top = kt.topk(k, dim=1)                                  # positions in NCHW order: no permute / reshape copy
         ks.append(k); idxs.append(top)
         lvls.append(torch.full((k,), l, dtype=torch.int64, device=dev))
     idx = torch.cat(idxs, dim=1).contiguous()
@@ -134,8 +148,6 @@ def rpn_select_proposals(objectness: Sequence[Tensor], pred_bbox_deltas: Sequenc
     boxes = torch.empty(N, K, 4, device=dev, dtype=torch.float32)
     scores = torch.empty(N, K, device=dev, dtype=torch.float32)
     ref_index = torch.empty(N, K, device=dev, dtype=torch.int64)
-    VP = ctypes.c_void_p * L
-    IA = ctypes.c_int * L
     with torch.cuda.device(dev):
         rc = lib.snn_rpn_decode_selected(
             VP(*[t.data_ptr() for t in logits]), VP(*[t.data_ptr() for t in deltas]), VP(*[t.data_ptr() for t in bases]),

@@ -8,7 +8,10 @@ Same constructor arguments, parameter names / shapes (state_dict compatible:
 shared_conv / conv_cls / conv_bbox and fc6 / fc7 / cls_score / bbox_pred, all
 bias-free), same initialisation order, same forward signatures and outputs
 (last-step leaky-integrator membranes).  Inference only: no autograd graph is
-built.  CUDA tensors only -- there is no CPU fallback.
+built, and a forward in training mode with gradients enabled raises instead of
+handing detached outputs to the losses (the reference trains through these heads
+with Norse's surrogate gradient, train.py:149-200 -- that path is out of scope).
+CUDA tensors only -- there is no CPU fallback.
 """
 import ctypes
 from typing import List, NamedTuple, Optional, Tuple
@@ -43,9 +46,18 @@ def _stream(device):
 
 
 class _PreparedWeight:
-    """bf16 pieces of an fp32 weight, rebuilt only when the parameter changes."""
+    """16-bit pieces of an fp32 weight, rebuilt only when the parameter changes.
+
+    "Changes" is detected through (data_ptr, _version, mode, device, shape).  In-place edits through `.data`
+    (weight.data.copy_, EMA / clipping on .data) do not bump `_version`: call the module's
+    `invalidate_weight_cache()` after such an edit.  load_state_dict() and .to()/.cuda()/.float() invalidate
+    by themselves (module hooks below)."""
 
     def __init__(self):
+        self.key = None
+        self.buf = None
+
+    def invalidate(self):
         self.key = None
         self.buf = None
 
@@ -81,6 +93,36 @@ class _Workspace:
         return self.buf
 
 
+class _InferenceOnly(nn.Module):
+    """Shared host logic of the two heads: weight-cache invalidation hooks and the training-mode guard."""
+
+    def _prepared(self):
+        return [v for v in self.__dict__.values() if isinstance(v, _PreparedWeight)]
+
+    def invalidate_weight_cache(self):
+        """Forget the prepared (16-bit pieces) copies of the weights; the next forward rebuilds them."""
+        for w in self._prepared():
+            w.invalidate()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate_weight_cache()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_weight_cache()
+        return out
+
+    def _refuse_training(self, inputs):
+        if self.training and torch.is_grad_enabled() and (
+                any(p.requires_grad for p in self.parameters()) or any(t.requires_grad for t in inputs)):
+            raise RuntimeError(
+                f"{type(self).__name__} is inference-only: its CUDA kernels build no autograd graph, so in training "
+                "mode the RPN / RoI losses would be computed from detached outputs.  Call model.eval() and/or run "
+                "under torch.no_grad(); train with the reference's Norse heads and load the state_dict here "
+                "(parameter names and shapes are identical).")
+
+
 def _require_cuda(t: Tensor, what: str):
     if not t.is_cuda:
         raise RuntimeError(f"{what}: expected a CUDA tensor (B200); the spiking heads have no CPU fallback")
@@ -93,7 +135,7 @@ class EncodedRoIs(NamedTuple):
     num_steps: int
 
 
-class RPNHeadSNN(nn.Module):
+class RPNHeadSNN(_InferenceOnly):
     """Spiking RPN head (reference: rpn.py:33-121).
 
     Args (as the reference): in_channels, num_anchors, num_steps.
@@ -128,8 +170,12 @@ class RPNHeadSNN(nn.Module):
         self._w_shared = _PreparedWeight()
         self._ws = _Workspace()
 
-    @torch.no_grad()
     def forward(self, x: List[Tensor]) -> Tuple[List[Tensor], List[Tensor]]:
+        self._refuse_training(x)
+        with torch.no_grad():
+            return self._forward(x)
+
+    def _forward(self, x: List[Tensor]) -> Tuple[List[Tensor], List[Tensor]]:
         lib = _lib.load()
         mode = _lib.mode_id(self.mode)
         T = int(self.num_steps)
@@ -183,7 +229,7 @@ class RPNHeadSNN(nn.Module):
         return logits, bbox
 
 
-class FastRCNNPredictorSNNFull(nn.Module):
+class FastRCNNPredictorSNNFull(_InferenceOnly):
     """Spiking box head + predictor (reference: faster_rcnn.py:414-516).
 
     Args (as the reference): in_channels, representation_size, num_classes, num_steps,
@@ -214,8 +260,12 @@ class FastRCNNPredictorSNNFull(nn.Module):
         self._w7 = _PreparedWeight()
         self._ws = _Workspace()
 
-    @torch.no_grad()
     def forward(self, x: Tensor) -> Tuple[Tensor, Tensor]:
+        self._refuse_training([x.words if isinstance(x, EncodedRoIs) else x])
+        with torch.no_grad():
+            return self._forward(x)
+
+    def _forward(self, x: Tensor) -> Tuple[Tensor, Tensor]:
         lib = _lib.load()
         mode = _lib.mode_id(self.mode)
         T = int(self.num_steps)

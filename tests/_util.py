@@ -6,6 +6,7 @@ import numpy as np
 import torch
 
 from oracle import snn_oracle as O
+from oracle import parity as P  # noqa: F401  (the parity bar, shared with smoke() and bench.py --verify)
 from snn_automotive_object_detection_b200 import _lib
 from snn_automotive_object_detection_b200.heads import _TRAIN_DTYPE, unpack_trains  # noqa: F401
 from tests._util_cpu import split_reconstruct  # noqa: F401
@@ -66,14 +67,21 @@ def flip_mask(got_trains, ref_spk, T):
 
 
 def masked_logits_close(got, ref, keep, rel=1e-3):
-    """logits_close restricted to the positions `keep` (bool, broadcastable to got): positions fed by a
-    flipped spike legitimately move by ~kappa*w (a few percent of the logit scale) and are judged by the
-    flip criterion instead; everywhere else the 1e-3 bar applies."""
+    """logits_close restricted to the positions `keep` (bool, broadcastable to got).  Only for comparisons
+    against stored reference OUTPUTS whose spike trains differ in a way the goldens cannot bound; the tests
+    against the oracle use the bounded check of oracle/parity.py (no position exempt)."""
     ref = ref.cpu().float(); got = got.cpu().float()
     keep = keep.expand_as(ref)
     scale = max(ref.abs().max().item(), 1e-6)
     err = ((got - ref).abs() * keep).max().item()
     return err <= rel * scale, err, scale
+
+
+def flip_row_cap(n_rows, T):
+    """Upper bound on the RoI rows / pixels that may carry a (near-threshold) flipped neuron in a strict test:
+    measured on the full-size runs <= 2 % of the RoIs at T = 12 (profiles/parity/*.json); 4 % x T/12, and
+    never less than 2 rows so that tiny shapes are not judged on one neuron."""
+    return max(2, int(0.04 * n_rows * max(1.0, T / 12.0)))
 
 
 def li_readout_from_spikes(spk, w, conv):

@@ -36,7 +36,15 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 def test_abi_version_matches_the_header(lib):
     want = int(re.search(r"#define SNN_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
-    assert lib.snn_version() == want
+    assert lib.snn_version() == want == _lib.EXPECTED_ABI
+
+
+def test_a_stale_library_is_refused(lib, monkeypatch):
+    """load() compares snn_version() with the ABI its argtypes describe before binding anything."""
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "EXPECTED_ABI", _lib.EXPECTED_ABI + 1)
+    with pytest.raises(RuntimeError, match="stale"):
+        _lib.load()
 
 
 def test_host_only_helpers(lib):
@@ -123,4 +131,5 @@ def test_workspace_sizes_are_host_only_and_cover_the_carried_state(lib):
     b32 = lib.snn_box_head_workspace_bytes(R, K, Hd, 32, 3)
     assert R * K * 2 + 2 * R * Hd * 2 <= b12 <= R * K * 2 + 2 * R * Hd * 2 + 16384
     assert R * K * 4 + 2 * R * Hd * 4 + R * Hd * 16 <= b32 <= R * K * 4 + 2 * R * Hd * 4 + R * Hd * 16 + 16384
-    assert lib.snn_box_head_workspace_bytes(R, K, Hd, 2, 3) == 0
+    assert lib.snn_box_head_workspace_bytes(R, K, Hd, 2, 3) > 0          # T < 3 runs (zero membranes, as the reference)
+    assert lib.snn_box_head_workspace_bytes(R, K, Hd, 0, 3) == 0 and lib.snn_box_head_workspace_bytes(R, K, Hd, 33, 3) == 0

@@ -155,8 +155,31 @@ def test_fused_roi_align_encoder_matches_torchvision_pool_then_encode():
     from snn_automotive_object_detection_b200.heads import unpack_trains
     assert torch.equal(unpack_trains(enc.words.cpu(), T - 1).float(), ref_spk)
     # and the head gives the same outputs from either input (up to near-threshold flips of RoIAlign rounding)
-    head = S.FastRCNNPredictorSNNFull(C * 49, 1024, 9, T).cuda()
+    head = S.FastRCNNPredictorSNNFull(C * 49, 1024, 9, T).cuda().eval()
     cls_a, box_a = head(want)
     cls_b, box_b = head(enc)
     bad = ((cls_a - cls_b).abs().amax(dim=1) > 1e-3 * cls_a.abs().max()).float().mean().item()
     assert bad <= 0.05, bad
+
+
+@pytest.mark.gpu
+def test_topk_ties_are_broken_in_the_references_order():
+    """Pixels where no shared_lif neuron spiked have exactly-zero membranes for every anchor, so large tie groups at
+    the k boundary are real.  The reference takes top-k on the (H, W, A)-flattened logits (rpn.py:248-259, 468-472);
+    the selection here must be "largest first, ties by the lowest reference index" -- a stable descending sort of the
+    reference-ordered tensor."""
+    torch.manual_seed(11)
+    N, A, H, W = 2, 3, 20, 30
+    logits = torch.zeros(N, A, H, W)
+    hot = torch.rand(N, A, H, W) < 0.02                      # 2 % distinct positive values, the rest exact ties at 0
+    logits[hot] = torch.rand(int(hot.sum())) + 0.1
+    logits[0, 1, 3, 4] = -0.0
+    neg = torch.rand(N, A, H, W) < 0.3
+    logits[neg & ~hot] = -torch.rand(int((neg & ~hot).sum())) - 0.1
+    deltas = 0.1 * torch.randn(N, 4 * A, H, W)
+    cell = torch.tensor([[-16., -8., 16., 8.], [-11., -11., 11., 11.], [-8., -16., 8., 16.]])
+    k = 400                                                  # well inside the zero plateau
+    _, _, _, ref_index = S.rpn_select_proposals([logits.cuda()], [deltas.cuda()], [cell], [(16, 16)], k)
+    flat = logits.permute(0, 2, 3, 1).reshape(N, -1)         # the reference's order
+    want = torch.sort(flat, dim=1, descending=True, stable=True)[1][:, :k]
+    assert torch.equal(ref_index.cpu(), want)

@@ -7,7 +7,7 @@ import torch
 
 from oracle import snn_oracle as O
 import snn_automotive_object_detection_b200 as S
-from tests._util import unpack_trains, flip_mask, spike_agreement
+from tests._util import P, unpack_trains, flip_row_cap
 
 pytestmark = pytest.mark.gpu
 
@@ -21,7 +21,7 @@ def test_rpn_spike_rate_report_matches_oracle_format():
     m = S.RPNHeadSNN(256, 3, T)
     with torch.no_grad():
         m.shared_conv.weight.copy_(w[0]); m.conv_cls.weight.copy_(w[1]); m.conv_bbox.weight.copy_(w[2])
-    m = m.cuda(); m.record_spikes = True
+    m = m.cuda().eval(); m.record_spikes = True
     m([f.cuda() for f in feats])
     got = S.rpn_spike_rates_and_flops(m)
     want = O.rpn_head_rates(feats, *w, T, 3)
@@ -41,14 +41,28 @@ def test_box_spike_rate_report_matches_oracle_format():
     m = S.FastRCNNPredictorSNNFull(K, Hd, C, T)
     with torch.no_grad():
         m.fc6.weight.copy_(w[0]); m.fc7.weight.copy_(w[1]); m.cls_score.weight.copy_(w[2]); m.bbox_pred.weight.copy_(w[3])
-    m = m.cuda(); m.record_spikes = True
+    m = m.cuda().eval(); m.record_spikes = True
     m(x.cuda())
     got = S.box_spike_rates_and_flops(m)
     want = O.box_head_rates(x, *w, T)
+    # (a) every row against the same statistics recomputed (stepped oracle LI) from the kernel's OWN spike trains
+    own6, own7 = (unpack_trains(t.cpu(), T) for t in m.last_spike_trains)
+    cv = ci = torch.zeros(R, C); bv = bi = torch.zeros(R, 4 * C)
+    ac = torch.zeros(R, C); ab = torch.zeros(R, 4 * C)
+    for t in range(T):
+        cv, ci = O.li_step(torch.nn.functional.linear(own7[t].float(), w[2]), cv, ci); ac += cv
+        bv, bi = O.li_step(torch.nn.functional.linear(own7[t].float(), w[3]), bv, bi); ab += bv
+    own = [own6.float().sum(0).mean(1) / T, own7.float().sum(0).mean(1) / T, (ac / T).mean(1), (ab / T).mean(1)]
+    for a, o in zip(got, own):
+        assert torch.allclose(a[:, 0].cpu(), o, rtol=1e-4, atol=2e-6)
+    # (b) against the oracle's report: FLOP constants equal; rates equal on every row whose spike trains agree with
+    # the oracle's (the rows with a near-threshold flip are identified exactly and capped, not exempted blindly)
+    _, _, tr = O.box_head_forward(x, *w, T, record=True)
+    flipped = (own6 != tr["spk6"]).any(dim=0).any(dim=1) | (own7 != tr["spk7"]).any(dim=0).any(dim=1)
+    assert int(flipped.sum()) <= flip_row_cap(R, T)
     for a, b in zip(got, want):
         assert torch.equal(a[:, 1].cpu(), b[:, 1])
-        bad = ((a[:, 0].cpu() - b[:, 0]).abs() > 2e-3 * b[:, 0].abs().max() + 1e-7).float().mean().item()
-        assert bad <= 0.1        # rows hit by a near-threshold flip may move; the rest match
+        assert torch.allclose(a[~flipped, 0].cpu(), b[~flipped, 0], rtol=2e-3, atol=2e-6)
 
 
 def test_attach_to_torchvision_faster_rcnn_runs_end_to_end():
@@ -80,56 +94,72 @@ def test_attach_to_torchvision_faster_rcnn_runs_end_to_end():
         assert bad <= 0.01, (l, bad)
 
 
+_ORACLE_CACHE = {}
+
+
+def _oracle_full_size(workload, n_images):
+    """Oracle run of one full-size configuration, shared by the weight modes (about 15 s of CPU for two images)."""
+    key = (workload, n_images)
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE.clear()                                 # one configuration at a time: the traces are ~2 GB
+        levels = O.CITYSCAPES_LEVELS if workload == "cityscapes" else O.BDD_LEVELS
+        C = 9 if workload == "cityscapes" else 5
+        W = O.reference_weights(num_classes=C, seed=0)
+        feats, rois = O.synthetic_inputs(levels, n_images, rois_per_image=1000)
+        torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
+        rpn_ref = O.rpn_head_forward(feats, W["shared_conv"], W["conv_cls"], W["conv_bbox"], 8, record=True)
+        box_ref = O.box_head_forward(rois, W["fc6"], W["fc7"], W["cls_score"], W["bbox_pred"], 12, record=True)
+        _ORACLE_CACHE[key] = (levels, C, W, feats, rois, rpn_ref, box_ref)
+    return _ORACLE_CACHE[key]
+
+
 @pytest.mark.parametrize("mode", ["fp32_exact", "fp16x2"])
-@pytest.mark.parametrize("workload", ["cityscapes", "bdd"])
-def test_full_size_level_shapes_parity(workload, mode):
-    """BASELINE configs 1/2/3 at their real per-image sizes (one image): every FPN level of the
-    Cityscapes (768x1536) and BDD (768x1376, ragged widths) shapes against the oracle."""
-    levels = O.CITYSCAPES_LEVELS if workload == "cityscapes" else O.BDD_LEVELS
-    C = 9 if workload == "cityscapes" else 5
-    W = O.reference_weights(num_classes=C, seed=0)
-    w = [W["shared_conv"], W["conv_cls"], W["conv_bbox"]]
-    feats, rois = O.synthetic_inputs(levels, 1, rois_per_image=300)
+@pytest.mark.parametrize("workload,n_images", [("cityscapes", 2), ("bdd", 1)])
+def test_full_size_parity(workload, n_images, mode):
+    """SURVEY 8(d) config 2 EXACTLY -- the tensors bench.py's headline runs on: N = 2 Cityscapes-shaped images (seed
+    1234), R = 2000 RoIs, T 8/12, 9 classes, weights of seed 0, default tiling (batch-2 conv schedule; fc6 as three
+    waves of dual tiles + the tail wave of single tiles in a second launch; fc7; readout) -- and one BDD image
+    (768x1376, ragged widths, 1000 RoIs, 5 classes), against the oracle port of rpn.py:84-121 / faster_rcnn.py:470-516:
+    spike agreement >= 99.9 %, no flip outside the 1e-5 band, every logit within 1e-3 of its scale plus the exact bound
+    of the flipped neurons that feed it."""
+    levels, C, W, feats, rois, (rlo, rbb, tr), (rc, rd, trb) = _oracle_full_size(workload, n_images)
     T = 8
     m = S.RPNHeadSNN(256, 3, T, mode=mode)
     with torch.no_grad():
-        m.shared_conv.weight.copy_(w[0]); m.conv_cls.weight.copy_(w[1]); m.conv_bbox.weight.copy_(w[2])
-    m = m.cuda(); m.record_spikes = True
-    stats = {"workload": workload, "mode": mode, "rpn_levels": []}
+        m.shared_conv.weight.copy_(W["shared_conv"]); m.conv_cls.weight.copy_(W["conv_cls"]); m.conv_bbox.weight.copy_(W["conv_bbox"])
+    m = m.cuda().eval(); m.record_spikes = True; m.record_rates = True
+    stats = {"workload": workload, "mode": mode, "images": n_images, "rois": rois.shape[0], "rpn_levels": []}
     lo, bb = m([f.cuda() for f in feats])
     torch.cuda.synchronize()
-    torch.set_num_threads(max(torch.get_num_threads(), 8))
-    rlo, rbb, tr = O.rpn_head_forward(feats, *w, T, record=True)
     for l in range(len(levels)):
-        trains = m.last_spike_trains[l].permute(0, 3, 1, 2)
-        fm = flip_mask(trains, tr[l]["spk"], T)
-        agree, unexplained = spike_agreement(trains, tr[l]["spk"], tr[l]["v_dec"], T)
-        stats["rpn_levels"].append({"neurons": fm.numel(), "flipped_neurons": int(fm.sum()), "spike_agreement": agree,
-                                    "flips_outside_1e-5_band": unexplained})
-        assert unexplained == 0 and agree >= 0.999
-        assert fm.float().mean().item() <= 1e-3, f"level {l}: flipped neurons {fm.float().mean().item()}"
-        keep = ~fm.any(dim=1, keepdim=True)
-        scale = rlo[l].abs().max().item()
-        assert ((lo[l].cpu() - rlo[l]).abs() * keep).max().item() <= 1e-3 * scale
-        assert ((bb[l].cpu() - rbb[l]).abs() * keep).max().item() <= 1e-3 * rbb[l].abs().max().item()
+        trains = m.last_spike_trains[l].permute(0, 3, 1, 2).cpu()
+        st = P.rpn_level_parity(lo[l], bb[l], trains, rlo[l], rbb[l], tr[l], W["conv_cls"], W["conv_bbox"], T)
+        stats["rpn_levels"].append(st)
+        P.assert_layer(st, f"level {l} shared_lif")
+        assert st["flipped_neurons"] <= 1e-4 * trains.numel() + 2, f"level {l}: {st['flipped_neurons']} flipped neurons"
+        P.assert_close(st["logits"], f"level {l} logits"); P.assert_close(st["bbox"], f"level {l} bbox")
+        want = tr[l]["spk"].sum(dim=(0, 2, 3, 4)).to(torch.int64)
+        assert (m.last_spike_counts[l].cpu() - want).abs().max().item() <= max(2, int(1e-4 * want.max().item()))
     b = S.FastRCNNPredictorSNNFull(12544, 1024, C, 12, mode=mode)
     with torch.no_grad():
         b.fc6.weight.copy_(W["fc6"]); b.fc7.weight.copy_(W["fc7"]); b.cls_score.weight.copy_(W["cls_score"])
         b.bbox_pred.weight.copy_(W["bbox_pred"])
-    b = b.cuda(); b.record_spikes = True
+    b = b.cuda().eval(); b.record_spikes = True; b.record_rates = True
     cls, dl = b(rois.cuda())
-    rc, rd, trb = O.box_head_forward(rois, W["fc6"], W["fc7"], W["cls_score"], W["bbox_pred"], 12, record=True)
-    f6 = flip_mask(b.last_spike_trains[0], trb["spk6"], 12); f7 = flip_mask(b.last_spike_trains[1], trb["spk7"], 12)
-    assert f6.float().mean().item() <= 1e-3 and f7.float().mean().item() <= 1e-3
-    stats["box"] = {"neurons_per_layer": f6.numel(), "lif6_flipped": int(f6.sum()), "lif7_flipped": int(f7.sum())}
-    out_dir = os.environ.get("SNN_PARITY_STATS_DIR")          # profiles/: measured flip counts of both fp32-grade modes
+    torch.cuda.synchronize()
+    launches = b.last_launch_count
+    t6, t7 = (t.cpu() for t in b.last_spike_trains)
+    sb = P.box_parity(cls, dl, t6, t7, rc, rd, trb, W["cls_score"], W["bbox_pred"], 12)
+    sb["launches"] = launches
+    stats["box"] = sb
+    out_dir = os.environ.get("SNN_PARITY_STATS_DIR")          # profiles/parity: measured flip counts per mode
     if out_dir:
         import json
-        with open(os.path.join(out_dir, f"parity_stats_{workload}_{mode}.json"), "w") as f:
-            json.dump(stats, f)
-    keep = ~(f6.any(dim=1) | f7.any(dim=1)).unsqueeze(1)
-    assert ((cls.cpu() - rc).abs() * keep).max().item() <= 1e-3 * rc.abs().max().item()
-    assert ((dl.cpu() - rd).abs() * keep).max().item() <= 1e-3 * rd.abs().max().item()
+        with open(os.path.join(out_dir, f"parity_stats_{workload}_b{n_images}_{mode}.json"), "w") as f:
+            json.dump(stats, f, indent=1)
+    P.assert_layer(sb["lif6"], "lif6"); P.assert_layer(sb["lif7"], "lif7")
+    assert sb["rows_with_flip"] <= flip_row_cap(sb["rows"], 12), (sb["rows_with_flip"], sb["rows"])
+    P.assert_close(sb["cls"], "cls"); P.assert_close(sb["bbox"], "bbox")
 
 
 def test_fast_postprocessing_keeps_the_detections_of_the_stock_path():
