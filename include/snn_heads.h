@@ -133,6 +133,9 @@ int snn_fc_lif_layer(const void* z_words, int in_word_bytes, int in_bit0, int R,
 int snn_roi_align_encode(const void* const* feat_ptrs, const int* H, const int* W, const float* scales, int n_levels,
                          int C, const float* rois, const int* roi_level, int R, int pooled_size, int sampling_ratio,
                          int T_live, void* words_out, float* pooled_out, snn_stream_t stream);
+/* tests / A-B timing: 0 = auto (one block per RoI with its feature window staged in shared memory for the fixed 1 x 1 or
+ * 2 x 2 sampling grids and pooled_size <= 8), 1 = always the per-thread kernel (any sampling grid) */
+void snn_set_roi_kernel(int which);
 /* snn_box_head_forward on input that is already encoded: words [R][K] of snn_train_word_bytes-like size for T - 1 steps
  * (1/2/4 bytes for T - 1 <= 8/16/32), e.g. from snn_roi_align_encode(..., T_live = T - 1, ...). */
 int snn_box_head_forward_encoded(const void* words, int R, int K, int Hdim, int C, int n_box_out, int T, int mode,
@@ -162,6 +165,20 @@ int snn_rpn_decode_selected(const void* const* logits, const void* const* deltas
  * the lowest reference index, whatever the top-k implementation does with equal elements. */
 int snn_rpn_topk_keys(const void* const* logits, const int* H, const int* W, int n_levels, int N, int A,
                       long long* const* keys_out, snn_stream_t stream);
+
+/* ---- "next" row 8f-3: linear statistics of the spike trains the heads emit (the spike-rate / energy report the
+ * reference obtains from hand-edited forwards, rpn.py:126-200, faster_rcnn.py:520-618; train.py:426-517).
+ * out[o] = sum_c w[o][c] * sum_t step_weights[t] * spk_t[c], the two leaky-integrator readout kernels with a caller-given
+ * weight per step (32 doubles; entries beyond the word's bits are ignored): kappa_{T-1-t} gives the last LI membrane,
+ * the cumulative K_t = sum_{n <= T-1-t} kappa_n the sum over time of the LI membrane (its time mean, the reference's LI
+ * "rate", is K_t / T), 1 the spike count.
+ * nhwc: trains [N][HW][C] words (RPNHeadSNN spike_trains_out) -> out_a [N][n_a][HW], out_b [N][n_b][HW];
+ * rows: trains [R][Hd] words (spk6 / spk7 trains) -> out_a [R][n_a], out_b [R][n_b]. */
+int snn_li_readout_nhwc(const void* trains, int train_bytes, int N, int HW, int C, const double* step_weights,
+                        const float* w_a, int n_a, const float* w_b, int n_b, float* out_a, float* out_b,
+                        snn_stream_t stream);
+int snn_li_readout_rows(const void* trains, int train_bytes, int R, int Hd, const double* step_weights, const float* w_a,
+                        int n_a, const float* w_b, int n_b, float* out_a, float* out_b, snn_stream_t stream);
 
 /* number of kernels the last forward call on this thread enqueued (for bench accounting) */
 int snn_last_launch_count(void);

@@ -28,6 +28,7 @@ thread_local int g_force_cg = 0;
 thread_local int g_fc_dual = 0;      // 0 auto, 1 never, 2 whenever the tile shape allows it (tests)
 thread_local int g_fc_units = 0;     // > 0: cap on the units per fc tile (experiments)
 thread_local int g_fc_split = 0;
+thread_local int g_roi_kernel = 0;   // 0 auto, 1 force the per-thread RoIAlign kernel (tests / A-B timing)
 thread_local unsigned long long* g_role_cycles = nullptr;   // profiling: MMA-thread wait counters of the next launches
 thread_local int g_role_phase = -1;                        // which launch gets them: 0 conv, 1 / 3 fc with K >= 4096 in dual / single tiles, 2 other fc     // 1: never run the last partial wave of dual tiles as single tiles (experiments)
 
@@ -587,15 +588,15 @@ int fc_layer_passes(const DeviceInfo& di, const void* z_words, int in_wb, int in
 }
 
 template <typename T>
-cudaError_t launch_readout_rpn(const void* trains, int C, int HW, int N, const float* wc, const float* wb, int A,
+cudaError_t launch_readout_rpn(const void* trains, int C, int HW, int N, const float* wc, int n_a, const float* wb, int n_b,
                                const KappaTable& lut, float* lo, float* bo, unsigned long long* counts, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(5 * A) * C * 4 + 256 * sizeof(T) * 4 +
+    const size_t smem = static_cast<size_t>(n_a + n_b) * C * 4 + 256 * sizeof(T) * 4 +
                         static_cast<size_t>(kRpnRoPx) * ((C * sizeof(T)) / 4 + 1) * 4;
     auto kern = readout_rpn_kernel<T>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // size varies with C / A
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // size varies with C / outputs
     if (e != cudaSuccess) return e;
     dim3 grid((HW + kRpnRoPx - 1) / kRpnRoPx, N);
-    return launch_pdl(kern, grid, dim3(kRpnRoPx), smem, st, reinterpret_cast<const T*>(trains), C, HW, wc, wb, A, lut, lo, bo, counts);
+    return launch_pdl(kern, grid, dim3(kRpnRoPx), smem, st, reinterpret_cast<const T*>(trains), C, HW, wc, wb, n_a, n_b, lut, lo, bo, counts);
 }
 
 template <typename T>
@@ -625,6 +626,7 @@ void snn_set_role_timers(unsigned long long* device_counters, int phase) {
     g_role_phase = phase;
 }
 void snn_set_clock_probe(unsigned long long* device_counters) { g_clock_probe = device_counters; }
+void snn_set_roi_kernel(int which) { g_roi_kernel = which == 1 ? 1 : 0; }
 void snn_host_cache_stats(unsigned long long* hits, unsigned long long* misses) {
     if (hits) *hits = g_tmap_hits;
     if (misses) *misses = g_tmap_misses;
@@ -830,9 +832,9 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
         cudaError_t e;
         float* lo = reinterpret_cast<float*>(logits_out[l]);
         float* bo = reinterpret_cast<float*>(bbox_out[l]);
-        if (tb == 1) e = launch_readout_rpn<uint8_t>(trains[l], C_in, H[l] * W[l], N, w_cls, w_bbox, A, lut, lo, bo, cnt, st);
-        else if (tb == 2) e = launch_readout_rpn<uint16_t>(trains[l], C_in, H[l] * W[l], N, w_cls, w_bbox, A, lut, lo, bo, cnt, st);
-        else e = launch_readout_rpn<uint32_t>(trains[l], C_in, H[l] * W[l], N, w_cls, w_bbox, A, lut, lo, bo, cnt, st);
+        if (tb == 1) e = launch_readout_rpn<uint8_t>(trains[l], C_in, H[l] * W[l], N, w_cls, A, w_bbox, 4 * A, lut, lo, bo, cnt, st);
+        else if (tb == 2) e = launch_readout_rpn<uint16_t>(trains[l], C_in, H[l] * W[l], N, w_cls, A, w_bbox, 4 * A, lut, lo, bo, cnt, st);
+        else e = launch_readout_rpn<uint32_t>(trains[l], C_in, H[l] * W[l], N, w_cls, A, w_bbox, 4 * A, lut, lo, bo, cnt, st);
         if (e != cudaSuccess) return fail(SNN_E_CUDA, "readout_rpn launch failed: %s", cudaGetErrorString(e));
         ++g_launches;
     }
@@ -960,9 +962,27 @@ int snn_roi_align_encode(const void* const* feat_ptrs, const int* H, const int* 
     p.n_levels = n_levels; p.C = C; p.R = R; p.P = pooled_size; p.sampling = sampling_ratio; p.T_live = T_live;
     p.wb = word_bytes(T_live);
     p.rois = rois; p.roi_level = roi_level; p.words = reinterpret_cast<uint8_t*>(words_out); p.pooled = pooled_out;
-    const size_t items = static_cast<size_t>(R) * pooled_size * pooled_size * ((C + kRoiChPerThread - 1) / kRoiChPerThread);
-    const int blocks = static_cast<int>((items + 255) / 256 > 148 * 32 ? 148 * 32 : (items + 255) / 256);
-    SNN_ENC_BUCKETS(T_live, (roi_align_encode_kernel<NT><<<blocks, 256, 0, (cudaStream_t)stream>>>(p)));
+    // Faster R-CNN's pooler (7 x 7 bins, 2 x 2 samples per bin): one block per RoI, its feature window staged in shared
+    // memory; adaptive sampling grids / larger poolers take the per-thread kernel
+    const bool staged = (sampling_ratio == 1 || sampling_ratio == 2) && pooled_size <= kRoiMaxP && g_roi_kernel != 1;
+    if (staged) {
+        DeviceInfo di;
+        int rc = device_info(di);
+        if (rc) return rc;
+        const size_t smem = static_cast<size_t>(kRoiChunk) * kRoiPlaneMax * sizeof(float);
+        const int blocks = R < di.sms * 4 ? R : di.sms * 4;
+        cudaError_t e = cudaSuccess;
+        SNN_ENC_BUCKETS(T_live, {
+            auto kern = roi_align_encode_staged_kernel<NT>;
+            e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
+            if (e == cudaSuccess) kern<<<blocks, kRoiStagedThreads, smem, (cudaStream_t)stream>>>(p);
+        });
+        if (e != cudaSuccess) return fail(SNN_E_CUDA, "roi_align_encode: %s", cudaGetErrorString(e));
+    } else {
+        const size_t items = static_cast<size_t>(R) * pooled_size * pooled_size * ((C + kRoiChPerThread - 1) / kRoiChPerThread);
+        const int blocks = static_cast<int>((items + 255) / 256 > 148 * 32 ? 148 * 32 : (items + 255) / 256);
+        SNN_ENC_BUCKETS(T_live, (roi_align_encode_kernel<NT><<<blocks, 256, 0, (cudaStream_t)stream>>>(p)));
+    }
     CUDA_TRY(cudaGetLastError());
     return SNN_OK;
 }
@@ -1020,6 +1040,44 @@ int snn_rpn_topk_keys(const void* const* logits, const int* H, const int* W, int
     const long long want = (total + 255) / 256;
     rpn_topk_keys_kernel<<<static_cast<int>(want < 148 * 8 ? want : 148 * 8), 256, 0, (cudaStream_t)stream>>>(p);
     CUDA_TRY(cudaGetLastError());
+    return SNN_OK;
+}
+
+// ---- linear statistics of spike trains (the spike-rate / energy report, rates.py)
+int snn_li_readout_nhwc(const void* trains, int train_bytes, int N, int HW, int C, const double* step_weights,
+                        const float* w_a, int n_a, const float* w_b, int n_b, float* out_a, float* out_b,
+                        snn_stream_t stream) {
+    if (!trains || !step_weights || !w_a || !w_b || !out_a || !out_b) return fail(SNN_E_ARG, "li_readout_nhwc: null argument");
+    if (N < 1 || HW < 1 || C < 1 || n_a < 1 || n_b < 1 || (train_bytes != 1 && train_bytes != 2 && train_bytes != 4) ||
+        (C * train_bytes) % 4 != 0)
+        return fail(SNN_E_ARG, "li_readout_nhwc: unsupported sizes (N %d, HW %d, C %d, outputs %d + %d, %d-byte words)", N, HW, C,
+                    n_a, n_b, train_bytes);
+    KappaTable kt;
+    for (int t = 0; t < 32; ++t) kt.k[t] = (t < 8 * train_bytes) ? step_weights[t] : 0.0;
+    cudaError_t e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (train_bytes == 1) e = launch_readout_rpn<uint8_t>(trains, C, HW, N, w_a, n_a, w_b, n_b, kt, out_a, out_b, nullptr, st);
+    else if (train_bytes == 2) e = launch_readout_rpn<uint16_t>(trains, C, HW, N, w_a, n_a, w_b, n_b, kt, out_a, out_b, nullptr, st);
+    else e = launch_readout_rpn<uint32_t>(trains, C, HW, N, w_a, n_a, w_b, n_b, kt, out_a, out_b, nullptr, st);
+    if (e != cudaSuccess) return fail(SNN_E_CUDA, "li_readout_nhwc launch failed: %s", cudaGetErrorString(e));
+    return SNN_OK;
+}
+
+int snn_li_readout_rows(const void* trains, int train_bytes, int R, int Hd, const double* step_weights, const float* w_a,
+                        int n_a, const float* w_b, int n_b, float* out_a, float* out_b, snn_stream_t stream) {
+    if (!trains || !step_weights || !w_a || !w_b || !out_a || !out_b) return fail(SNN_E_ARG, "li_readout_rows: null argument");
+    if (R < 1 || Hd < 1 || n_a < 1 || n_b < 1 || (train_bytes != 1 && train_bytes != 2 && train_bytes != 4) ||
+        (Hd * train_bytes) % 16 != 0 || Hd % 4 != 0)
+        return fail(SNN_E_ARG, "li_readout_rows: unsupported sizes (R %d, Hd %d, outputs %d + %d, %d-byte words)", R, Hd, n_a, n_b,
+                    train_bytes);
+    KappaTable kt;
+    for (int t = 0; t < 32; ++t) kt.k[t] = (t < 8 * train_bytes) ? step_weights[t] : 0.0;
+    cudaError_t e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (train_bytes == 1) e = launch_readout_rows<uint8_t>(trains, nullptr, R, Hd, w_a, n_a, w_b, n_b, kt, out_a, out_b, nullptr, st);
+    else if (train_bytes == 2) e = launch_readout_rows<uint16_t>(trains, nullptr, R, Hd, w_a, n_a, w_b, n_b, kt, out_a, out_b, nullptr, st);
+    else e = launch_readout_rows<uint32_t>(trains, nullptr, R, Hd, w_a, n_a, w_b, n_b, kt, out_a, out_b, nullptr, st);
+    if (e != cudaSuccess) return fail(SNN_E_CUDA, "li_readout_rows launch failed: %s", cudaGetErrorString(e));
     return SNN_OK;
 }
 
