@@ -120,8 +120,34 @@ def main():
     def fused_pool():
         return fused(fmaps, props, [IMG] * N)
 
+    # the fused kernel alone (C ABI call, inputs prepared), staged (one block per RoI, window in shared memory) against
+    # the per-thread kernel of round 1
+    from torchvision.ops.poolers import _setup_scales, _convert_to_roi_format
+    fl = [fmaps[k] for k in ("0", "1", "2", "3")]
+    scales, mapper = _setup_scales(fl, [IMG] * N, 224, 4)
+    rois5 = _convert_to_roi_format(props).float().contiguous()
+    lv = mapper(props).to(torch.int32).contiguous()
+    words = torch.empty(N * R, 12544, dtype=torch.int16, device=dev)
+    VP, IA, FA = ctypes.c_void_p * 4, ctypes.c_int * 4, ctypes.c_float * 4
+
+    def roi_kernel_only():
+        rc = lib.snn_roi_align_encode(VP(*[f.data_ptr() for f in fl]), IA(*[f.shape[2] for f in fl]), IA(*[f.shape[3] for f in fl]),
+                                      FA(*[float(s_) for s_ in scales]), 4, 256, ctypes.c_void_p(rois5.data_ptr()),
+                                      ctypes.c_void_p(lv.data_ptr()), N * R, 7, 2, 11, ctypes.c_void_p(words.data_ptr()), None,
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+
+    t_staged = timed(roi_kernel_only, iters=50)
+    w_staged = words.clone()
+    lib.snn_set_roi_kernel(1)
+    t_thread = timed(roi_kernel_only, iters=50)
+    lib.snn_set_roi_kernel(0)
+    same_words = (w_staged == words).float().mean().item()
     line = {"rows": "SURVEY 8f-1 / 8f-2 / 8f-4",
-            "roi_align_encode_ms": {"torchvision_roi_align_then_encoder": timed(pool_then_encode), "fused": timed(fused_pool)}, "shapes": "cityscapes batch 2 (294 624 anchors/img, 1000 RoIs/img)",
+            "roi_align_encode_ms": {"torchvision_roi_align_then_encoder": timed(pool_then_encode), "fused": timed(fused_pool),
+                                    "kernel_only_staged": t_staged, "kernel_only_per_thread": t_thread,
+                                    "words_equal_between_kernels": same_words},
+            "shapes": "cityscapes batch 2 (294 624 anchors/img, 1000 RoIs/img)",
             "rpn_select_ms": {"reference_path": timed(reference_path), "ours": timed(ours)},
             "postprocess_ms": {"reference_python_mask_loop_only": timed(loop_mask_only, iters=3), "ours_whole_function": timed(vectorised)}}
     print(json.dumps(line))

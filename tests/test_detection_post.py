@@ -187,6 +187,7 @@ def test_topk_ties_are_broken_in_the_references_order():
     the k boundary are real.  The reference takes top-k on the (H, W, A)-flattened logits (rpn.py:248-259, 468-472);
     the selection here must be "largest first, ties by the lowest reference index" -- a stable descending sort of the
     reference-ordered tensor."""
+    import snn_automotive_object_detection_b200 as S
     torch.manual_seed(11)
     N, A, H, W = 2, 3, 20, 30
     logits = torch.zeros(N, A, H, W)
