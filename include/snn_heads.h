@@ -133,8 +133,7 @@ int snn_fc_lif_layer(const void* z_words, int in_word_bytes, int in_bit0, int R,
 int snn_roi_align_encode(const void* const* feat_ptrs, const int* H, const int* W, const float* scales, int n_levels,
                          int C, const float* rois, const int* roi_level, int R, int pooled_size, int sampling_ratio,
                          int T_live, void* words_out, float* pooled_out, snn_stream_t stream);
-/* tests / A-B timing: 0 = auto (one block per RoI with its feature window staged in shared memory for the fixed 1 x 1 or
- * 2 x 2 sampling grids and pooled_size <= 8), 1 = always the per-thread kernel (any sampling grid) */
+/* A-B timing: 0 = two channel planes (32 loads) in flight per thread, 1 = four (64 loads, one block fewer per SM) */
 void snn_set_roi_kernel(int which);
 /* snn_box_head_forward on input that is already encoded: words [R][K] of snn_train_word_bytes-like size for T - 1 steps
  * (1/2/4 bytes for T - 1 <= 8/16/32), e.g. from snn_roi_align_encode(..., T_live = T - 1, ...). */

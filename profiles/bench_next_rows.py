@@ -120,8 +120,7 @@ def main():
     def fused_pool():
         return fused(fmaps, props, [IMG] * N)
 
-    # the fused kernel alone (C ABI call, inputs prepared), staged (one block per RoI, window in shared memory) against
-    # the per-thread kernel of round 1
+    # the fused kernel alone (C ABI call, inputs prepared): two against four channel planes in flight per thread
     from torchvision.ops.poolers import _setup_scales, _convert_to_roi_format
     fl = [fmaps[k] for k in ("0", "1", "2", "3")]
     scales, mapper = _setup_scales(fl, [IMG] * N, 224, 4)
@@ -145,7 +144,7 @@ def main():
     same_words = (w_staged == words).float().mean().item()
     line = {"rows": "SURVEY 8f-1 / 8f-2 / 8f-4",
             "roi_align_encode_ms": {"torchvision_roi_align_then_encoder": timed(pool_then_encode), "fused": timed(fused_pool),
-                                    "kernel_only_staged": t_staged, "kernel_only_per_thread": t_thread,
+                                    "kernel_only_unroll2": t_staged, "kernel_only_unroll4": t_thread,
                                     "words_equal_between_kernels": same_words},
             "shapes": "cityscapes batch 2 (294 624 anchors/img, 1000 RoIs/img)",
             "rpn_select_ms": {"reference_path": timed(reference_path), "ours": timed(ours)},

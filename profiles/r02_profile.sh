@@ -12,6 +12,15 @@ ncu --set full --clock-control none -k regex:"encode_|readout_" -s 9 -c 3 -o gpu
 ncu --set full --clock-control none --import-source on -k regex:spike_gemm_lif -s 12 -c 4 -o gpurun_out/${TAG}_gemm_bdd_bf16 $CMD --mode bf16 --workload bdd --batch 4 > gpurun_out/${TAG}_gemm_bdd_bf16.log 2>&1
 # fused RoIAlign kernels
 ncu --set full --clock-control none -k regex:roi_align -s 6 -c 2 -o gpurun_out/${TAG}_roi python profiles/bench_next_rows.py > gpurun_out/${TAG}_roi.log 2>&1
+# gpurun brings back at most 64 MiB: export the pages read here (raw metrics; per-line source counters of the GEMMs) on
+# the box and drop the .ncu-rep files
+for R in gemm_fp16x2 aux_fp16x2 gemm_bdd_bf16 roi; do
+  F=gpurun_out/${TAG}_${R}.ncu-rep
+  [ -f $F ] || continue
+  ncu -i $F --page raw --csv > gpurun_out/${TAG}_${R}_raw.csv 2>/dev/null
+  case $R in gemm_*) ncu -i $F --page source --csv --print-source sass > gpurun_out/${TAG}_${R}_source.csv 2>/dev/null; gzip -f gpurun_out/${TAG}_${R}_source.csv;; esac
+  rm -f $F
+done
 ls -la gpurun_out | grep ${TAG}
 # timed (no profiler): next rows, configs 3 / 4 / 5 (N = 1 leg), energy sweep, long run with NVML power
 timeout 300 python profiles/bench_next_rows.py > gpurun_out/${TAG}_next_rows.json 2> gpurun_out/${TAG}_next_rows.err; cat gpurun_out/${TAG}_next_rows.json

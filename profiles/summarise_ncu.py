@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Summarise .ncu-rep captures (brought back in gpurun_out/) into small CSVs under profiles/.
-Usage: python profiles/summarise_ncu.py gpurun_out/<tag>_gemm_<mode>.ncu-rep [...]"""
+Usage: python profiles/summarise_ncu.py gpurun_out/<tag>_gemm_<mode>.ncu-rep | gpurun_out/<tag>_..._raw.csv [...]
+(a *_raw.csv is the `ncu -i <rep> --page raw --csv` export made on the GPU box: gpurun returns at most 64 MiB)"""
 import csv
 import io
 import os
@@ -23,11 +24,14 @@ METRICS = [
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
     for rep in sys.argv[1:]:
-        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if rep.endswith(".csv"):
+            out = open(rep).read()
+        else:
+            out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(out)))
         hdr, units = rows[0], rows[1]
         col = {h: i for i, h in enumerate(hdr)}
-        name = os.path.splitext(os.path.basename(rep))[0] + "_summary.csv"
+        name = os.path.splitext(os.path.basename(rep))[0].replace("_raw", "") + "_summary.csv"
         with open(os.path.join(here, name), "w", newline="") as f:
             w = csv.writer(f)
             # every tensor-pipe counter the capture holds (the guide's sm__pipe_tensor_cycles_active among them)

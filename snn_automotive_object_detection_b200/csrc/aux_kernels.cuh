@@ -648,7 +648,6 @@ __device__ __forceinline__ RoiSample roi_prepare(int H, int W, float y, float x)
 }
 
 constexpr int kRoiChPerThread = 64;
-constexpr int kRoiUnroll = 2;
 
 // Thread = (RoI, bin (ph, pw), group of 64 channels).  The sampling grid of a bin -- positions, border rules and the
 // four bilinear weights of each sample -- depends on the RoI and the bin only, so it is prepared ONCE (up to 2 x 2
@@ -657,8 +656,16 @@ constexpr int kRoiUnroll = 2;
 // (the first version: 8 consecutive k = c*PP + bin per thread).  Consecutive threads are consecutive bins of a RoI, so
 // a warp's loads fall into a few rows of one channel plane and its stores are consecutive words.
 // Other sampling grids (adaptive, or more than 4 samples per bin) take the per-channel path.
-template <int NT>
-__global__ void __launch_bounds__(256, 3) roi_align_encode_kernel(const __grid_constant__ RoiEncParams p) {
+// What bounds it (r02b): not DRAM (8.6 %) but the L1 data path.  A 2 x 2 x 49 sampling grid over a window of 15-29
+// pixels a side (torchvision's level mapping puts a RoI of 112-224 px on the stride-8 level, i.e. 14-28 feature
+// pixels) reads almost every pixel of the window exactly once per channel, so there is no reuse for shared-memory
+// staging to exploit -- a version with one block per RoI and the window staged in shared memory was 4x SLOWER
+// (1.21 vs 0.30 ms, profiles/r02/r02b_next_rows.json) and was dropped -- and every warp-level load touches ~8 cache lines
+// for its 32 lanes: 401 M lane-loads = 12.5 M warp-loads x ~8 wavefronts / (148 SMs x 1 wavefront/clk) = 0.36 ms at
+// 1.9 GHz, the measured 0.30 ms.  The useful bytes alone (<= 784 floats per RoI and channel, 1.6 GB per 2000 RoIs)
+// are 0.28 ms of L2 -> SM bandwidth.  kRoiUnroll channel planes per iteration keep 16 x kRoiUnroll loads in flight.
+template <int NT, int kRoiUnroll>
+__global__ void __launch_bounds__(256, kRoiUnroll <= 2 ? 3 : 2) roi_align_encode_kernel(const __grid_constant__ RoiEncParams p) {
     const uint32_t tmask = (p.T_live >= 32) ? 0xFFFFFFFFu : ((1u << p.T_live) - 1u);
     const int PP = p.P * p.P;
     const int K = p.C * PP;
@@ -745,147 +752,6 @@ __global__ void __launch_bounds__(256, 3) roi_align_encode_kernel(const __grid_c
                 if (p.wb == 1) p.words[o] = static_cast<uint8_t>(w);
                 else if (p.wb == 2) reinterpret_cast<uint16_t*>(p.words)[o] = static_cast<uint16_t>(w);
                 else reinterpret_cast<uint32_t*>(p.words)[o] = w;
-            }
-        }
-    }
-}
-
-// ---- staged version: one block per RoI, the RoI's feature window in shared memory
-// ncu of the per-thread kernel above (r01ba): DRAM 8.6 %, issue 33 % -- its 16 scattered 4-byte global loads per output
-// (401 M per 2000 RoIs, each warp instruction several L1 wavefronts) bound it.  A RoI only touches a small window of
-// its FPN level (at torchvision's level mapping 7-14 pixels across, +1 for the bilinear corner), every pixel of which
-// is read by several samples of several bins.  Here a block owns one RoI: it derives the 2 x P sample coordinates per
-// axis ONCE (the border rules of roi_align are separable: a sample is dropped if either coordinate is out of range,
-// clamped per axis, and its four weights are products hy|ly x hx|lx), stages the window of 32 channels at a time in
-// shared memory with coalesced row loads, and thread = (bin, channel lane) evaluates its bin -- 16 (offset, weight)
-// pairs kept in registers -- from shared memory for every channel of the chunk, feeding the comparator-bank encoder.
-// The words of a channel's P x P bins are contiguous, so a warp's stores are contiguous runs.
-// The sums are evaluated in torchvision's order (w1*v1 + w2*v2 + w3*v3 + w4*v4 per sample, samples row-major, one
-// division by the sample count).  A RoI whose window does not fit (kRoiPlaneMax floats per channel) reads global
-// memory directly with the same thread mapping.
-constexpr int kRoiChunk = 32;          // channels staged per pass
-constexpr int kRoiPlaneMax = 384;      // floats per staged channel plane (window rows x pitch): 48 KB per block
-constexpr int kRoiMaxP = 8;            // pooled size supported by the staged kernel (Faster R-CNN: 7)
-constexpr int kRoiStagedThreads = 256;
-
-struct RoiAxisSample { int lo, hi; float wl, wh; };      // corner indices (clamped) and weights (0, 0 = dropped)
-
-// one coordinate of torchvision's bilinear_interpolate (roi_align_kernel.cu): drop / clamp / split into corners
-__device__ __forceinline__ RoiAxisSample roi_axis_sample(float v, int size) {
-    RoiAxisSample s{0, 0, 0.f, 0.f};
-    if (v < -1.0f || v > static_cast<float>(size)) return s;
-    if (v <= 0.f) v = 0.f;
-    int lo = static_cast<int>(v), hi;
-    if (lo >= size - 1) { hi = lo = size - 1; v = static_cast<float>(lo); } else { hi = lo + 1; }
-    const float l = v - lo;
-    s.lo = lo; s.hi = hi; s.wh = l; s.wl = 1.f - l;      // wl multiplies the low corner (hy / hx), wh the high one
-    return s;
-}
-
-template <int NT>
-__global__ void __launch_bounds__(kRoiStagedThreads, 3) roi_align_encode_staged_kernel(const __grid_constant__ RoiEncParams p) {
-    extern __shared__ float s_win[];                       // [kRoiChunk][plane]
-    __shared__ RoiAxisSample s_ax[2][2 * kRoiMaxP];        // [y | x][bin index * 2 + sample]
-    const uint32_t tmask = (p.T_live >= 32) ? 0xFFFFFFFFu : ((1u << p.T_live) - 1u);
-    const int P = p.P, PP = P * P, G = p.sampling;         // G = 1 or 2 samples per bin and axis (host-checked)
-    const int K = p.C * PP;
-    const int t = static_cast<int>(threadIdx.x);
-    const int lanes = kRoiStagedThreads / PP;              // channel lanes (5 for P = 7)
-    const int bin = t % PP, csub = t / PP;
-    const bool worker = csub < lanes;
-    const int ph = bin / P, pw = bin - ph * P;
-    for (int r = blockIdx.x; r < p.R; r += gridDim.x) {
-        const float* roi = p.rois + 5 * static_cast<size_t>(r);
-        const RoiLevel& L = p.lv[p.roi_level[r]];
-        const int b = static_cast<int>(roi[0]);
-        const float rsw = roi[1] * L.scale, rsh = roi[2] * L.scale, rew = roi[3] * L.scale, reh = roi[4] * L.scale;
-        const float roi_w = fmaxf(rew - rsw, 1.f), roi_h = fmaxf(reh - rsh, 1.f);
-        const float bin_h = roi_h / static_cast<float>(P), bin_w = roi_w / static_cast<float>(P);
-        const float count = fmaxf(static_cast<float>(G * G), 1.f);
-        __syncthreads();                                   // the previous RoI's readers of s_ax / s_win are done
-        if (t < 4 * P) {                                   // 2P samples per axis
-            const int axis = t / (2 * P), i = t - axis * 2 * P;
-            const int pb = i >> 1, is = i & 1;
-            RoiAxisSample s{0, 0, 0.f, 0.f};
-            if (is < G) {
-                if (axis == 0) s = roi_axis_sample(rsh + pb * bin_h + static_cast<float>(is + .5f) * bin_h / static_cast<float>(G), L.H);
-                else s = roi_axis_sample(rsw + pb * bin_w + static_cast<float>(is + .5f) * bin_w / static_cast<float>(G), L.W);
-            }
-            s_ax[axis][i] = s;
-        }
-        __syncthreads();
-        // window of the level this RoI touches (every thread derives it from the 4P samples)
-        int y0 = L.H, y1 = -1, x0 = L.W, x1 = -1;
-        for (int i = 0; i < 2 * P; ++i) {
-            const RoiAxisSample sy = s_ax[0][i], sx = s_ax[1][i];
-            if (sy.wl != 0.f || sy.wh != 0.f) { y0 = min(y0, sy.lo); y1 = max(y1, sy.hi); }
-            if (sx.wl != 0.f || sx.wh != 0.f) { x0 = min(x0, sx.lo); x1 = max(x1, sx.hi); }
-        }
-        if (y1 < y0) { y0 = 0; y1 = 0; }                   // no valid sample on an axis: every output is zero
-        if (x1 < x0) { x0 = 0; x1 = 0; }
-        const int Hw = y1 - y0 + 1, Ww = x1 - x0 + 1;
-        const int pitch = Ww | 1;                          // odd row pitch: rows of a bin column fall in different banks
-        const int plane = Hw * pitch;
-        const bool staged = plane <= kRoiPlaneMax;
-        // this thread's bin: 4 samples x 4 corners, offsets into the staged window (or the global plane) and weights
-        int off[16];
-        float wgt[16];
-#pragma unroll
-        for (int iy = 0; iy < 2; ++iy)
-#pragma unroll
-            for (int ix = 0; ix < 2; ++ix) {
-                const RoiAxisSample sy = s_ax[0][ph * 2 + iy], sx = s_ax[1][pw * 2 + ix];
-                const int q = (iy * 2 + ix) * 4;
-                const int rl = staged ? (sy.lo - y0) * pitch : sy.lo * L.W, rh = staged ? (sy.hi - y0) * pitch : sy.hi * L.W;
-                const int cl = staged ? sx.lo - x0 : sx.lo, chh = staged ? sx.hi - x0 : sx.hi;
-                const bool live = (sy.wl != 0.f || sy.wh != 0.f) && (sx.wl != 0.f || sx.wh != 0.f);
-                off[q + 0] = live ? rl + cl : 0; off[q + 1] = live ? rl + chh : 0;
-                off[q + 2] = live ? rh + cl : 0; off[q + 3] = live ? rh + chh : 0;
-                wgt[q + 0] = sy.wl * sx.wl; wgt[q + 1] = sy.wl * sx.wh; wgt[q + 2] = sy.wh * sx.wl; wgt[q + 3] = sy.wh * sx.wh;
-            }
-        const size_t hw = static_cast<size_t>(L.H) * L.W;
-        const float* fb = L.x + static_cast<size_t>(b) * p.C * hw;
-        const size_t out_r = static_cast<size_t>(r) * K;
-        for (int c0 = 0; c0 < p.C; c0 += kRoiChunk) {
-            const int nc = min(kRoiChunk, p.C - c0);
-            if (staged) {
-                __syncthreads();                           // the previous chunk's readers are done
-                const int tx = t & 15, ty = t >> 4;
-                int c = 0, yy = ty;
-                while (yy >= Hw) { yy -= Hw; ++c; }
-                while (c < nc) {
-                    const float* src = fb + static_cast<size_t>(c0 + c) * hw + static_cast<size_t>(y0 + yy) * L.W + x0;
-                    float* dst = s_win + c * plane + yy * pitch;
-                    for (int xx = tx; xx < Ww; xx += 16) dst[xx] = __ldg(src + xx);
-                    yy += kRoiStagedThreads / 16;
-                    while (yy >= Hw) { yy -= Hw; ++c; }
-                }
-                __syncthreads();
-            }
-            if (worker) {
-                for (int c = csub; c < nc; c += lanes) {
-                    float v[16];
-                    if (staged) {
-                        const float* f = s_win + c * plane;
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) v[q] = f[off[q]];
-                    } else {
-                        const float* f = fb + static_cast<size_t>(c0 + c) * hw;
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) v[q] = __ldg(f + off[q]);
-                    }
-                    float acc = 0.f;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        acc += wgt[4 * q] * v[4 * q] + wgt[4 * q + 1] * v[4 * q + 1] + wgt[4 * q + 2] * v[4 * q + 2] + wgt[4 * q + 3] * v[4 * q + 3];
-                    const float val = acc / count;
-                    const size_t o = out_r + static_cast<size_t>(c0 + c) * PP + bin;
-                    if (p.pooled != nullptr) p.pooled[o] = val;
-                    const uint32_t w = encode_word<NT>(val, tmask);
-                    if (p.wb == 1) p.words[o] = static_cast<uint8_t>(w);
-                    else if (p.wb == 2) reinterpret_cast<uint16_t*>(p.words)[o] = static_cast<uint16_t>(w);
-                    else reinterpret_cast<uint32_t*>(p.words)[o] = w;
-                }
             }
         }
     }

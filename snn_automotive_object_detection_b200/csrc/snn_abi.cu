@@ -28,7 +28,7 @@ thread_local int g_force_cg = 0;
 thread_local int g_fc_dual = 0;      // 0 auto, 1 never, 2 whenever the tile shape allows it (tests)
 thread_local int g_fc_units = 0;     // > 0: cap on the units per fc tile (experiments)
 thread_local int g_fc_split = 0;
-thread_local int g_roi_kernel = 0;   // 0 auto, 1 force the per-thread RoIAlign kernel (tests / A-B timing)
+thread_local int g_roi_kernel = 0;   // 0 = two channel planes in flight per thread, 1 = four (A-B timing)
 thread_local unsigned long long* g_role_cycles = nullptr;   // profiling: MMA-thread wait counters of the next launches
 thread_local int g_role_phase = -1;                        // which launch gets them: 0 conv, 1 / 3 fc with K >= 4096 in dual / single tiles, 2 other fc     // 1: never run the last partial wave of dual tiles as single tiles (experiments)
 
@@ -962,26 +962,12 @@ int snn_roi_align_encode(const void* const* feat_ptrs, const int* H, const int* 
     p.n_levels = n_levels; p.C = C; p.R = R; p.P = pooled_size; p.sampling = sampling_ratio; p.T_live = T_live;
     p.wb = word_bytes(T_live);
     p.rois = rois; p.roi_level = roi_level; p.words = reinterpret_cast<uint8_t*>(words_out); p.pooled = pooled_out;
-    // Faster R-CNN's pooler (7 x 7 bins, 2 x 2 samples per bin): one block per RoI, its feature window staged in shared
-    // memory; adaptive sampling grids / larger poolers take the per-thread kernel
-    const bool staged = (sampling_ratio == 1 || sampling_ratio == 2) && pooled_size <= kRoiMaxP && g_roi_kernel != 1;
-    if (staged) {
-        DeviceInfo di;
-        int rc = device_info(di);
-        if (rc) return rc;
-        const size_t smem = static_cast<size_t>(kRoiChunk) * kRoiPlaneMax * sizeof(float);
-        const int blocks = R < di.sms * 4 ? R : di.sms * 4;
-        cudaError_t e = cudaSuccess;
-        SNN_ENC_BUCKETS(T_live, {
-            auto kern = roi_align_encode_staged_kernel<NT>;
-            e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), static_cast<int>(smem));
-            if (e == cudaSuccess) kern<<<blocks, kRoiStagedThreads, smem, (cudaStream_t)stream>>>(p);
-        });
-        if (e != cudaSuccess) return fail(SNN_E_CUDA, "roi_align_encode: %s", cudaGetErrorString(e));
+    const size_t items = static_cast<size_t>(R) * pooled_size * pooled_size * ((C + kRoiChPerThread - 1) / kRoiChPerThread);
+    const int blocks = static_cast<int>((items + 255) / 256 > 148 * 32 ? 148 * 32 : (items + 255) / 256);
+    if (g_roi_kernel == 1) {
+        SNN_ENC_BUCKETS(T_live, (roi_align_encode_kernel<NT, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(p)));
     } else {
-        const size_t items = static_cast<size_t>(R) * pooled_size * pooled_size * ((C + kRoiChPerThread - 1) / kRoiChPerThread);
-        const int blocks = static_cast<int>((items + 255) / 256 > 148 * 32 ? 148 * 32 : (items + 255) / 256);
-        SNN_ENC_BUCKETS(T_live, (roi_align_encode_kernel<NT><<<blocks, 256, 0, (cudaStream_t)stream>>>(p)));
+        SNN_ENC_BUCKETS(T_live, (roi_align_encode_kernel<NT, 2><<<blocks, 256, 0, (cudaStream_t)stream>>>(p)));
     }
     CUDA_TRY(cudaGetLastError());
     return SNN_OK;

@@ -123,14 +123,12 @@ def test_ref_index_points_at_the_reference_anchor(golden_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kernel", ["staged", "per_thread"])
+@pytest.mark.parametrize("kernel", ["unroll2", "unroll4"])
 @pytest.mark.parametrize("names,sampling", [(["0", "1", "2", "3"], 2), (["0"], 2), (["0", "1", "2", "3"], 1), (["1"], 0)])
 def test_fused_roi_align_encoder_matches_torchvision_pool_then_encode(names, sampling, kernel):
     """RoIAlign fused with the box head's encoder against torchvision's MultiScaleRoIAlign followed by
-    the head's own encoder, and the box head outputs on both inputs.  Both kernels: one block per RoI with the RoI's
-    feature window staged in shared memory (windows that do not fit -- every large RoI of the single-level "0" pooler --
-    read global memory with the same thread mapping), and the per-thread kernel (also the only one for the adaptive
-    sampling grid, sampling_ratio 0)."""
+    the head's own encoder, and the box head outputs on both inputs; multi-level and single-level poolers, fixed 2 x 2 and
+    1 x 1 sampling grids and torchvision's adaptive grid (sampling_ratio 0), both unroll variants of the kernel."""
     from collections import OrderedDict
     from torchvision.ops import MultiScaleRoIAlign
     from oracle import snn_oracle as O
@@ -156,7 +154,7 @@ def test_fused_roi_align_encoder_matches_torchvision_pool_then_encode(names, sam
     fused = S.FusedRoIAlignEncoder.from_pooler(pooler, T)
     fused.return_pooled = True
     lib = _lib.load()
-    lib.snn_set_roi_kernel(1 if kernel == "per_thread" else 0)
+    lib.snn_set_roi_kernel(1 if kernel == "unroll4" else 0)
     try:
         enc = fused(feats, props, shapes)
         torch.cuda.synchronize()

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 def test_library_reports_version_and_rejects_bad_args():
     lib = _lib.load()
-    assert lib.snn_version() == 4
+    assert lib.snn_version() == _lib.EXPECTED_ABI
     rc = lib.snn_fc_lif_layer(None, 1, 0, 1, 64, 128, 8, 0, 7, 0, None, None, None, 0, None)
     assert rc == -1 and b"null" in lib.snn_last_error()
 
