@@ -699,7 +699,7 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
     // The LI readout (and the spike counts) are fused into the GEMM epilogue when a CTA pair covers all
     // output channels (cta_group 2, C_in == 256) and the 5A outputs fit one pass; otherwise a separate
     // readout kernel consumes the spike trains (and needs the kappa lookup table).
-    const bool fused = T_live > 0 && tc.cg == 2 && C_in == 256 && 5 * A <= kRoMaxOut;
+    const bool fused = T_live > 0 && tc.cg == 2 && tc.CW == 8 && C_in == 256 && 5 * A <= kRoMaxOut;
     void* trains[kMaxLevels];
     for (int l = 0; l < n_levels; ++l) {
         trains[l] = (spike_trains_out && spike_trains_out[l]) ? spike_trains_out[l] : (wsp + ws.tr_off[l]);

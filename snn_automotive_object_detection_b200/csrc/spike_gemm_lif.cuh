@@ -142,6 +142,24 @@ __device__ __forceinline__ bool lif_update(float& v, float& i, float cur) {
     i = __fadd_rn(i_dec, cur);
     return z;
 }
+// The same with the input current given as (raw accumulator, power-of-two row scale): acc * scale is exact, so the one
+// rounding of fma(acc, scale, i_dec) is the rounding of i_dec + cur -- bit-identical, one instruction less per step.
+__device__ __forceinline__ bool lif_update_scaled(float& v, float& i, float acc, float scale) {
+    const float dv = __fmul_rn(0.1f, __fsub_rn(i, v));
+    const float v_dec = __fadd_rn(v, dv);
+    const float i_dec = __fadd_rn(i, __fmul_rn(-0.2f, i));
+    const bool z = v_dec > 0.1f;
+    v = z ? 0.0f : v_dec;
+    i = __fmaf_rn(acc, scale, i_dec);
+    return z;
+}
+// named barriers of the fused readout (conv): the epilogue warps hand the kappa-weighted spike sums of an 8-pixel chunk
+// to the readout warp through two shared-memory buffers
+constexpr int kBarRoFull = 2;               // + buffer: chunk written (128 epilogue threads arrive, the readout warp syncs)
+constexpr int kBarRoFree = 4;               // + buffer: chunk consumed (the readout warp arrives, the epilogue threads sync)
+constexpr int kRoBarThreads = 128 + 32;
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // Decoded position of a unit tile.
 struct TilePos { int lvl, n, h0, w0; };
@@ -363,6 +381,73 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 }
             }
         }
+    } else if (warp == 2) {
+        // ===================================================== fused LI readout (conv): out[o][px] += sum_c W[o][c] * sk[c][px]
+        // The epilogue warps stage the kappa-weighted spike sums of an 8-pixel chunk ([8 px][128 ch of this CTA]) in one
+        // of two shared-memory buffers; this warp (idle after the TMEM allocation) runs the 16 outputs x 8 pixels dot
+        // products and adds them to the zeroed outputs (two commutative adds per output, one per CTA of the pair:
+        // deterministic).  ncu r02c (bf16, where the epilogue bounds the conv): the readout was 27 % of the epilogue
+        // warps' samples plus a barrier per chunk; here it overlaps the LIF recurrence of the next chunk.
+        if constexpr (kConv && CW == 8) {
+            if (p.fuse_readout != 0) {
+                const int c0 = static_cast<int>(rank) * 128;
+                const int n_out = 5 * p.A;
+                for (int i = lane; i < kRoMaxOut * 128; i += 32) {
+                    const int o = i >> 7, cc = i & 127;
+                    float wv = 0.f;
+                    if (o < p.A) wv = p.w_cls[o * p.m_total + c0 + cc];
+                    else if (o < n_out) wv = p.w_bbox[(o - p.A) * p.m_total + c0 + cc];
+                    ro_w[o * kRoWStride + cc] = wv;
+                }
+                __syncwarp();
+                const int u = lane & 7, og0 = (lane >> 3) * 4;          // lane = (pixel u, outputs og0 .. og0 + 3)
+                const int chunks_per_sub = p.Jh / CW;
+                const int my_tiles = (group < p.total_tiles) ? (p.total_tiles - group + n_groups - 1) / n_groups : 0;
+                const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * kCG * chunks_per_sub;
+                const uint32_t w_a = smem_u32(ro_w) + static_cast<uint32_t>(og0 * kRoWStride) * 4u;
+                uint32_t ctr = 0;
+                for (int tile = group; tile < p.total_tiles; tile += n_groups) {
+                    const TilePos tp = decode_tile(p, tile / p.m_tiles);
+                    const LevelDesc& L = p.lv[tp.lvl];
+                    const size_t hw = static_cast<size_t>(L.H) * L.W;
+                    for (int ch = 0; ch < kCG * chunks_per_sub; ++ch, ++ctr) {
+                        const int sub = ch / chunks_per_sub, j0 = (ch - sub * chunks_per_sub) * CW;
+                        const int hh = tp.h0 + sub * p.sub_dh + (j0 >> 3), ww = tp.w0 + sub * p.sub_dw + (j0 & 7);
+                        const uint32_t buf = ctr & 1u;
+                        named_bar_sync(kBarRoFull + static_cast<int>(buf), kRoBarThreads);
+                        const uint32_t s_a = smem_u32(ro_s) + (buf * 8u * kRoWStride + static_cast<uint32_t>(u) * kRoWStride) * 4u;
+                        float a[4][2];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) a[j][0] = a[j][1] = 0.f;
+#pragma unroll 4
+                        for (int cc = 0; cc < 32; ++cc) {
+                            const uint4 sv = lds_v4(s_a + 16u * cc);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint4 wv = lds_v4(w_a + static_cast<uint32_t>(j * kRoWStride) * 4u + 16u * cc);
+                                a[j][0] = fmaf(__uint_as_float(wv.x), __uint_as_float(sv.x), a[j][0]);
+                                a[j][1] = fmaf(__uint_as_float(wv.y), __uint_as_float(sv.y), a[j][1]);
+                                a[j][0] = fmaf(__uint_as_float(wv.z), __uint_as_float(sv.z), a[j][0]);
+                                a[j][1] = fmaf(__uint_as_float(wv.w), __uint_as_float(sv.w), a[j][1]);
+                            }
+                        }
+                        // the buffer is free again (the epilogue only waits for it from its third chunk on, so the last two
+                        // arrivals have no partner and are not made)
+                        if (ctr + 2u < total_chunks) named_bar_arrive(kBarRoFree + static_cast<int>(buf), kRoBarThreads);
+                        if (hh < L.H && ww + u < L.W) {
+                            const size_t pix = static_cast<size_t>(hh) * L.W + ww + u;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int og = og0 + j;
+                                const float r = a[j][0] + a[j][1];
+                                if (og < p.A) atomicAdd(&L.logits[(static_cast<size_t>(tp.n) * p.A + og) * hw + pix], r);
+                                else if (og < n_out) atomicAdd(&L.bbox[(static_cast<size_t>(tp.n) * 4 * p.A + (og - p.A)) * hw + pix], r);
+                            }
+                        }
+                    }
+                }
+            }
+        }
     } else if (warp >= 8 && warp < 8 + kProducerWarps) {
         // ============================== spike-tile producers (n_pg groups): words -> swizzled {0,1} tile
         // The k-blocks of this CTA's tile sequence are numbered i = 0, 1, 2, ...; producer group g expands
@@ -546,19 +631,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         const int q = warp & 3;                        // TMEM lane quadrant of this warp
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const int te = q * 32 + lane;                  // 0..127: channel of this thread inside the CTA's 128
-        const int n_out = 5 * p.A;
-        const bool fused = kConv && p.fuse_readout != 0;
-        if (fused) {                                   // this CTA's 128-channel slice of the two 1x1 readout convs
-            const int c0 = static_cast<int>(rank) * 128;
-            for (int i = te; i < kRoMaxOut * 128; i += 128) {
-                const int o = i >> 7, cc = i & 127;
-                float wv = 0.f;
-                if (o < p.A) wv = p.w_cls[o * p.m_total + c0 + cc];
-                else if (o < n_out) wv = p.w_bbox[(o - p.A) * p.m_total + c0 + cc];
-                ro_w[o * kRoWStride + cc] = wv;
-            }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-        }
+        const bool fused = kConv && CW == 8 && p.fuse_readout != 0;
         float* ro_sg = ro_s + eg * (2 * 8 * kRoWStride);
         uint32_t chunk_ctr = 0;
         uint32_t it = 0;
@@ -650,17 +723,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                             const float kap = p.kappa[t];
                             const uint32_t bit = 1u << t;
 #pragma unroll
-                            for (int u = 0; u < CW; ++u) {
-                                cu[g][u] = __fmul_rn(cu[g][u], wscale);          // exact: power of two
-                                if (lif_update(v[u], ii[u], cu[g][u])) { tr[u] |= bit; sk[u] = __fadd_rn(sk[u], kap); }
-                            }
+                            for (int u = 0; u < CW; ++u)
+                                if (lif_update_scaled(v[u], ii[u], cu[g][u], wscale)) { tr[u] |= bit; sk[u] = __fadd_rn(sk[u], kap); }
                             if constexpr (!kConv) {
                                 if (p.dump != nullptr) {
 #pragma unroll
                                     for (int u = 0; u < CW; ++u) {
                                         const int r = unit0 + sub * sub_units + j0 + u;
                                         if (r < p.rows)
-                                            p.dump[(static_cast<size_t>(tl) * p.dump_rows + r) * p.m_total + c] = cu[g][u];
+                                            p.dump[(static_cast<size_t>(tl) * p.dump_rows + r) * p.m_total + c] = __fmul_rn(cu[g][u], wscale);
                                     }
                                 }
                             }
@@ -701,41 +772,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                             }
                         }
                     }
-                    // ---- fused LI readout: out[o][px] += sum_{c in this CTA} W[o][c] * sk[c][px]
+                    // ---- fused LI readout: hand the chunk's kappa-weighted spike sums to the readout warp (warp 2)
                     if constexpr (kConv) {
                         if (fused) {
-                            float* S = ro_sg + (chunk_ctr & 1u) * (8 * kRoWStride);    // [CW pixels][128 channels + pad]
+                            const uint32_t rb = chunk_ctr & 1u;
+                            // the readout warp must have consumed what this buffer held two chunks ago
+                            if (chunk_ctr >= 2u) named_bar_sync(kBarRoFree + static_cast<int>(rb), kRoBarThreads);
                             ++chunk_ctr;
-                            {   // explicit shared-space accesses (the generic-pointer form compiled to LD.E / ST.E)
-                                const uint32_t s_dst = smem_u32(S) + static_cast<uint32_t>(te) * 4u;
+                            // explicit shared-space stores (the generic-pointer form compiled to ST.E): S[px u][channel te]
+                            const uint32_t s_dst = smem_u32(ro_sg) + (rb * 8u * kRoWStride + static_cast<uint32_t>(te)) * 4u;
 #pragma unroll
-                                for (int u = 0; u < CW; ++u)
-                                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_dst + static_cast<uint32_t>(u * kRoWStride) * 4u), "f"(sk[u]) : "memory");
-                            }
-                            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-                            const int u = te % CW, og = te / CW;            // thread = (pixel u, output og)
-                            if (og < kRoMaxOut) {
-                                const uint32_t s_a = smem_u32(S) + static_cast<uint32_t>(u * kRoWStride) * 4u;
-                                const uint32_t w_a = smem_u32(ro_w) + static_cast<uint32_t>(og * kRoWStride) * 4u;
-                                // four independent chains (one chain of 128 dependent FMAs was ~500 cycles of latency
-                                // per chunk, r01aj: the readout is 42 % of the epilogue role)
-                                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-                                for (int cc = 0; cc < 32; ++cc) {
-                                    const uint4 sv = lds_v4(s_a + 16u * cc), wv = lds_v4(w_a + 16u * cc);
-                                    a0 = fmaf(__uint_as_float(wv.x), __uint_as_float(sv.x), a0);
-                                    a1 = fmaf(__uint_as_float(wv.y), __uint_as_float(sv.y), a1);
-                                    a2 = fmaf(__uint_as_float(wv.z), __uint_as_float(sv.z), a2);
-                                    a3 = fmaf(__uint_as_float(wv.w), __uint_as_float(sv.w), a3);
-                                }
-                                const float a = (a0 + a1) + (a2 + a3);
-                                if (row_ok && u < lim && og < n_out) {
-                                    const LevelDesc& L = p.lv[lvl];
-                                    const size_t hw = static_cast<size_t>(H) * W, pix = static_cast<size_t>(hh) * W + ww + u;
-                                    if (og < p.A) atomicAdd(&L.logits[(static_cast<size_t>(n) * p.A + og) * hw + pix], a);
-                                    else atomicAdd(&L.bbox[(static_cast<size_t>(n) * 4 * p.A + (og - p.A)) * hw + pix], a);
-                                }
-                            }
+                            for (int u = 0; u < CW; ++u)
+                                asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_dst + static_cast<uint32_t>(u * kRoWStride) * 4u), "f"(sk[u]) : "memory");
+                            named_bar_arrive(kBarRoFull + static_cast<int>(rb), kRoBarThreads);
                         }
                     }
                 }
@@ -749,8 +798,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {
+                // the TMEM reads of this warp are complete (tcgen05.wait::ld) and fenced (fence::before_thread_sync); the
+                // arrive only carries the signal to the MMA thread, which fences after its wait -- CTA-scope release as in
+                // CUTLASS's ClusterBarrier::arrive(cta_id) (the cluster-scope release compiled to an ERRBAR that was 6 %
+                // of the epilogue warps' samples, ncu r02c)
                 if constexpr (kCG == 1) mbar_arrive(&acc_empty[buf]);
-                else mbar_arrive_cluster(&acc_empty[buf], 0);
+                else mbar_arrive_remote(&acc_empty[buf], 0);
             }
             }   // bi
         }
