@@ -675,6 +675,9 @@ def run_ours(args):
     verify = None
     if world == 1 and not args.no_verify and B <= 4:
         verify = verify_step(args.workload, B, rank, args.t_rpn, args.t_det, rpn, box, d_feats, d_rois)
+        # the bar is north_star's fp32-mode bar; the reduced weight modes (bf16, fp16, bf16x2: BASELINE config 3) are
+        # measured against it and reported, but only the fp32-grade modes must meet it
+        verify["enforced"] = args.mode in ("fp32_exact", "fp16x2")
 
     if rank != 0:
         if world > 1:
@@ -716,7 +719,7 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-    if verify is not None and not verify["ok"]:
+    if verify is not None and verify["enforced"] and not verify["ok"]:
         raise SystemExit("bench.py: the outputs at the bench shape FAILED the oracle check (see \"verify\" in the line above)")
 
 
