@@ -366,15 +366,12 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    def run_for(seconds):
-        """Un-reported steps for at least `seconds` of wall time: puts the board into its sustained power state."""
-        n = 0
-        t0 = time.perf_counter()
-        while time.perf_counter() - t0 < seconds:
-            for _ in range(10):
-                step_resident()
-            n += 10
-            torch.cuda.synchronize(dev)
+    def run_steps(n):
+        """n un-reported steps (the SAME count on every rank: each step starts an all-gather of the records)."""
+        for k in range(n):
+            step_resident()
+            if k % 10 == 9:
+                torch.cuda.synchronize(dev)
         drain()
         return n
 
@@ -401,7 +398,9 @@ def run_ours(args):
         burst = {"steps": 20, "ms_per_step": bms.item(), "value": world * B / (bms.item() * 1e-3), "unit": "images/s",
                  "note": "20 steps timed from idle (max over ranks), before the power cap settles the SM clock; "
                          "NOT the headline"}
-        pre_steps = run_for(args.precondition_s)
+        # at least precondition_s seconds of the same load; the count comes from the max-over-ranks burst time, so it is
+        # identical on every rank
+        pre_steps = run_steps(int(args.precondition_s * 1e3 / bms.item() / 10.0 + 1.0) * 10)
     sync_all()
 
     # ---------------- device-resident timing (sustained regime)
