@@ -40,3 +40,27 @@ def test_our_arm_needs_a_cuda_device():
         return
     r = _run(["--steps", "1", "--warmup", "0"])
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_canonical_flop_count_is_the_surveys():
+    """the reference's own FLOP count per image (every layer at all T steps, 1 MAC = 2 FLOP):
+    Cityscapes T 8/12, 9 classes = 1267.4 GFLOP; BDD, 5 classes = 1169.8 GFLOP."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert abs(bench.canonical_gflop_per_image("cityscapes", 8, 12) - 1267.4) < 0.05
+    assert abs(bench.canonical_gflop_per_image("bdd", 8, 12) - 1169.8) < 0.05
+    a = bench.parse([])
+    assert a.steps == 100 and a.warmup == 10 and a.gpus == 1 and a.mode == "fp16x2" and a.precondition_s == 1.0
+
+
+def test_bench_inputs_are_seeded_per_global_image_index():
+    """shards are reproducible because every image is drawn from its own seed, whichever rank owns it."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import bench
+    f0, r0 = bench.bench_inputs("bdd", 3)
+    f1, r1 = bench.bench_inputs("bdd", 3)
+    f2, _ = bench.bench_inputs("bdd", 4)
+    assert all(torch.equal(a, b) for a, b in zip(f0, f1)) and torch.equal(r0, r1)
+    assert not torch.equal(f0[4], f2[4])
+    assert [tuple(f.shape) for f in f0] == [(256, h, w) for (h, w) in bench.BDD_LEVELS] and r0.shape == (1000, 256, 7, 7)
