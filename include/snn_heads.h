@@ -165,6 +165,15 @@ int snn_rpn_decode_selected(const void* const* logits, const void* const* deltas
 int snn_rpn_topk_keys(const void* const* logits, const int* H, const int* W, int n_levels, int N, int A,
                       long long* const* keys_out, snn_stream_t stream);
 
+/* The per-level top-k itself, all levels and images of a batch in eight launches: exact radix select on those keys
+ * (recomputed from the logits on every pass; 2048-bin histograms, six passes) + a shared-memory sort of the k selected
+ * keys per (level, image).  idx_out [N][K] int64, K = sum_l min(k, A*H[l]*W[l]), level-major: positions inside the
+ * level's [A][H][W] logits, largest logit first, ties by the lowest index in the reference's (H, W, A) order -- the input
+ * of snn_rpn_decode_selected.  k <= 2048 (pre_nms_top_n: 1000 at test time, 2000 in training, model.py:50-53). */
+size_t snn_rpn_topk_workspace_bytes(int n_levels, int N);
+int snn_rpn_topk_select(const void* const* logits, const int* H, const int* W, int n_levels, int N, int A, int k,
+                        long long* idx_out, void* workspace, size_t workspace_bytes, snn_stream_t stream);
+
 /* ---- "next" row 8f-3: linear statistics of the spike trains the heads emit (the spike-rate / energy report the
  * reference obtains from hand-edited forwards, rpn.py:126-200, faster_rcnn.py:520-618; train.py:426-517).
  * out[o] = sum_c w[o][c] * sum_t step_weights[t] * spk_t[c], the two leaky-integrator readout kernels with a caller-given

@@ -596,6 +596,150 @@ __global__ void __launch_bounds__(256) rpn_topk_keys_kernel(const __grid_constan
     }
 }
 
+// ---- the per-level top-k itself, for all levels and images at once
+// torch.topk on those int64 keys is one call per level, each a handful of kernels working on N (= 2) rows: 0.56 ms for
+// the Cityscapes batch (r02g) -- the top-k, not the decode, was the cost of the proposal selection.  Here: an exact radix
+// select over all L x N segments at once.  The key of an anchor is recomputed from its logit on every pass (no key
+// tensor); six histogram passes (digits of 11, 11, 11, 11, 10, 10 bits from the top, 2048-bin shared-memory histograms
+// with warp-aggregated atomics, so a plateau of equal logits costs one atomic per warp) narrow the k-th largest key down
+// to all its 64 bits -- the last block of a segment to finish a pass (ticket counter) scans the segment's histogram and
+// publishes the digit -- then one pass collects the k keys >= that threshold (keys are unique, so there are exactly k)
+// and one block per segment sorts them (bitonic, shared memory) and writes the positions, largest key first.
+constexpr int kTopkPasses = 6;
+constexpr int kTopkBins = 2048;
+constexpr int kTopkChunk = 4096;            // anchors per block and pass
+constexpr int kTopkThreads = 256;
+constexpr int kTopkMaxK = 2048;             // candidates sorted per segment (pre_nms_top_n: 1000 at test time, 2000 in training)
+__host__ __device__ constexpr int topk_bits(int pass) { return pass < 4 ? 11 : 10; }
+__host__ __device__ constexpr int topk_shift(int pass) { return pass < 4 ? 64 - 11 * (pass + 1) : 10 * (5 - pass); }
+
+struct TopkLevel { const float* logits; int A, HW, n, k, k_begin, chunks; };      // n = A * HW anchors per image
+struct TopkParams {
+    TopkLevel lv[kPropMaxLevels];
+    int n_levels, N, K_total;
+    unsigned long long* prefix;     // [segments] digits of the k-th largest key found so far (segment = level * N + image)
+    unsigned int* k_rem;            // [segments] rank of that key among the anchors that share the prefix
+    unsigned int* done;             // [segments][kTopkPasses] blocks that finished the pass
+    unsigned int* hist;             // [segments][kTopkPasses][kTopkBins]
+    unsigned int* n_cand;           // [segments]
+    unsigned long long* cand;       // [segments][kTopkMaxK]
+    long long* idx;                 // [N][K_total] selected positions inside the level's [A][H][W] logits
+};
+
+// unsigned 64-bit key: larger = better; (order-preserving image of the logit, -0 folded into +0) then the LOWER index in
+// the reference's (H, W, A) flattening wins
+__device__ __forceinline__ unsigned long long topk_key(float logit, int pos, int A, int HW) {
+    const int a = pos / HW, rem = pos - a * HW;
+    const int b = __float_as_int(__fadd_rn(logit, 0.0f));
+    const unsigned int hi = static_cast<unsigned int>(b ^ ((b >> 31) & 0x7FFFFFFF)) ^ 0x80000000u;
+    return (static_cast<unsigned long long>(hi) << 32) | (0xFFFFFFFFu - (static_cast<unsigned int>(rem) * A + a));
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kTopkThreads) rpn_topk_pass_kernel(const __grid_constant__ TopkParams p) {
+    constexpr int shift = topk_shift(PASS), bits = topk_bits(PASS);
+    const int seg = blockIdx.y, l = seg / p.N, n = seg - l * p.N;
+    const TopkLevel& L = p.lv[l];
+    if (static_cast<int>(blockIdx.x) >= L.chunks) return;
+    __shared__ unsigned int h[kTopkBins];
+    __shared__ unsigned int s_part[kTopkThreads];
+    __shared__ unsigned int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int b = tid; b < kTopkBins; b += kTopkThreads) h[b] = 0u;
+    __syncthreads();
+    const unsigned long long prefix = PASS ? p.prefix[seg] : 0ull;
+    const float* base = L.logits + static_cast<size_t>(n) * L.n;
+    const int i0 = blockIdx.x * kTopkChunk, i1 = min(L.n, i0 + kTopkChunk);
+    for (int i = i0 + tid; i < i0 + kTopkChunk; i += kTopkThreads) {      // uniform trip count: the warp votes below are full
+        unsigned int d = 0xFFFFFFFFu;
+        if (i < i1) {
+            const unsigned long long key = topk_key(__ldg(base + i), i, L.A, L.HW);
+            bool in = true;
+            if constexpr (PASS > 0) in = (key >> (shift + bits)) == (prefix >> (shift + bits));
+            if (in) d = static_cast<unsigned int>(key >> shift) & ((1u << bits) - 1u);
+        }
+        const unsigned int m = __match_any_sync(0xFFFFFFFFu, d);
+        if (d != 0xFFFFFFFFu && lane == __ffs(static_cast<int>(m)) - 1) atomicAdd(&h[d], static_cast<unsigned int>(__popc(m)));
+    }
+    __syncthreads();
+    unsigned int* gh = p.hist + (static_cast<size_t>(seg) * kTopkPasses + PASS) * kTopkBins;
+    for (int b = tid; b < kTopkBins; b += kTopkThreads)
+        if (h[b]) atomicAdd(&gh[b], h[b]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&p.done[seg * kTopkPasses + PASS], 1u);
+    __syncthreads();
+    if (s_ticket != static_cast<unsigned int>(L.chunks - 1)) return;
+    // ---- last block of the segment: the digit of the k-th largest key = the highest bin whose suffix count reaches k
+    __threadfence();
+    const unsigned int k_rem = PASS ? p.k_rem[seg] : static_cast<unsigned int>(L.k);
+    constexpr int per = kTopkBins / kTopkThreads;                 // bins per thread, thread 0 owns the TOP bins
+    unsigned int mine[per], sum = 0u;
+#pragma unroll
+    for (int j = 0; j < per; ++j) {
+        mine[j] = __ldcg(&gh[kTopkBins - 1 - (tid * per + j)]);
+        sum += mine[j];
+    }
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {                                               // 256 partial sums: serial exclusive scan from the top
+        unsigned int run = 0u;
+        for (int t = 0; t < kTopkThreads; ++t) { const unsigned int v = s_part[t]; s_part[t] = run; run += v; }
+    }
+    __syncthreads();
+    unsigned int above = s_part[tid];                             // anchors in bins above this thread's
+#pragma unroll
+    for (int j = 0; j < per; ++j) {
+        if (above < k_rem && above + mine[j] >= k_rem) {          // exactly one (thread, j) satisfies this
+            const unsigned long long digit = static_cast<unsigned long long>(kTopkBins - 1 - (tid * per + j));
+            p.prefix[seg] = prefix | (digit << shift);
+            p.k_rem[seg] = k_rem - above;
+        }
+        above += mine[j];
+    }
+}
+
+__global__ void __launch_bounds__(kTopkThreads) rpn_topk_collect_kernel(const __grid_constant__ TopkParams p) {
+    const int seg = blockIdx.y, l = seg / p.N, n = seg - l * p.N;
+    const TopkLevel& L = p.lv[l];
+    if (static_cast<int>(blockIdx.x) >= L.chunks) return;
+    const unsigned long long thr = p.prefix[seg];
+    const float* base = L.logits + static_cast<size_t>(n) * L.n;
+    const int i0 = blockIdx.x * kTopkChunk, i1 = min(L.n, i0 + kTopkChunk);
+    for (int i = i0 + threadIdx.x; i < i1; i += kTopkThreads) {
+        const unsigned long long key = topk_key(__ldg(base + i), i, L.A, L.HW);
+        if (key >= thr) {
+            const unsigned int slot = atomicAdd(&p.n_cand[seg], 1u);
+            if (slot < static_cast<unsigned int>(kTopkMaxK)) p.cand[static_cast<size_t>(seg) * kTopkMaxK + slot] = key;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) rpn_topk_sort_kernel(const __grid_constant__ TopkParams p) {
+    __shared__ unsigned long long s[kTopkMaxK];
+    const int seg = blockIdx.x, l = seg / p.N, n = seg - l * p.N;
+    const TopkLevel& L = p.lv[l];
+    const int tid = threadIdx.x;
+    const int cnt = min(static_cast<int>(p.n_cand[seg]), kTopkMaxK);
+    for (int i = tid; i < kTopkMaxK; i += 1024) s[i] = i < cnt ? p.cand[static_cast<size_t>(seg) * kTopkMaxK + i] : 0ull;
+    __syncthreads();
+    for (int size = 2; size <= kTopkMaxK; size <<= 1)             // bitonic sort, descending
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < kTopkMaxK / 2; t += 1024) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long a = s[lo], b = s[hi];
+                if ((a < b) == desc) { s[lo] = b; s[hi] = a; }
+            }
+            __syncthreads();
+        }
+    for (int j = tid; j < L.k && j < cnt; j += 1024) {
+        const unsigned int ref = 0xFFFFFFFFu - static_cast<unsigned int>(s[j] & 0xFFFFFFFFull);
+        const unsigned int a = ref % static_cast<unsigned int>(L.A), rem = ref / static_cast<unsigned int>(L.A);
+        p.idx[static_cast<size_t>(n) * p.K_total + L.k_begin + j] = static_cast<long long>(a) * L.HW + rem;
+    }
+}
+
 // ------------------------------------------------- RoIAlign fused with the encoder
 // The step before FastRCNNPredictorSNNFull in RoIHeadsSNN.forward (roi_heads.py:1217 -> faster_rcnn.py:474-494):
 // MultiScaleRoIAlign writes [R][C][7][7] fp32 only for the encoder to threshold it into spikes.  Here one thread

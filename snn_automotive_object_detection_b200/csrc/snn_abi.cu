@@ -1029,6 +1029,72 @@ int snn_rpn_topk_keys(const void* const* logits, const int* H, const int* W, int
     return SNN_OK;
 }
 
+// ---- per-level top-k of the objectness logits, all levels and images in eight launches (radix select + sort)
+struct TopkWs { size_t prefix, k_rem, done, hist, n_cand, cand, zero_begin, zero_end, total; };
+static TopkWs topk_ws_layout(int n_levels, int N) {
+    const size_t segs = static_cast<size_t>(n_levels) * N;
+    TopkWs w{};
+    size_t off = 0;
+    w.prefix = off; off = align_up(off + segs * 8, 256);
+    w.k_rem = off; off = align_up(off + segs * 4, 256);
+    w.cand = off; off = align_up(off + segs * kTopkMaxK * 8, 256);
+    w.zero_begin = off;                                   // everything from here on is cleared by one memset per call
+    w.done = off; off = align_up(off + segs * kTopkPasses * 4, 256);
+    w.n_cand = off; off = align_up(off + segs * 4, 256);
+    w.hist = off; off = align_up(off + segs * kTopkPasses * kTopkBins * 4, 256);
+    w.zero_end = off;
+    w.total = off;
+    return w;
+}
+
+size_t snn_rpn_topk_workspace_bytes(int n_levels, int N) {
+    if (n_levels < 1 || n_levels > kPropMaxLevels || N < 1) return 0;
+    return topk_ws_layout(n_levels, N).total;
+}
+
+int snn_rpn_topk_select(const void* const* logits, const int* H, const int* W, int n_levels, int N, int A, int k,
+                        long long* idx_out, void* workspace, size_t workspace_bytes, snn_stream_t stream) {
+    if (!logits || !H || !W || !idx_out || !workspace) return fail(SNN_E_ARG, "rpn_topk_select: null argument");
+    if (n_levels < 1 || n_levels > kPropMaxLevels || N < 1 || A < 1 || k < 1 || k > kTopkMaxK)
+        return fail(SNN_E_ARG, "rpn_topk_select: bad sizes (levels %d, N %d, A %d, k %d; k <= %d)", n_levels, N, A, k, kTopkMaxK);
+    if (static_cast<long long>(n_levels) * N > 65535) return fail(SNN_E_ARG, "rpn_topk_select: too many (level, image) segments");
+    const TopkWs w = topk_ws_layout(n_levels, N);
+    if (workspace_bytes < w.total) return fail(SNN_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, w.total);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(SNN_E_ARG, "workspace must be 256-B aligned");
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    TopkParams p;
+    memset(&p, 0, sizeof(p));
+    int kb = 0, max_chunks = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        if (!logits[l] || H[l] < 1 || W[l] < 1) return fail(SNN_E_ARG, "rpn_topk_select: level %d: bad argument", l);
+        TopkLevel& L = p.lv[l];
+        const long long n = static_cast<long long>(A) * H[l] * W[l];
+        if (n > 0x7FFFFFFFll) return fail(SNN_E_ARG, "rpn_topk_select: level %d too large", l);
+        L.logits = reinterpret_cast<const float*>(logits[l]); L.A = A; L.HW = H[l] * W[l]; L.n = static_cast<int>(n);
+        L.k = k < L.n ? k : L.n; L.k_begin = kb; L.chunks = (L.n + kTopkChunk - 1) / kTopkChunk;
+        kb += L.k;
+        if (L.chunks > max_chunks) max_chunks = L.chunks;
+    }
+    p.n_levels = n_levels; p.N = N; p.K_total = kb;
+    p.prefix = reinterpret_cast<unsigned long long*>(ws + w.prefix); p.k_rem = reinterpret_cast<unsigned int*>(ws + w.k_rem);
+    p.done = reinterpret_cast<unsigned int*>(ws + w.done); p.hist = reinterpret_cast<unsigned int*>(ws + w.hist);
+    p.n_cand = reinterpret_cast<unsigned int*>(ws + w.n_cand); p.cand = reinterpret_cast<unsigned long long*>(ws + w.cand);
+    p.idx = idx_out;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(ws + w.zero_begin, 0, w.zero_end - w.zero_begin, st));
+    const dim3 grid(max_chunks, n_levels * N);
+    rpn_topk_pass_kernel<0><<<grid, kTopkThreads, 0, st>>>(p);
+    rpn_topk_pass_kernel<1><<<grid, kTopkThreads, 0, st>>>(p);
+    rpn_topk_pass_kernel<2><<<grid, kTopkThreads, 0, st>>>(p);
+    rpn_topk_pass_kernel<3><<<grid, kTopkThreads, 0, st>>>(p);
+    rpn_topk_pass_kernel<4><<<grid, kTopkThreads, 0, st>>>(p);
+    rpn_topk_pass_kernel<5><<<grid, kTopkThreads, 0, st>>>(p);
+    rpn_topk_collect_kernel<<<grid, kTopkThreads, 0, st>>>(p);
+    rpn_topk_sort_kernel<<<n_levels * N, 1024, 0, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return SNN_OK;
+}
+
 // ---- linear statistics of spike trains (the spike-rate / energy report, rates.py)
 int snn_li_readout_nhwc(const void* trains, int train_bytes, int N, int HW, int C, const double* step_weights,
                         const float* w_a, int n_a, const float* w_b, int n_b, float* out_a, float* out_b,

@@ -103,6 +103,10 @@ def nchw_index_to_reference_order(idx: Tensor, A: int, H: int, W: int) -> Tensor
     return rem * A + a
 
 
+TOPK_KERNEL_MAX_K = 2048          # csrc/aux_kernels.cuh kTopkMaxK
+_TOPK_WS = {}                     # (device, levels, images) -> workspace of the top-k kernels
+
+
 def rpn_select_proposals(objectness: Sequence[Tensor], pred_bbox_deltas: Sequence[Tensor], cell_anchors: Sequence[Tensor],
                          strides: Sequence[Tuple[int, int]], pre_nms_top_n: int):
     """Per-level top-k on the head's NCHW logits + decode of the selected anchors only (CUDA).
@@ -128,22 +132,30 @@ def rpn_select_proposals(objectness: Sequence[Tensor], pred_bbox_deltas: Sequenc
     # order as the reference's top-k on its permuted tensor, ties included -- pixels where no shared_lif neuron spiked
     # have exactly-zero membranes for every anchor, so tie groups at the k boundary are real
     sizes = [o[0].numel() for o in logits]
-    keys_flat = torch.empty(N * sum(sizes), dtype=torch.int64, device=dev)
-    keys, off = [], 0
-    for n_anchors in sizes:
-        keys.append(keys_flat[off:off + N * n_anchors].view(N, n_anchors)); off += N * n_anchors
-    with torch.cuda.device(dev):
-        rc = lib.snn_rpn_topk_keys(VP(*[t.data_ptr() for t in logits]), IA(*[t.shape[2] for t in logits]),
-                                   IA(*[t.shape[3] for t in logits]), L, N, A, VP(*[t.data_ptr() for t in keys]),
-                                   ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-    _lib.check(rc, "snn_rpn_topk_keys")
-    ks, idxs, lvls = [], [], []
-    for l, kt in enumerate(keys):
-        k = min(int(pre_nms_top_n), sizes[l])
-        _, top = kt.topk(k, dim=1)                                  # positions in NCHW order: no permute / reshape copy
-        ks.append(k); idxs.append(top)
-        lvls.append(torch.full((k,), l, dtype=torch.int64, device=dev))
-    idx = torch.cat(idxs, dim=1).contiguous()
+    ks = [min(int(pre_nms_top_n), n) for n in sizes]
+    lvls = [torch.full((k,), l, dtype=torch.int64, device=dev) for l, k in enumerate(ks)]
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    Hs, Ws = IA(*[t.shape[2] for t in logits]), IA(*[t.shape[3] for t in logits])
+    if int(pre_nms_top_n) <= TOPK_KERNEL_MAX_K:
+        # all levels and images at once: radix select + sort in the library (eight launches)
+        idx = torch.empty(N, sum(ks), dtype=torch.int64, device=dev)
+        ws = _TOPK_WS.get((str(dev), L, N))
+        if ws is None:
+            ws = _TOPK_WS[(str(dev), L, N)] = torch.empty(lib.snn_rpn_topk_workspace_bytes(L, N), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.snn_rpn_topk_select(VP(*[t.data_ptr() for t in logits]), Hs, Ws, L, N, A, int(pre_nms_top_n),
+                                         ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(), st)
+        _lib.check(rc, "snn_rpn_topk_select")
+    else:
+        # larger k: the keys as a tensor + torch.topk per level
+        keys_flat = torch.empty(N * sum(sizes), dtype=torch.int64, device=dev)
+        keys, off = [], 0
+        for n_anchors in sizes:
+            keys.append(keys_flat[off:off + N * n_anchors].view(N, n_anchors)); off += N * n_anchors
+        with torch.cuda.device(dev):
+            rc = lib.snn_rpn_topk_keys(VP(*[t.data_ptr() for t in logits]), Hs, Ws, L, N, A, VP(*[t.data_ptr() for t in keys]), st)
+        _lib.check(rc, "snn_rpn_topk_keys")
+        idx = torch.cat([kt.topk(k, dim=1)[1] for kt, k in zip(keys, ks)], dim=1).contiguous()
     K = idx.shape[1]
     boxes = torch.empty(N, K, 4, device=dev, dtype=torch.float32)
     scores = torch.empty(N, K, device=dev, dtype=torch.float32)

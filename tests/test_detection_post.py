@@ -180,24 +180,41 @@ def test_fused_roi_align_encoder_matches_torchvision_pool_then_encode(names, sam
 
 
 @pytest.mark.gpu
-def test_topk_ties_are_broken_in_the_references_order():
+@pytest.mark.parametrize("k", [400, 1000, 3000])
+def test_topk_ties_are_broken_in_the_references_order(k):
     """Pixels where no shared_lif neuron spiked have exactly-zero membranes for every anchor, so large tie groups at
     the k boundary are real.  The reference takes top-k on the (H, W, A)-flattened logits (rpn.py:248-259, 468-472);
     the selection here must be "largest first, ties by the lowest reference index" -- a stable descending sort of the
-    reference-ordered tensor."""
+    reference-ordered tensor.  k <= 2048 runs the library's radix-select + sort kernels over all (level, image)
+    segments at once (k = 400 cuts the zero plateau of the large level; the small level has fewer anchors than k and is
+    sorted whole); k = 3000 takes the key tensor + torch.topk path."""
     import snn_automotive_object_detection_b200 as S
     torch.manual_seed(11)
-    N, A, H, W = 2, 3, 20, 30
-    logits = torch.zeros(N, A, H, W)
-    hot = torch.rand(N, A, H, W) < 0.02                      # 2 % distinct positive values, the rest exact ties at 0
-    logits[hot] = torch.rand(int(hot.sum())) + 0.1
-    logits[0, 1, 3, 4] = -0.0
-    neg = torch.rand(N, A, H, W) < 0.3
-    logits[neg & ~hot] = -torch.rand(int((neg & ~hot).sum())) - 0.1
-    deltas = 0.1 * torch.randn(N, 4 * A, H, W)
+    N, A = 3, 3
+    shapes = [(40, 50), (5, 7)]
+    logits, deltas = [], []
+    for (H, W) in shapes:
+        lg = torch.zeros(N, A, H, W)
+        hot = torch.rand(N, A, H, W) < 0.02                  # 2 % distinct positive values, the rest exact ties at 0
+        lg[hot] = torch.rand(int(hot.sum())) + 0.1
+        neg = (torch.rand(N, A, H, W) < 0.3) & ~hot
+        lg[neg] = -torch.rand(int(neg.sum())) - 0.1
+        lg[0, 1, 3, 4] = -0.0
+        lg[1, 0, 0, 0] = float("inf")
+        lg[2, 2, 1, 1] = -float("inf")
+        lg[1, 2, 2:4, :] = 0.25                              # a tie group of positive values as well
+        logits.append(lg); deltas.append(0.1 * torch.randn(N, 4 * A, H, W))
     cell = torch.tensor([[-16., -8., 16., 8.], [-11., -11., 11., 11.], [-8., -16., 8., 16.]])
-    k = 400                                                  # well inside the zero plateau
-    _, _, _, ref_index = S.rpn_select_proposals([logits.cuda()], [deltas.cuda()], [cell], [(16, 16)], k)
-    flat = logits.permute(0, 2, 3, 1).reshape(N, -1)         # the reference's order
-    want = torch.sort(flat, dim=1, descending=True, stable=True)[1][:, :k]
-    assert torch.equal(ref_index.cpu(), want)
+    _, probs, levels, ref_index = S.rpn_select_proposals([t.cuda() for t in logits], [t.cuda() for t in deltas],
+                                                         [cell, cell], [(16, 16), (32, 32)], k)
+    want, off = [], 0
+    for lg in logits:
+        flat = lg.permute(0, 2, 3, 1).reshape(N, -1)         # the reference's order
+        kk = min(k, flat.shape[1])
+        want.append(torch.sort(flat, dim=1, descending=True, stable=True)[1][:, :kk] + off)
+        off += flat.shape[1]
+    want = torch.cat(want, dim=1)
+    assert ref_index.shape == want.shape and torch.equal(ref_index.cpu(), want)
+    allf = torch.cat([lg.permute(0, 2, 3, 1).reshape(N, -1) for lg in logits], dim=1)
+    assert torch.allclose(probs.cpu(), torch.sigmoid(torch.gather(allf, 1, want)), atol=1e-6)
+    assert levels.shape == want.shape and int(levels[0, -1]) == 1
