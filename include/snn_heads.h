@@ -112,7 +112,12 @@ int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_words, snn
  * n(x) = min{ n : x >= thresholds[n] }.  HOST call: copies the 33-entry tables (index n = 1..32; thresholds[n] =
  * the smallest fp32 input whose first spike comes at step <= n; deltas[n] = train(n) ^ train(n+1) over 32 steps). */
 void snn_encoder_table(float* thresholds33, unsigned int* deltas33);
-/* Exhaustive device self-test: counts, over ALL 2^32 fp32 bit patterns, the inputs whose comparator-bank word differs
+/* The encoder kernels evaluate that comparator bank through ONE table lookup per input: the input, clamped to [0.25, 4],
+ * is rounded to fp16 and indexes a 4097-entry table of 32-step train words; entries whose rounding interval contains a
+ * threshold carry bit 31 and are evaluated exactly (at most 31 live steps are ever encoded, so bit 31 is free).  HOST
+ * call: copies the table (entries may be NULL), its length and the fp16 bit pattern of entry 0 (0.25). */
+void snn_encoder_lut(unsigned int* entries, int* n_entries, int* first_half_bits);
+/* Exhaustive device self-test (comparator bank AND table path): counts, over ALL 2^32 fp32 bit patterns, the inputs whose comparator-bank word differs
  * from the step-by-step simulation of lif_current_encoder for T_live steps; *mismatches (device, zeroed by the caller)
  * must stay 0. */
 int snn_encoder_selftest(int T_live, unsigned long long* mismatches, snn_stream_t stream);

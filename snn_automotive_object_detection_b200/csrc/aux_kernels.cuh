@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restri
 
 // ---------------------------------------------------------------- encoder
 // Norse lif_current_encoder, op for op: v += 0.1f*((0-v)+x); z = (v-0.25f > 0); v -= z*v.
-// Returns the spike train of the first T steps as a bit word (bit t = z_t).
+// Returns the spike train of the first T steps as a bit word (bit t = z_t).  (x = +inf spikes once: the arithmetic reset
+// inf - inf leaves NaN, which never crosses the threshold again -- reproduced, see encode_word.)
 // The threshold test is evaluated as v > 0.25f: for fp32 numbers a and b, fl(a - b) > 0 <=> a > b (the
 // difference of two floats near the threshold is a multiple of 2^-26, never flushed), so it is the same bit.
 __device__ __forceinline__ uint32_t encode_train(float x, int T) {
@@ -80,7 +81,7 @@ __device__ __forceinline__ uint32_t encode_train(float x, int T) {
         v = __fadd_rn(v, __fmul_rn(0.1f, __fsub_rn(x, v)));
         const bool z = v > 0.25f;
         if (z) w |= 1u << t;
-        v = z ? 0.f : v;
+        v = z ? __fsub_rn(v, v) : v;          // Norse resets arithmetically, v - z * (v - v_reset): 0 for finite v, NaN for +inf
     }
     return w;
 }
@@ -182,6 +183,11 @@ __device__ __forceinline__ void encode_words(const float (&x)[N], uint32_t tmask
             for (int k = 0; k < N; ++k) xor_if_ge(w[k], x[k], th, dl);
         }
     }
+    // the one input whose train is not periodic: +inf spikes at step 0 and leaves v = inf - inf = NaN (Norse's
+    // arithmetic reset), which never spikes again
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+        if (x[k] == __int_as_float(0x7f800000)) w[k] = 1u & tmask;
 }
 template <int NT>
 __device__ __forceinline__ uint32_t encode_word(float x, uint32_t tmask) {
@@ -189,6 +195,76 @@ __device__ __forceinline__ uint32_t encode_word(float x, uint32_t tmask) {
     uint32_t w[1];
     encode_words<NT, 1>(xs, tmask, w);
     return w[0];
+}
+
+// ---- the encoder as ONE table lookup (round 2)
+// ncu r02c: both encoder kernels are instruction-bound, not HBM-bound (issue slots 73-75 % busy, ALU pipe 65-81 %, DRAM
+// 4.1-4.2 of 6.5 TB/s): 2 instructions per step and neuron are still 14-22 per neuron.  The train is a step function of x
+// with at most 32 steps, all inside (0.25, 2.5]: round x (clamped to [0.25, 4]) to fp16 -- 4097 possible values -- and look
+// the word up.  The lookup is exact whenever every fp32 input that rounds to the same fp16 value has the same train;
+// the <= 64 table entries whose rounding interval contains a threshold carry a flag (bit 31; at most 31 live steps are
+// ever encoded) and take the comparator bank above.  The table is built at compile time from the same thresholds, so
+// the exhaustive self-test (every fp32 bit pattern) covers it: ~9 instructions per neuron instead of 23-30.
+constexpr int kEncLutLo = 0x3400;            // fp16 bits of 0.25
+constexpr int kEncLutHi = 0x4400;            // fp16 bits of 4.0
+constexpr int kEncLutEntries = kEncLutHi - kEncLutLo + 1;
+struct EncLut { uint32_t w[kEncLutEntries]; };
+
+__host__ __device__ constexpr float enc_half_value(int bits) {       // positive normal fp16 bit pattern -> value
+    const int e = (bits >> 10) & 31, m = bits & 1023;
+    float v = 1.0f + static_cast<float>(m) * (1.0f / 1024.0f);
+    for (int i = e; i < 15; ++i) v *= 0.5f;
+    for (int i = 15; i < e; ++i) v *= 2.0f;
+    return v;
+}
+__host__ __device__ constexpr int enc_first_spike_by_table(const EncTable& tb, float x) {
+    for (int n = 1; n <= 32; ++n)
+        if (x >= tb.thr[n]) return n;
+    return 33;
+}
+__host__ __device__ constexpr EncLut make_enc_lut() {
+    const EncTable tb = make_enc_table();
+    EncLut l{};
+    for (int i = 0; i < kEncLutEntries; ++i) {
+        const int bits = kEncLutLo + i;
+        const float h = enc_half_value(bits);
+        // every fp32 value that rounds (to nearest) to h lies in [lo, hi] = the midpoints to its fp16 neighbours (both
+        // included: conservative about ties); below the first / above the last entry the clamp collapses everything
+        const float lo = 0.5f * (enc_half_value(bits - 1) + h), hi = 0.5f * (h + enc_half_value(bits + 1));
+        const int n_lo = (i == 0) ? 33 : enc_first_spike_by_table(tb, lo);
+        const int n_hi = (i == kEncLutEntries - 1) ? 1 : enc_first_spike_by_table(tb, hi);
+        const uint32_t word = enc_full_train(n_hi) & 0x7FFFFFFFu;
+        // the last entry also holds +inf, whose train is not the periodic one: evaluated exactly
+        l.w[i] = (n_lo == n_hi && i != kEncLutEntries - 1) ? word : 0x80000000u;
+    }
+    return l;
+}
+__device__ const EncLut g_enc_lut = make_enc_lut();
+
+// block-cooperative copy of the table into shared memory (16 KB)
+__device__ __forceinline__ void enc_lut_load(uint32_t* s_lut) {
+    for (int i = threadIdx.x; i < kEncLutEntries; i += blockDim.x) s_lut[i] = g_enc_lut.w[i];
+}
+// out of line: taken by ~1 % of the neurons (those whose fp16 image sits next to a threshold)
+template <int NT>
+__device__ __noinline__ uint32_t encode_word_slow(float x, uint32_t tmask) { return encode_word<NT>(x, tmask); }
+
+// N inputs -> words through the table in shared memory (T_live <= 31); NaN clamps to 0.25 = never spikes, as simulated
+template <int NT, int N>
+__device__ __forceinline__ void encode_words_lut(const float (&x)[N], uint32_t tmask, const uint32_t* __restrict__ s_lut, uint32_t (&w)[N]) {
+    static_assert(N % 2 == 0, "inputs are converted in pairs");
+#pragma unroll
+    for (int k = 0; k < N; k += 2) {
+        const float a = fminf(fmaxf(x[k], 0.25f), 4.0f), b = fminf(fmaxf(x[k + 1], 0.25f), 4.0f);
+        const __half2 h2 = __floats2half2_rn(a, b);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+        const uint32_t e0 = s_lut[(hb & 0xFFFFu) - kEncLutLo], e1 = s_lut[(hb >> 16) - kEncLutLo];
+        w[k] = e0 & tmask; w[k + 1] = e1 & tmask;
+        if (static_cast<int>(e0 | e1) < 0) {                      // a flagged entry: exact comparator bank for that input
+            if (static_cast<int>(e0) < 0) w[k] = encode_word_slow<NT>(x[k], tmask);
+            if (static_cast<int>(e1) < 0) w[k + 1] = encode_word_slow<NT>(x[k + 1], tmask);
+        }
+    }
 }
 
 // dispatch a kernel template on the bucket of live steps (exact for the step counts of the reference's sweeps)
@@ -243,8 +319,12 @@ __device__ __forceinline__ void store_words16(uint8_t* dst, const uint32_t (&w)[
 // HBM traffic: 4 B read + wb B written per input neuron (the per-timestep planes never exist).
 template <int NT, int WB>
 __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant__ EncParams p) {
+    __shared__ uint32_t s_lut[kEncLutEntries];
+    const bool use_lut = p.T_live <= 31;
+    if (use_lut) enc_lut_load(s_lut);
     griddep_launch_dependents();
     griddep_wait();             // the words buffer may still be read by the previous forward's GEMM
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int n_warps = gridDim.x * (blockDim.x >> 5);
     const int cgroups = p.C / kEncCh;
@@ -274,7 +354,8 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
             uint32_t w[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) xs[k] = xv[16 * h + k];
-            encode_words<NT, 16>(xs, tmask, w);
+            if (use_lut) encode_words_lut<NT, 16>(xs, tmask, s_lut, w);
+            else encode_words<NT, 16>(xs, tmask, w);
             if (ok) store_words16<WB>(dst + 16 * h * WB, w);
         }
     }
@@ -284,8 +365,12 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
 template <int NT, int WB>
 __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total16, int T_live,
                                                           uint8_t* __restrict__ z) {
+    __shared__ uint32_t s_lut[kEncLutEntries];
+    const bool use_lut = T_live <= 31;
+    if (use_lut) enc_lut_load(s_lut);
     griddep_launch_dependents();
     griddep_wait();
+    __syncthreads();
     const uint32_t tmask = (T_live >= 32) ? 0xFFFFFFFFu : ((1u << T_live) - 1u);
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total16;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -293,7 +378,8 @@ __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restric
         const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
         const float xs[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
         uint32_t w[16];
-        encode_words<NT, 16>(xs, tmask, w);
+        if (use_lut) encode_words_lut<NT, 16>(xs, tmask, s_lut, w);
+        else encode_words<NT, 16>(xs, tmask, w);
         store_words16<WB>(z + i * 16 * WB, w);
     }
 }
@@ -904,12 +990,25 @@ __global__ void __launch_bounds__(256, kRoiUnroll <= 2 ? 3 : 2) roi_align_encode
 // Exhaustive check of the comparator bank against the simulation: every one of the 2^32 fp32 bit patterns.
 template <int NT>
 __global__ void __launch_bounds__(256) encoder_selftest_kernel(int T_live, unsigned long long* __restrict__ mismatches) {
+    __shared__ uint32_t s_lut[kEncLutEntries];
+    enc_lut_load(s_lut);
+    __syncthreads();
     const uint32_t tmask = (T_live >= 32) ? 0xFFFFFFFFu : ((1u << T_live) - 1u);
     unsigned int bad = 0;
     for (unsigned long long b = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; b < (1ull << 32);
          b += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
         const float x = __uint_as_float(static_cast<uint32_t>(b));
-        bad += encode_word<NT>(x, tmask) != encode_train(x, T_live);
+        const uint32_t want = encode_train(x, T_live);
+        bad += encode_word<NT>(x, tmask) != want;
+        if (T_live <= 31) {                       // the table path of the encoder kernels, in both pair positions
+            const float xs[2] = {x, __uint_as_float(static_cast<uint32_t>(b) ^ 0x00400000u)};
+            uint32_t w[2];
+            encode_words_lut<NT, 2>(xs, tmask, s_lut, w);
+            bad += w[0] != want;
+            const float ys[2] = {xs[1], x};
+            encode_words_lut<NT, 2>(ys, tmask, s_lut, w);
+            bad += w[1] != want;
+        }
     }
     for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, static_cast<unsigned long long>(bad));

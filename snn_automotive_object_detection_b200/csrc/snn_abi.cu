@@ -1173,6 +1173,13 @@ void snn_encoder_table(float* thresholds33, unsigned int* deltas33) {
     }
 }
 
+void snn_encoder_lut(unsigned int* entries, int* n_entries, int* first_half_bits) {
+    static const EncLut lut = make_enc_lut();
+    if (entries) for (int i = 0; i < kEncLutEntries; ++i) entries[i] = lut.w[i];
+    if (n_entries) *n_entries = kEncLutEntries;
+    if (first_half_bits) *first_half_bits = kEncLutLo;
+}
+
 int snn_encoder_selftest(int T_live, unsigned long long* mismatches, snn_stream_t stream) {
     if (!mismatches || T_live < 1 || T_live > 32) return fail(SNN_E_ARG, "encoder_selftest: bad argument");
     SNN_ENC_BUCKETS(T_live, (encoder_selftest_kernel<NT><<<148 * 16, 256, 0, (cudaStream_t)stream>>>(T_live, mismatches)));

@@ -133,3 +133,43 @@ def test_workspace_sizes_are_host_only_and_cover_the_carried_state(lib):
     assert R * K * 4 + 2 * R * Hd * 4 + R * Hd * 16 <= b32 <= R * K * 4 + 2 * R * Hd * 4 + R * Hd * 16 + 16384
     assert lib.snn_box_head_workspace_bytes(R, K, Hd, 2, 3) > 0          # T < 3 runs (zero membranes, as the reference)
     assert lib.snn_box_head_workspace_bytes(R, K, Hd, 0, 3) == 0 and lib.snn_box_head_workspace_bytes(R, K, Hd, 33, 3) == 0
+
+
+def test_encoder_lookup_table_against_the_oracle_encoder(lib):
+    """The encoder kernels look the spike train up by the fp16 image of the (clamped) input (snn_encoder_lut).  Every
+    entry without the "evaluate exactly" flag must give the oracle encoder's 31-step train for EVERY fp32 input that
+    rounds to its fp16 value -- checked on both ends of the rounding interval, its neighbours and random members -- the
+    flagged entries are the few whose interval contains a threshold, and the clamp ends are the constant trains."""
+    import numpy as np
+    import torch
+    from oracle import snn_oracle as O
+    n, first = ctypes.c_int(0), ctypes.c_int(0)
+    lib.snn_encoder_lut(None, ctypes.byref(n), ctypes.byref(first))
+    assert n.value == 4097 and first.value == 0x3400
+    ent = (ctypes.c_uint * n.value)()
+    lib.snn_encoder_lut(ent, None, None)
+    ent = np.array(ent[:], dtype=np.uint32)
+    flagged = (ent >> 31) == 1
+    assert 1 <= flagged.sum() <= 65 and ent[0] == 0 and flagged[-1] and ent[-2] == 0x7FFFFFFF      # the last entry holds +inf
+    halves = (np.arange(n.value, dtype=np.uint16) + np.uint16(first.value)).view(np.float16)
+    rng = np.random.default_rng(0)
+    xs, idx = [], []
+    for i, h in enumerate(halves):
+        if flagged[i]:
+            continue
+        hf = np.float32(h)
+        lo = np.float32(0.5) * (np.float32(np.nextafter(h, np.float16(0))) + hf)
+        hi = np.float32(0.5) * (hf + np.float32(np.nextafter(h, np.float16(8))))
+        cand = [np.nextafter(lo, np.float32(8)), hf, np.nextafter(hi, np.float32(0))] + list(rng.uniform(lo, hi, 4).astype(np.float32))
+        if i == 0:
+            cand += [np.float32(-3.0), np.float32(0.0), np.float32(0.2), np.float32(-np.inf)]
+        for x in cand:
+            xc = np.float32(min(max(np.float32(x), np.float32(0.25)), np.float32(4.0)))
+            if np.float16(xc) == h:                      # the input really rounds to this entry
+                xs.append(x); idx.append(i)
+    xs = np.array(xs, dtype=np.float32)
+    z = torch.stack(O.encoder_spikes(torch.from_numpy(xs), 31)).numpy() > 0
+    sim = np.zeros(xs.shape, dtype=np.uint32)
+    for t in range(31):
+        sim |= z[t].astype(np.uint32) << np.uint32(t)
+    assert len(xs) > 20000 and np.array_equal(sim, ent[np.array(idx)])

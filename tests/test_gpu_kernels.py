@@ -1,5 +1,7 @@
 """GPU building-block parity: encoder, the tcgen05 contraction (raw currents) and the fused LIF
 epilogue, each against the CPU oracle, through the C ABI.  Run on the B200 box: pytest -m gpu."""
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -36,6 +38,13 @@ def test_encoder_rows_bit_exact(T):
     g = torch.Generator().manual_seed(5)
     x = (torch.randn(37, 192, generator=g) * 1.5)
     x[0, :8] = torch.tensor([0.25, 0.2500001, 0.439, 0.44, -1.0, 0.0, 1e-30, 100.0])
+    # the ends of the lookup table's clamp, non-finite inputs (+inf spikes exactly once in Norse's arithmetic: the reset
+    # inf - inf leaves NaN) and both neighbours of every one of the encoder's 32 thresholds
+    x[1, :8] = torch.tensor([float("inf"), -float("inf"), float("nan"), 4.0, 3.9999998, 4.0000005, 3.0e38, 2.5])
+    thr = (ctypes.c_float * 33)()
+    lib.snn_encoder_table(thr, None)
+    t = torch.tensor(thr[1:33], dtype=torch.float32)
+    x[2, :32] = t; x[3, :32] = torch.nextafter(t, torch.zeros(32)); x[4, :32] = torch.nextafter(t, torch.full((32,), 9.0))
     xd = x.cuda()
     wb = 1 if T <= 8 else 2 if T <= 16 else 4
     z = torch.zeros(37, 192, dtype=_TRAIN_DTYPE[wb], device="cuda")
