@@ -65,7 +65,8 @@ def _declare(lib):
     lib.snn_roi_align_encode.restype = i
     lib.snn_encoder_table.argtypes = [c.POINTER(c.c_float), c.POINTER(c.c_uint)]; lib.snn_encoder_table.restype = None
     lib.snn_encoder_selftest.argtypes = [i, vp, vp]; lib.snn_encoder_selftest.restype = i
-    lib.snn_encoder_lut.argtypes = [c.POINTER(c.c_uint), pi, pi]; lib.snn_encoder_lut.restype = None
+    lib.snn_encoder_lut.argtypes = [c.POINTER(c.c_ubyte), pi, pi, c.POINTER(c.c_float), c.POINTER(c.c_uint), c.POINTER(c.c_uint)]
+    lib.snn_encoder_lut.restype = None
     lib.snn_last_launch_count.restype = i
     lib.snn_set_cta_group.argtypes = [i]; lib.snn_set_cta_group.restype = None
     lib.snn_set_fc_tiling.argtypes = [i, i, i]; lib.snn_set_fc_tiling.restype = None

@@ -197,18 +197,25 @@ __device__ __forceinline__ uint32_t encode_word(float x, uint32_t tmask) {
     return w[0];
 }
 
-// ---- the encoder as ONE table lookup (round 2)
+// ---- the encoder as a two-step table lookup (round 2)
 // ncu r02c: both encoder kernels are instruction-bound, not HBM-bound (issue slots 73-75 % busy, ALU pipe 65-81 %, DRAM
 // 4.1-4.2 of 6.5 TB/s): 2 instructions per step and neuron are still 14-22 per neuron.  The train is a step function of x
-// with at most 32 steps, all inside (0.25, 2.5]: round x (clamped to [0.25, 4]) to fp16 -- 4097 possible values -- and look
-// the word up.  The lookup is exact whenever every fp32 input that rounds to the same fp16 value has the same train;
-// the <= 64 table entries whose rounding interval contains a threshold carry a flag (bit 31; at most 31 live steps are
-// ever encoded) and take the comparator bank above.  The table is built at compile time from the same thresholds, so
-// the exhaustive self-test (every fp32 bit pattern) covers it: ~9 instructions per neuron instead of 23-30.
+// with at most 32 steps, all inside (0.25, 2.5].  Round x (clamped to [0.25, 4]) to fp16 -- 4097 possible values.  All
+// fp32 inputs that round to one fp16 value form an interval that contains AT MOST ONE threshold (neighbouring thresholds
+// are >= 4 fp16 ulps apart; checked at compile time), so a byte table gives, per fp16 value, the index n of the only
+// threshold that can matter -- the first-spike step of the interval's upper end -- and ONE exact fp32 comparison
+// finishes: word = x >= thr[n] ? train(n) : train(n + 1).  Branch-free, the same cost for every T: clamp, convert,
+// byte lookup, one 16-byte lookup (thr[n], train(n), train(n+1)), compare, select.  Index 33 = below every threshold
+// (train 0; also NaN, which the clamp sends to 0.25); index 0 = the last entry, which also holds +inf, the one input
+// whose train is not periodic (it spikes at step 0, then the arithmetic reset inf - inf leaves NaN): thr = +inf,
+// train 1 if x >= +inf else train(1).  Both tables are built at compile time from the thresholds above, and the
+// exhaustive self-test (every fp32 bit pattern) runs this path as well.
 constexpr int kEncLutLo = 0x3400;            // fp16 bits of 0.25
 constexpr int kEncLutHi = 0x4400;            // fp16 bits of 4.0
 constexpr int kEncLutEntries = kEncLutHi - kEncLutLo + 1;
-struct EncLut { uint32_t w[kEncLutEntries]; };
+constexpr int kEncLutWords = (kEncLutEntries + 3) / 4 + 1;      // the byte table as 32-bit words
+struct EncPair { float thr; uint32_t ge, lt, pad; };           // x >= thr ? ge : lt
+struct EncLut { uint32_t idx[kEncLutWords]; EncPair pair[34]; int ok; };
 
 __host__ __device__ constexpr float enc_half_value(int bits) {       // positive normal fp16 bit pattern -> value
     const int e = (bits >> 10) & 31, m = bits & 1023;
@@ -225,6 +232,7 @@ __host__ __device__ constexpr int enc_first_spike_by_table(const EncTable& tb, f
 __host__ __device__ constexpr EncLut make_enc_lut() {
     const EncTable tb = make_enc_table();
     EncLut l{};
+    l.ok = 1;
     for (int i = 0; i < kEncLutEntries; ++i) {
         const int bits = kEncLutLo + i;
         const float h = enc_half_value(bits);
@@ -232,38 +240,45 @@ __host__ __device__ constexpr EncLut make_enc_lut() {
         // included: conservative about ties); below the first / above the last entry the clamp collapses everything
         const float lo = 0.5f * (enc_half_value(bits - 1) + h), hi = 0.5f * (h + enc_half_value(bits + 1));
         const int n_lo = (i == 0) ? 33 : enc_first_spike_by_table(tb, lo);
-        const int n_hi = (i == kEncLutEntries - 1) ? 1 : enc_first_spike_by_table(tb, hi);
-        const uint32_t word = enc_full_train(n_hi) & 0x7FFFFFFFu;
-        // the last entry also holds +inf, whose train is not the periodic one: evaluated exactly
-        l.w[i] = (n_lo == n_hi && i != kEncLutEntries - 1) ? word : 0x80000000u;
+        int n = (i == 0) ? 33 : enc_first_spike_by_table(tb, hi);
+        if (i == kEncLutEntries - 1) n = 0;                      // [.., +inf]: the special pair
+        else if (n_lo > n + 1) l.ok = 0;                         // two thresholds inside one interval: must not happen
+        l.idx[i >> 2] |= static_cast<uint32_t>(n) << (8 * (i & 3));
     }
+    for (int n = 1; n <= 32; ++n) l.pair[n] = EncPair{tb.thr[n], enc_full_train(n), enc_full_train(n + 1), 0u};
+    l.pair[33] = EncPair{tb.thr[32], 0u, 0u, 0u};                // below every threshold
+    l.pair[0] = EncPair{__builtin_huge_valf(), 1u, enc_full_train(1), 0u};   // x >= +inf ? one spike : every step
     return l;
 }
+constexpr EncLut kEncLutHost = make_enc_lut();
+static_assert(kEncLutHost.ok == 1, "an fp16 rounding interval contains two encoder thresholds");
 __device__ const EncLut g_enc_lut = make_enc_lut();
 
-// block-cooperative copy of the table into shared memory (16 KB)
+constexpr int kEncLutSmemWords = kEncLutWords + 34 * 4;
+constexpr int kEncLutFromSteps = 10;        // encoder kernels: comparator bank below, two-step table from this many live steps on
+// block-cooperative copy of both tables into shared memory (4.7 KB): [byte table][34 x (thr, ge, lt, pad)]
 __device__ __forceinline__ void enc_lut_load(uint32_t* s_lut) {
-    for (int i = threadIdx.x; i < kEncLutEntries; i += blockDim.x) s_lut[i] = g_enc_lut.w[i];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_enc_lut);
+    for (int i = threadIdx.x; i < kEncLutSmemWords; i += blockDim.x) s_lut[i] = src[i];
 }
-// out of line: taken by ~1 % of the neurons (those whose fp16 image sits next to a threshold)
-template <int NT>
-__device__ __noinline__ uint32_t encode_word_slow(float x, uint32_t tmask) { return encode_word<NT>(x, tmask); }
+static_assert(offsetof(EncLut, pair) == kEncLutWords * 4, "the pair table follows the byte table");
 
-// N inputs -> words through the table in shared memory (T_live <= 31); NaN clamps to 0.25 = never spikes, as simulated
-template <int NT, int N>
+// N inputs -> words through the tables in shared memory (any T_live <= 32)
+template <int N>
 __device__ __forceinline__ void encode_words_lut(const float (&x)[N], uint32_t tmask, const uint32_t* __restrict__ s_lut, uint32_t (&w)[N]) {
     static_assert(N % 2 == 0, "inputs are converted in pairs");
+    const uint32_t s_idx = smem_u32(s_lut), s_pair = s_idx + kEncLutWords * 4u;
 #pragma unroll
     for (int k = 0; k < N; k += 2) {
         const float a = fminf(fmaxf(x[k], 0.25f), 4.0f), b = fminf(fmaxf(x[k + 1], 0.25f), 4.0f);
         const __half2 h2 = __floats2half2_rn(a, b);
         const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
-        const uint32_t e0 = s_lut[(hb & 0xFFFFu) - kEncLutLo], e1 = s_lut[(hb >> 16) - kEncLutLo];
-        w[k] = e0 & tmask; w[k + 1] = e1 & tmask;
-        if (static_cast<int>(e0 | e1) < 0) {                      // a flagged entry: exact comparator bank for that input
-            if (static_cast<int>(e0) < 0) w[k] = encode_word_slow<NT>(x[k], tmask);
-            if (static_cast<int>(e1) < 0) w[k + 1] = encode_word_slow<NT>(x[k + 1], tmask);
-        }
+        uint32_t n0, n1;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(n0) : "r"(s_idx + (hb & 0xFFFFu) - kEncLutLo));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(n1) : "r"(s_idx + (hb >> 16) - kEncLutLo));
+        const uint4 p0 = lds_v4(s_pair + n0 * 16u), p1 = lds_v4(s_pair + n1 * 16u);
+        w[k] = (x[k] >= __uint_as_float(p0.x) ? p0.y : p0.z) & tmask;
+        w[k + 1] = (x[k + 1] >= __uint_as_float(p1.x) ? p1.y : p1.z) & tmask;
     }
 }
 
@@ -319,12 +334,13 @@ __device__ __forceinline__ void store_words16(uint8_t* dst, const uint32_t (&w)[
 // HBM traffic: 4 B read + wb B written per input neuron (the per-timestep planes never exist).
 template <int NT, int WB>
 __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant__ EncParams p) {
-    __shared__ uint32_t s_lut[kEncLutEntries];
-    const bool use_lut = p.T_live <= 31;
-    if (use_lut) enc_lut_load(s_lut);
+    // the two-step table pays from ~10 live steps on (11.5 instructions per neuron whatever T, against 2 per step)
+    constexpr bool kLut = NT >= kEncLutFromSteps;
+    __shared__ __align__(16) uint32_t s_lut[kLut ? kEncLutSmemWords : 4];
+    if constexpr (kLut) enc_lut_load(s_lut);
     griddep_launch_dependents();
     griddep_wait();             // the words buffer may still be read by the previous forward's GEMM
-    __syncthreads();
+    if constexpr (kLut) __syncthreads();
     const int lane = threadIdx.x & 31;
     const int n_warps = gridDim.x * (blockDim.x >> 5);
     const int cgroups = p.C / kEncCh;
@@ -354,7 +370,7 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
             uint32_t w[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) xs[k] = xv[16 * h + k];
-            if (use_lut) encode_words_lut<NT, 16>(xs, tmask, s_lut, w);
+            if constexpr (kLut) encode_words_lut<16>(xs, tmask, s_lut, w);
             else encode_words<NT, 16>(xs, tmask, w);
             if (ok) store_words16<WB>(dst + 16 * h * WB, w);
         }
@@ -365,12 +381,12 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
 template <int NT, int WB>
 __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total16, int T_live,
                                                           uint8_t* __restrict__ z) {
-    __shared__ uint32_t s_lut[kEncLutEntries];
-    const bool use_lut = T_live <= 31;
-    if (use_lut) enc_lut_load(s_lut);
+    constexpr bool kLut = NT >= kEncLutFromSteps;
+    __shared__ __align__(16) uint32_t s_lut[kLut ? kEncLutSmemWords : 4];
+    if constexpr (kLut) enc_lut_load(s_lut);
     griddep_launch_dependents();
     griddep_wait();
-    __syncthreads();
+    if constexpr (kLut) __syncthreads();
     const uint32_t tmask = (T_live >= 32) ? 0xFFFFFFFFu : ((1u << T_live) - 1u);
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total16;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -378,7 +394,7 @@ __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restric
         const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
         const float xs[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
         uint32_t w[16];
-        if (use_lut) encode_words_lut<NT, 16>(xs, tmask, s_lut, w);
+        if constexpr (kLut) encode_words_lut<16>(xs, tmask, s_lut, w);
         else encode_words<NT, 16>(xs, tmask, w);
         store_words16<WB>(z + i * 16 * WB, w);
     }
@@ -990,7 +1006,7 @@ __global__ void __launch_bounds__(256, kRoiUnroll <= 2 ? 3 : 2) roi_align_encode
 // Exhaustive check of the comparator bank against the simulation: every one of the 2^32 fp32 bit patterns.
 template <int NT>
 __global__ void __launch_bounds__(256) encoder_selftest_kernel(int T_live, unsigned long long* __restrict__ mismatches) {
-    __shared__ uint32_t s_lut[kEncLutEntries];
+    __shared__ __align__(16) uint32_t s_lut[kEncLutSmemWords];
     enc_lut_load(s_lut);
     __syncthreads();
     const uint32_t tmask = (T_live >= 32) ? 0xFFFFFFFFu : ((1u << T_live) - 1u);
@@ -1000,15 +1016,14 @@ __global__ void __launch_bounds__(256) encoder_selftest_kernel(int T_live, unsig
         const float x = __uint_as_float(static_cast<uint32_t>(b));
         const uint32_t want = encode_train(x, T_live);
         bad += encode_word<NT>(x, tmask) != want;
-        if (T_live <= 31) {                       // the table path of the encoder kernels, in both pair positions
-            const float xs[2] = {x, __uint_as_float(static_cast<uint32_t>(b) ^ 0x00400000u)};
-            uint32_t w[2];
-            encode_words_lut<NT, 2>(xs, tmask, s_lut, w);
-            bad += w[0] != want;
-            const float ys[2] = {xs[1], x};
-            encode_words_lut<NT, 2>(ys, tmask, s_lut, w);
-            bad += w[1] != want;
-        }
+        // the table path of the encoder kernels, in both pair positions
+        const float xs[2] = {x, __uint_as_float(static_cast<uint32_t>(b) ^ 0x00400000u)};
+        uint32_t w[2];
+        encode_words_lut<2>(xs, tmask, s_lut, w);
+        bad += w[0] != want;
+        const float ys[2] = {xs[1], x};
+        encode_words_lut<2>(ys, tmask, s_lut, w);
+        bad += w[1] != want;
     }
     for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, static_cast<unsigned long long>(bad));

@@ -136,40 +136,41 @@ def test_workspace_sizes_are_host_only_and_cover_the_carried_state(lib):
 
 
 def test_encoder_lookup_table_against_the_oracle_encoder(lib):
-    """The encoder kernels look the spike train up by the fp16 image of the (clamped) input (snn_encoder_lut).  Every
-    entry without the "evaluate exactly" flag must give the oracle encoder's 31-step train for EVERY fp32 input that
-    rounds to its fp16 value -- checked on both ends of the rounding interval, its neighbours and random members -- the
-    flagged entries are the few whose interval contains a threshold, and the clamp ends are the constant trains."""
+    """The encoder kernels find the spike train by a two-step lookup (snn_encoder_lut): the fp16 image of the clamped
+    input names the one threshold its rounding interval can contain, one exact fp32 comparison finishes.  Replayed here
+    in numpy for inputs on both ends of every fp16 rounding interval, its centre, random members and the non-finite /
+    out-of-range cases, against the oracle's step-by-step encoder over 32 steps."""
     import numpy as np
     import torch
     from oracle import snn_oracle as O
     n, first = ctypes.c_int(0), ctypes.c_int(0)
-    lib.snn_encoder_lut(None, ctypes.byref(n), ctypes.byref(first))
+    thr, ge, lt = (ctypes.c_float * 34)(), (ctypes.c_uint * 34)(), (ctypes.c_uint * 34)()
+    lib.snn_encoder_lut(None, ctypes.byref(n), ctypes.byref(first), thr, ge, lt)
     assert n.value == 4097 and first.value == 0x3400
-    ent = (ctypes.c_uint * n.value)()
-    lib.snn_encoder_lut(ent, None, None)
-    ent = np.array(ent[:], dtype=np.uint32)
-    flagged = (ent >> 31) == 1
-    assert 1 <= flagged.sum() <= 65 and ent[0] == 0 and flagged[-1] and ent[-2] == 0x7FFFFFFF      # the last entry holds +inf
+    idx = (ctypes.c_ubyte * n.value)()
+    lib.snn_encoder_lut(idx, None, None, None, None, None)
+    idx = np.array(idx[:], dtype=np.int64)
+    thr, ge, lt = np.array(thr[:], dtype=np.float32), np.array(ge[:], dtype=np.uint32), np.array(lt[:], dtype=np.uint32)
+    assert idx[0] == 33 and idx[-1] == 0 and idx.max() == 33 and np.isinf(thr[0]) and ge[0] == 1 and lt[0] == 0xFFFFFFFF
     halves = (np.arange(n.value, dtype=np.uint16) + np.uint16(first.value)).view(np.float16)
     rng = np.random.default_rng(0)
-    xs, idx = [], []
-    for i, h in enumerate(halves):
-        if flagged[i]:
-            continue
+    xs = [np.float32(v) for v in (-3.0, 0.0, 0.2, -np.inf, np.inf, np.nan, 5.0, 1e30, 3.9999998, 4.0000005, 0.25, 1e-30)]
+    for h in halves:
         hf = np.float32(h)
         lo = np.float32(0.5) * (np.float32(np.nextafter(h, np.float16(0))) + hf)
         hi = np.float32(0.5) * (hf + np.float32(np.nextafter(h, np.float16(8))))
-        cand = [np.nextafter(lo, np.float32(8)), hf, np.nextafter(hi, np.float32(0))] + list(rng.uniform(lo, hi, 4).astype(np.float32))
-        if i == 0:
-            cand += [np.float32(-3.0), np.float32(0.0), np.float32(0.2), np.float32(-np.inf)]
-        for x in cand:
-            xc = np.float32(min(max(np.float32(x), np.float32(0.25)), np.float32(4.0)))
-            if np.float16(xc) == h:                      # the input really rounds to this entry
-                xs.append(x); idx.append(i)
+        xs += [lo, np.nextafter(lo, np.float32(8)), hf, np.nextafter(hi, np.float32(0)), hi] + list(rng.uniform(lo, hi, 3).astype(np.float32))
+    for t in thr[1:33]:                                  # both neighbours of every threshold
+        xs += [t, np.nextafter(t, np.float32(0)), np.nextafter(t, np.float32(9))]
     xs = np.array(xs, dtype=np.float32)
-    z = torch.stack(O.encoder_spikes(torch.from_numpy(xs), 31)).numpy() > 0
+    with np.errstate(invalid="ignore"):
+        xc = np.minimum(np.maximum(xs, np.float32(0.25)), np.float32(4.0))
+        xc = np.where(np.isnan(xs), np.float32(0.25), xc)                  # fmaxf(NaN, 0.25) = 0.25 on the device
+        e = xc.astype(np.float16).view(np.uint16).astype(np.int64) - first.value
+        k = idx[e]
+        got = np.where(xs >= thr[k], ge[k], lt[k]).astype(np.uint32)
+    z = torch.stack(O.encoder_spikes(torch.from_numpy(xs), 32)).numpy() > 0
     sim = np.zeros(xs.shape, dtype=np.uint32)
-    for t in range(31):
+    for t in range(32):
         sim |= z[t].astype(np.uint32) << np.uint32(t)
-    assert len(xs) > 20000 and np.array_equal(sim, ent[np.array(idx)])
+    assert len(xs) > 30000 and np.array_equal(sim, got)
