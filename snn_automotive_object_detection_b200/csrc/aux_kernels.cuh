@@ -213,7 +213,7 @@ __device__ __forceinline__ uint32_t encode_word(float x, uint32_t tmask) {
 constexpr int kEncLutLo = 0x3400;            // fp16 bits of 0.25
 constexpr int kEncLutHi = 0x4400;            // fp16 bits of 4.0
 constexpr int kEncLutEntries = kEncLutHi - kEncLutLo + 1;
-constexpr int kEncLutWords = (kEncLutEntries + 3) / 4 + 1;      // the byte table as 32-bit words
+constexpr int kEncLutWords = ((kEncLutEntries + 3) / 4 + 3) / 4 * 4;      // the byte table as 32-bit words, padded so that the 16-byte pairs behind it are aligned
 struct EncPair { float thr; uint32_t ge, lt, pad; };           // x >= thr ? ge : lt
 struct EncLut { uint32_t idx[kEncLutWords]; EncPair pair[34]; int ok; };
 
@@ -261,7 +261,7 @@ __device__ __forceinline__ void enc_lut_load(uint32_t* s_lut) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_enc_lut);
     for (int i = threadIdx.x; i < kEncLutSmemWords; i += blockDim.x) s_lut[i] = src[i];
 }
-static_assert(offsetof(EncLut, pair) == kEncLutWords * 4, "the pair table follows the byte table");
+static_assert(offsetof(EncLut, pair) == kEncLutWords * 4 && (kEncLutWords * 4) % 16 == 0, "the 16-byte pairs follow the byte table, aligned");
 
 // N inputs -> words through the tables in shared memory (any T_live <= 32)
 template <int N>
