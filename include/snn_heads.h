@@ -112,14 +112,7 @@ int snn_encode_rows(const float* x, int R, int K, int T_live, void* z_words, snn
  * n(x) = min{ n : x >= thresholds[n] }.  HOST call: copies the 33-entry tables (index n = 1..32; thresholds[n] =
  * the smallest fp32 input whose first spike comes at step <= n; deltas[n] = train(n) ^ train(n+1) over 32 steps). */
 void snn_encoder_table(float* thresholds33, unsigned int* deltas33);
-/* The encoder kernels evaluate that comparator bank through a two-step lookup: the input, clamped to [0.25, 4], is
- * rounded to fp16 and indexes a 4097-entry byte table that names the only threshold its rounding interval can contain
- * (index n = 1..32; 33 = below every threshold; 0 = the last entry, which also holds +inf); one exact comparison
- * finishes: word = x >= thr[n] ? ge[n] : lt[n] (32-step trains; the caller masks the live steps).  HOST call: copies
- * the byte table (may be NULL), its length, the fp16 bit pattern of entry 0 (0.25) and the 34 (thr, ge, lt) triples. */
-void snn_encoder_lut(unsigned char* index_of_half, int* n_entries, int* first_half_bits, float* thr34, unsigned int* ge34,
-                     unsigned int* lt34);
-/* Exhaustive device self-test (comparator bank AND table path): counts, over ALL 2^32 fp32 bit patterns, the inputs whose comparator-bank word differs
+/* Exhaustive device self-test: counts, over ALL 2^32 fp32 bit patterns, the inputs whose comparator-bank word differs
  * from the step-by-step simulation of lif_current_encoder for T_live steps; *mismatches (device, zeroed by the caller)
  * must stay 0. */
 int snn_encoder_selftest(int T_live, unsigned long long* mismatches, snn_stream_t stream);

@@ -24,7 +24,7 @@ EXPORTS = [
     "snn_box_head_workspace_bytes", "snn_box_head_forward", "snn_fc_lif_layer", "snn_encode_rows",
     "snn_last_launch_count", "snn_set_cta_group", "snn_profile_enable", "snn_profile_read", "snn_rpn_decode_selected",
     "snn_roi_align_encode", "snn_box_head_forward_encoded", "snn_encoder_table", "snn_encoder_selftest", "snn_set_fc_tiling", "snn_set_role_timers",
-    "snn_set_clock_probe", "snn_host_cache_stats", "snn_rpn_topk_keys", "snn_set_roi_kernel", "snn_li_readout_nhwc", "snn_li_readout_rows", "snn_rpn_topk_workspace_bytes", "snn_rpn_topk_select", "snn_encoder_lut",
+    "snn_set_clock_probe", "snn_host_cache_stats", "snn_rpn_topk_keys", "snn_set_roi_kernel", "snn_li_readout_nhwc", "snn_li_readout_rows", "snn_rpn_topk_workspace_bytes", "snn_rpn_topk_select",
 ]
 # the ABI the argtypes below describe (include/snn_heads.h SNN_ABI_VERSION); a library of another version is refused
 EXPECTED_ABI = 5
@@ -65,8 +65,6 @@ def _declare(lib):
     lib.snn_roi_align_encode.restype = i
     lib.snn_encoder_table.argtypes = [c.POINTER(c.c_float), c.POINTER(c.c_uint)]; lib.snn_encoder_table.restype = None
     lib.snn_encoder_selftest.argtypes = [i, vp, vp]; lib.snn_encoder_selftest.restype = i
-    lib.snn_encoder_lut.argtypes = [c.POINTER(c.c_ubyte), pi, pi, c.POINTER(c.c_float), c.POINTER(c.c_uint), c.POINTER(c.c_uint)]
-    lib.snn_encoder_lut.restype = None
     lib.snn_last_launch_count.restype = i
     lib.snn_set_cta_group.argtypes = [i]; lib.snn_set_cta_group.restype = None
     lib.snn_set_fc_tiling.argtypes = [i, i, i]; lib.snn_set_fc_tiling.restype = None

@@ -197,90 +197,14 @@ __device__ __forceinline__ uint32_t encode_word(float x, uint32_t tmask) {
     return w[0];
 }
 
-// ---- the encoder as a two-step table lookup (round 2)
-// ncu r02c: both encoder kernels are instruction-bound, not HBM-bound (issue slots 73-75 % busy, ALU pipe 65-81 %, DRAM
-// 4.1-4.2 of 6.5 TB/s): 2 instructions per step and neuron are still 14-22 per neuron.  The train is a step function of x
-// with at most 32 steps, all inside (0.25, 2.5].  Round x (clamped to [0.25, 4]) to fp16 -- 4097 possible values.  All
-// fp32 inputs that round to one fp16 value form an interval that contains AT MOST ONE threshold (neighbouring thresholds
-// are >= 4 fp16 ulps apart; checked at compile time), so a byte table gives, per fp16 value, the index n of the only
-// threshold that can matter -- the first-spike step of the interval's upper end -- and ONE exact fp32 comparison
-// finishes: word = x >= thr[n] ? train(n) : train(n + 1).  Branch-free, the same cost for every T: clamp, convert,
-// byte lookup, one 16-byte lookup (thr[n], train(n), train(n+1)), compare, select.  Index 33 = below every threshold
-// (train 0; also NaN, which the clamp sends to 0.25); index 0 = the last entry, which also holds +inf, the one input
-// whose train is not periodic (it spikes at step 0, then the arithmetic reset inf - inf leaves NaN): thr = +inf,
-// train 1 if x >= +inf else train(1).  Both tables are built at compile time from the thresholds above, and the
-// exhaustive self-test (every fp32 bit pattern) runs this path as well.
-constexpr int kEncLutLo = 0x3400;            // fp16 bits of 0.25
-constexpr int kEncLutHi = 0x4400;            // fp16 bits of 4.0
-constexpr int kEncLutEntries = kEncLutHi - kEncLutLo + 1;
-constexpr int kEncLutWords = ((kEncLutEntries + 3) / 4 + 3) / 4 * 4;      // the byte table as 32-bit words, padded so that the 16-byte pairs behind it are aligned
-struct EncPair { float thr; uint32_t ge, lt, pad; };           // x >= thr ? ge : lt
-struct EncLut { uint32_t idx[kEncLutWords]; EncPair pair[34]; int ok; };
-
-__host__ __device__ constexpr float enc_half_value(int bits) {       // positive normal fp16 bit pattern -> value
-    const int e = (bits >> 10) & 31, m = bits & 1023;
-    float v = 1.0f + static_cast<float>(m) * (1.0f / 1024.0f);
-    for (int i = e; i < 15; ++i) v *= 0.5f;
-    for (int i = 15; i < e; ++i) v *= 2.0f;
-    return v;
-}
-__host__ __device__ constexpr int enc_first_spike_by_table(const EncTable& tb, float x) {
-    for (int n = 1; n <= 32; ++n)
-        if (x >= tb.thr[n]) return n;
-    return 33;
-}
-__host__ __device__ constexpr EncLut make_enc_lut() {
-    const EncTable tb = make_enc_table();
-    EncLut l{};
-    l.ok = 1;
-    for (int i = 0; i < kEncLutEntries; ++i) {
-        const int bits = kEncLutLo + i;
-        const float h = enc_half_value(bits);
-        // every fp32 value that rounds (to nearest) to h lies in [lo, hi] = the midpoints to its fp16 neighbours (both
-        // included: conservative about ties); below the first / above the last entry the clamp collapses everything
-        const float lo = 0.5f * (enc_half_value(bits - 1) + h), hi = 0.5f * (h + enc_half_value(bits + 1));
-        const int n_lo = (i == 0) ? 33 : enc_first_spike_by_table(tb, lo);
-        int n = (i == 0) ? 33 : enc_first_spike_by_table(tb, hi);
-        if (i == kEncLutEntries - 1) n = 0;                      // [.., +inf]: the special pair
-        else if (n_lo > n + 1) l.ok = 0;                         // two thresholds inside one interval: must not happen
-        l.idx[i >> 2] |= static_cast<uint32_t>(n) << (8 * (i & 3));
-    }
-    for (int n = 1; n <= 32; ++n) l.pair[n] = EncPair{tb.thr[n], enc_full_train(n), enc_full_train(n + 1), 0u};
-    l.pair[33] = EncPair{tb.thr[32], 0u, 0u, 0u};                // below every threshold
-    l.pair[0] = EncPair{__builtin_huge_valf(), 1u, enc_full_train(1), 0u};   // x >= +inf ? one spike : every step
-    return l;
-}
-constexpr EncLut kEncLutHost = make_enc_lut();
-static_assert(kEncLutHost.ok == 1, "an fp16 rounding interval contains two encoder thresholds");
-__device__ const EncLut g_enc_lut = make_enc_lut();
-
-constexpr int kEncLutSmemWords = kEncLutWords + 34 * 4;
-constexpr int kEncLutFromSteps = 10;        // encoder kernels: comparator bank below, two-step table from this many live steps on
-// block-cooperative copy of both tables into shared memory (4.7 KB): [byte table][34 x (thr, ge, lt, pad)]
-__device__ __forceinline__ void enc_lut_load(uint32_t* s_lut) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&g_enc_lut);
-    for (int i = threadIdx.x; i < kEncLutSmemWords; i += blockDim.x) s_lut[i] = src[i];
-}
-static_assert(offsetof(EncLut, pair) == kEncLutWords * 4 && (kEncLutWords * 4) % 16 == 0, "the 16-byte pairs follow the byte table, aligned");
-
-// N inputs -> words through the tables in shared memory (any T_live <= 32)
-template <int N>
-__device__ __forceinline__ void encode_words_lut(const float (&x)[N], uint32_t tmask, const uint32_t* __restrict__ s_lut, uint32_t (&w)[N]) {
-    static_assert(N % 2 == 0, "inputs are converted in pairs");
-    const uint32_t s_idx = smem_u32(s_lut), s_pair = s_idx + kEncLutWords * 4u;
-#pragma unroll
-    for (int k = 0; k < N; k += 2) {
-        const float a = fminf(fmaxf(x[k], 0.25f), 4.0f), b = fminf(fmaxf(x[k + 1], 0.25f), 4.0f);
-        const __half2 h2 = __floats2half2_rn(a, b);
-        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
-        uint32_t n0, n1;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(n0) : "r"(s_idx + (hb & 0xFFFFu) - kEncLutLo));
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(n1) : "r"(s_idx + (hb >> 16) - kEncLutLo));
-        const uint4 p0 = lds_v4(s_pair + n0 * 16u), p1 = lds_v4(s_pair + n1 * 16u);
-        w[k] = (x[k] >= __uint_as_float(p0.x) ? p0.y : p0.z) & tmask;
-        w[k + 1] = (x[k + 1] >= __uint_as_float(p1.x) ? p1.y : p1.z) & tmask;
-    }
-}
+// Tried in round 2 and dropped (profiles/r02/r02k_enc_lut_experiment.txt): the encoder as a table lookup.  ncu r02c shows
+// both encoder kernels instruction-bound rather than HBM-bound (issue slots 73-75 % busy, ALU pipe 65-81 %, DRAM 4.1-4.2
+// of 6.5 TB/s), so a lookup keyed by the fp16 image of the clamped input (4097 values; the rounding interval of one
+// fp16 value contains at most one threshold, so one byte lookup + one 16-byte lookup + one exact compare finish, bit-exact
+// for all 2^32 inputs) looked attractive at 11.5 instructions per neuron against 2 per step.  Measured: the box encoder
+// (11 steps) went from 0.034 to 0.051 ms, a variant with flagged entries and an out-of-line exact path from 0.034 to
+// 0.041 ms and the RPN encoder from 0.063 to 0.070 ms -- 32 lanes reading random shared-memory addresses cost more issue
+// and wavefront cycles than 22 register-only instructions.  The comparator bank stays.
 
 // dispatch a kernel template on the bucket of live steps (exact for the step counts of the reference's sweeps)
 #define SNN_ENC_BUCKETS(T_live, ...)                                            \
@@ -334,13 +258,8 @@ __device__ __forceinline__ void store_words16(uint8_t* dst, const uint32_t (&w)[
 // HBM traffic: 4 B read + wb B written per input neuron (the per-timestep planes never exist).
 template <int NT, int WB>
 __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant__ EncParams p) {
-    // the two-step table pays from ~10 live steps on (11.5 instructions per neuron whatever T, against 2 per step)
-    constexpr bool kLut = NT >= kEncLutFromSteps;
-    __shared__ __align__(16) uint32_t s_lut[kLut ? kEncLutSmemWords : 4];
-    if constexpr (kLut) enc_lut_load(s_lut);
     griddep_launch_dependents();
     griddep_wait();             // the words buffer may still be read by the previous forward's GEMM
-    if constexpr (kLut) __syncthreads();
     const int lane = threadIdx.x & 31;
     const int n_warps = gridDim.x * (blockDim.x >> 5);
     const int cgroups = p.C / kEncCh;
@@ -370,8 +289,7 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
             uint32_t w[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) xs[k] = xv[16 * h + k];
-            if constexpr (kLut) encode_words_lut<16>(xs, tmask, s_lut, w);
-            else encode_words<NT, 16>(xs, tmask, w);
+            encode_words<NT, 16>(xs, tmask, w);
             if (ok) store_words16<WB>(dst + 16 * h * WB, w);
         }
     }
@@ -381,12 +299,8 @@ __global__ void __launch_bounds__(256) encode_nchw_kernel(const __grid_constant_
 template <int NT, int WB>
 __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restrict__ x, size_t total16, int T_live,
                                                           uint8_t* __restrict__ z) {
-    constexpr bool kLut = NT >= kEncLutFromSteps;
-    __shared__ __align__(16) uint32_t s_lut[kLut ? kEncLutSmemWords : 4];
-    if constexpr (kLut) enc_lut_load(s_lut);
     griddep_launch_dependents();
     griddep_wait();
-    if constexpr (kLut) __syncthreads();
     const uint32_t tmask = (T_live >= 32) ? 0xFFFFFFFFu : ((1u << T_live) - 1u);
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total16;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -394,8 +308,7 @@ __global__ void __launch_bounds__(256) encode_rows_kernel(const float* __restric
         const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
         const float xs[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
         uint32_t w[16];
-        if constexpr (kLut) encode_words_lut<16>(xs, tmask, s_lut, w);
-        else encode_words<NT, 16>(xs, tmask, w);
+        encode_words<NT, 16>(xs, tmask, w);
         store_words16<WB>(z + i * 16 * WB, w);
     }
 }
@@ -1006,24 +919,12 @@ __global__ void __launch_bounds__(256, kRoiUnroll <= 2 ? 3 : 2) roi_align_encode
 // Exhaustive check of the comparator bank against the simulation: every one of the 2^32 fp32 bit patterns.
 template <int NT>
 __global__ void __launch_bounds__(256) encoder_selftest_kernel(int T_live, unsigned long long* __restrict__ mismatches) {
-    __shared__ __align__(16) uint32_t s_lut[kEncLutSmemWords];
-    enc_lut_load(s_lut);
-    __syncthreads();
     const uint32_t tmask = (T_live >= 32) ? 0xFFFFFFFFu : ((1u << T_live) - 1u);
     unsigned int bad = 0;
     for (unsigned long long b = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; b < (1ull << 32);
          b += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
         const float x = __uint_as_float(static_cast<uint32_t>(b));
-        const uint32_t want = encode_train(x, T_live);
-        bad += encode_word<NT>(x, tmask) != want;
-        // the table path of the encoder kernels, in both pair positions
-        const float xs[2] = {x, __uint_as_float(static_cast<uint32_t>(b) ^ 0x00400000u)};
-        uint32_t w[2];
-        encode_words_lut<2>(xs, tmask, s_lut, w);
-        bad += w[0] != want;
-        const float ys[2] = {xs[1], x};
-        encode_words_lut<2>(ys, tmask, s_lut, w);
-        bad += w[1] != want;
+        bad += encode_word<NT>(x, tmask) != encode_train(x, T_live);
     }
     for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, static_cast<unsigned long long>(bad));

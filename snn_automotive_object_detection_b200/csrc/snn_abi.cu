@@ -1173,20 +1173,6 @@ void snn_encoder_table(float* thresholds33, unsigned int* deltas33) {
     }
 }
 
-void snn_encoder_lut(unsigned char* index_of_half, int* n_entries, int* first_half_bits, float* thr34, unsigned int* ge34,
-                     unsigned int* lt34) {
-    static const EncLut lut = make_enc_lut();
-    if (index_of_half)
-        for (int i = 0; i < kEncLutEntries; ++i) index_of_half[i] = static_cast<unsigned char>((lut.idx[i >> 2] >> (8 * (i & 3))) & 255u);
-    if (n_entries) *n_entries = kEncLutEntries;
-    if (first_half_bits) *first_half_bits = kEncLutLo;
-    for (int n = 0; n < 34; ++n) {
-        if (thr34) thr34[n] = lut.pair[n].thr;
-        if (ge34) ge34[n] = lut.pair[n].ge;
-        if (lt34) lt34[n] = lut.pair[n].lt;
-    }
-}
-
 int snn_encoder_selftest(int T_live, unsigned long long* mismatches, snn_stream_t stream) {
     if (!mismatches || T_live < 1 || T_live > 32) return fail(SNN_E_ARG, "encoder_selftest: bad argument");
     SNN_ENC_BUCKETS(T_live, (encoder_selftest_kernel<NT><<<148 * 16, 256, 0, (cudaStream_t)stream>>>(T_live, mismatches)));

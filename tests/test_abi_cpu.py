@@ -133,44 +133,3 @@ def test_workspace_sizes_are_host_only_and_cover_the_carried_state(lib):
     assert R * K * 4 + 2 * R * Hd * 4 + R * Hd * 16 <= b32 <= R * K * 4 + 2 * R * Hd * 4 + R * Hd * 16 + 16384
     assert lib.snn_box_head_workspace_bytes(R, K, Hd, 2, 3) > 0          # T < 3 runs (zero membranes, as the reference)
     assert lib.snn_box_head_workspace_bytes(R, K, Hd, 0, 3) == 0 and lib.snn_box_head_workspace_bytes(R, K, Hd, 33, 3) == 0
-
-
-def test_encoder_lookup_table_against_the_oracle_encoder(lib):
-    """The encoder kernels find the spike train by a two-step lookup (snn_encoder_lut): the fp16 image of the clamped
-    input names the one threshold its rounding interval can contain, one exact fp32 comparison finishes.  Replayed here
-    in numpy for inputs on both ends of every fp16 rounding interval, its centre, random members and the non-finite /
-    out-of-range cases, against the oracle's step-by-step encoder over 32 steps."""
-    import numpy as np
-    import torch
-    from oracle import snn_oracle as O
-    n, first = ctypes.c_int(0), ctypes.c_int(0)
-    thr, ge, lt = (ctypes.c_float * 34)(), (ctypes.c_uint * 34)(), (ctypes.c_uint * 34)()
-    lib.snn_encoder_lut(None, ctypes.byref(n), ctypes.byref(first), thr, ge, lt)
-    assert n.value == 4097 and first.value == 0x3400
-    idx = (ctypes.c_ubyte * n.value)()
-    lib.snn_encoder_lut(idx, None, None, None, None, None)
-    idx = np.array(idx[:], dtype=np.int64)
-    thr, ge, lt = np.array(thr[:], dtype=np.float32), np.array(ge[:], dtype=np.uint32), np.array(lt[:], dtype=np.uint32)
-    assert idx[0] == 33 and idx[-1] == 0 and idx.max() == 33 and np.isinf(thr[0]) and ge[0] == 1 and lt[0] == 0xFFFFFFFF
-    halves = (np.arange(n.value, dtype=np.uint16) + np.uint16(first.value)).view(np.float16)
-    rng = np.random.default_rng(0)
-    xs = [np.float32(v) for v in (-3.0, 0.0, 0.2, -np.inf, np.inf, np.nan, 5.0, 1e30, 3.9999998, 4.0000005, 0.25, 1e-30)]
-    for h in halves:
-        hf = np.float32(h)
-        lo = np.float32(0.5) * (np.float32(np.nextafter(h, np.float16(0))) + hf)
-        hi = np.float32(0.5) * (hf + np.float32(np.nextafter(h, np.float16(8))))
-        xs += [lo, np.nextafter(lo, np.float32(8)), hf, np.nextafter(hi, np.float32(0)), hi] + list(rng.uniform(lo, hi, 3).astype(np.float32))
-    for t in thr[1:33]:                                  # both neighbours of every threshold
-        xs += [t, np.nextafter(t, np.float32(0)), np.nextafter(t, np.float32(9))]
-    xs = np.array(xs, dtype=np.float32)
-    with np.errstate(invalid="ignore"):
-        xc = np.minimum(np.maximum(xs, np.float32(0.25)), np.float32(4.0))
-        xc = np.where(np.isnan(xs), np.float32(0.25), xc)                  # fmaxf(NaN, 0.25) = 0.25 on the device
-        e = xc.astype(np.float16).view(np.uint16).astype(np.int64) - first.value
-        k = idx[e]
-        got = np.where(xs >= thr[k], ge[k], lt[k]).astype(np.uint32)
-    z = torch.stack(O.encoder_spikes(torch.from_numpy(xs), 32)).numpy() > 0
-    sim = np.zeros(xs.shape, dtype=np.uint32)
-    for t in range(32):
-        sim |= z[t].astype(np.uint32) << np.uint32(t)
-    assert len(xs) > 30000 and np.array_equal(sim, got)
