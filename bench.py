@@ -78,6 +78,8 @@ def parse(argv=None):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of one step's outputs (N = 1)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--conv-multicast", type=int, default=0,
+                    help="experiment: 1 = conv weight tiles fetched once per cluster of two CTA pairs and multicast")
     ap.add_argument("--cta-group", type=int, default=0)
     ap.add_argument("--fc-dual", type=int, default=0, help="fc tiling experiments: 0 auto, 1 single tiles, 2 dual wherever possible")
     ap.add_argument("--fc-units", type=int, default=0, help="fc tiling experiments: cap on the units per accumulator tile")
@@ -313,6 +315,7 @@ def run_ours(args):
         B = args.global_batch // world
     lib = _lib.load()
     lib.snn_set_cta_group(args.cta_group)
+    lib.snn_set_conv_multicast(args.conv_multicast)
     lib.snn_set_fc_tiling(args.fc_dual, args.fc_units, args.fc_no_split)
 
     # weights: the reference constructors' init (random init; there are no checkpoints offline)
@@ -693,7 +696,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": DTYPE_OF_MODE[args.mode], "data": "synthetic",
         "config": {"workload": wl["name"], "images_per_gpu_per_step": B, "global_batch": B * world,
                    "T_rpn": args.t_rpn, "T_det": args.t_det, "rois_per_image": ROIS, "classes": C,
-                   "weight_mode": args.mode, "pieces_per_weight": pieces,
+                   "weight_mode": args.mode, "pieces_per_weight": pieces, "conv_weight_multicast": bool(args.conv_multicast),
                    "l2": f"inputs {in_bytes / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
                    "parallelism": f"image-sharded dp{world}, no hot-path collective",
                    "regime": ("sustained: warm-up, then %.1f s = %d un-reported steps of the same load before the timed region"

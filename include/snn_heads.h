@@ -133,6 +133,10 @@ int snn_fc_lif_layer(const void* z_words, int in_word_bytes, int in_bit0, int R,
 int snn_roi_align_encode(const void* const* feat_ptrs, const int* H, const int* W, const float* scales, int n_levels,
                          int C, const float* rois, const int* roi_level, int R, int pooled_size, int sampling_ratio,
                          int T_live, void* words_out, float* pooled_out, snn_stream_t stream);
+/* Experiment (off by default): 1 = the RPN conv runs in clusters of two CTA pairs and every weight tile is fetched from L2
+ * once per cluster (each CTA loads half of its tile and multicasts it to its counterpart, `.multicast::cluster`); the
+ * results are bit-identical to the default schedule.  0 = one CTA pair per cluster, unicast weight tiles. */
+void snn_set_conv_multicast(int on);
 /* A-B timing: 0 = two channel planes (32 loads) in flight per thread, 1 = four (64 loads, one block fewer per SM) */
 void snn_set_roi_kernel(int which);
 /* snn_box_head_forward on input that is already encoded: words [R][K] of snn_train_word_bytes-like size for T - 1 steps

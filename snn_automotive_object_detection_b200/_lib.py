@@ -24,7 +24,7 @@ EXPORTS = [
     "snn_box_head_workspace_bytes", "snn_box_head_forward", "snn_fc_lif_layer", "snn_encode_rows",
     "snn_last_launch_count", "snn_set_cta_group", "snn_profile_enable", "snn_profile_read", "snn_rpn_decode_selected",
     "snn_roi_align_encode", "snn_box_head_forward_encoded", "snn_encoder_table", "snn_encoder_selftest", "snn_set_fc_tiling", "snn_set_role_timers",
-    "snn_set_clock_probe", "snn_host_cache_stats", "snn_rpn_topk_keys", "snn_set_roi_kernel", "snn_li_readout_nhwc", "snn_li_readout_rows", "snn_rpn_topk_workspace_bytes", "snn_rpn_topk_select",
+    "snn_set_clock_probe", "snn_host_cache_stats", "snn_rpn_topk_keys", "snn_set_roi_kernel", "snn_li_readout_nhwc", "snn_li_readout_rows", "snn_rpn_topk_workspace_bytes", "snn_rpn_topk_select", "snn_set_conv_multicast",
 ]
 # the ABI the argtypes below describe (include/snn_heads.h SNN_ABI_VERSION); a library of another version is refused
 EXPECTED_ABI = 5
@@ -71,6 +71,7 @@ def _declare(lib):
     lib.snn_set_role_timers.argtypes = [vp, i]; lib.snn_set_role_timers.restype = None
     lib.snn_set_clock_probe.argtypes = [vp]; lib.snn_set_clock_probe.restype = None
     lib.snn_set_roi_kernel.argtypes = [i]; lib.snn_set_roi_kernel.restype = None
+    lib.snn_set_conv_multicast.argtypes = [i]; lib.snn_set_conv_multicast.restype = None
     pd = c.POINTER(c.c_double)
     lib.snn_li_readout_nhwc.argtypes = [vp, i, i, i, i, pd, vp, i, vp, i, vp, vp, vp]; lib.snn_li_readout_nhwc.restype = i
     lib.snn_li_readout_rows.argtypes = [vp, i, i, i, pd, vp, i, vp, i, vp, vp, vp]; lib.snn_li_readout_rows.restype = i

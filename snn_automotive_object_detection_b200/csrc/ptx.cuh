@@ -164,6 +164,16 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m,
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
+// the same, multicast: the box lands at the same shared-memory offset in every CTA of `cta_mask` (cluster ranks), and each
+// destination's bytes complete on the barrier at this offset in the LEADER of that destination's CTA pair
+__device__ __forceinline__ void tma_load_2d_2sm_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                      uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                                 int c2) {
     asm volatile(

@@ -28,6 +28,7 @@ thread_local int g_force_cg = 0;
 thread_local int g_fc_dual = 0;      // 0 auto, 1 never, 2 whenever the tile shape allows it (tests)
 thread_local int g_fc_units = 0;     // > 0: cap on the units per fc tile (experiments)
 thread_local int g_fc_split = 0;
+thread_local int g_conv_mc = 0;       // 1: conv weight tiles multicast across clusters of two CTA pairs (experiment, off by default)
 thread_local int g_roi_kernel = 0;   // 0 = two channel planes in flight per thread, 1 = four (A-B timing)
 thread_local unsigned long long* g_role_cycles = nullptr;   // profiling: MMA-thread wait counters of the next launches
 thread_local int g_role_phase = -1;                        // which launch gets them: 0 conv, 1 / 3 fc with K >= 4096 in dual / single tiles, 2 other fc     // 1: never run the last partial wave of dual tiles as single tiles (experiments)
@@ -275,7 +276,7 @@ bool pick_tile(int T_live, bool conv, int m_total, int force_cg, TileCfg& out) {
 }
 
 template <int kCG>
-cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_t st) {
+cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_t st, bool mc = false) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kGemmThreads);
@@ -283,7 +284,7 @@ cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = mc ? 2 * kCG : kCG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
@@ -295,6 +296,14 @@ cudaError_t launch_gemm_cw(const GemmLifParams& p, int CW, int grid, cudaStream_
         return cudaLaunchKernelEx(&cfg, kern, p);                                                              \
     }
     if (p.conv) {
+        if constexpr (kCG == 2) {
+            if (mc && CW == 8) {
+                auto kern = spike_gemm_lif_kernel<2, 8, true, false, true>;
+                cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)kGemmSmemBytes);
+                if (e != cudaSuccess) return e;
+                return cudaLaunchKernelEx(&cfg, kern, p);
+            }
+        }
         if (CW == 8) SNN_LAUNCH(8, true) else SNN_LAUNCH(4, true)
     } else if (p.dual) {
         if constexpr (kCG == 2) {
@@ -387,8 +396,11 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
     if (p.total_tiles <= 0) return SNN_OK;
     int groups = di.sms / tc.cg;
     if (groups > p.total_tiles) groups = p.total_tiles;
+    // weight multicast (experiment): clusters of two CTA pairs, an even number of pairs
+    const bool mc = p.conv && g_conv_mc == 1 && tc.cg == 2 && tc.CW == 8 && p.total_tiles >= 2;
+    if (mc) groups &= ~1;
     const int grid = groups * tc.cg;
-    cudaError_t e = (tc.cg == 2) ? launch_gemm_cw<2>(p, tc.CW, grid, st) : launch_gemm_cw<1>(p, tc.CW, grid, st);
+    cudaError_t e = (tc.cg == 2) ? launch_gemm_cw<2>(p, tc.CW, grid, st, mc) : launch_gemm_cw<1>(p, tc.CW, grid, st);
     if (e != cudaSuccess) return fail(SNN_E_CUDA, "spike_gemm_lif launch failed: %s", cudaGetErrorString(e));
     ++g_launches;
     return SNN_OK;
@@ -627,6 +639,7 @@ void snn_set_role_timers(unsigned long long* device_counters, int phase) {
 }
 void snn_set_clock_probe(unsigned long long* device_counters) { g_clock_probe = device_counters; }
 void snn_set_roi_kernel(int which) { g_roi_kernel = which == 1 ? 1 : 0; }
+void snn_set_conv_multicast(int on) { g_conv_mc = on == 1 ? 1 : 0; }
 void snn_host_cache_stats(unsigned long long* hits, unsigned long long* misses) {
     if (hits) *hits = g_tmap_hits;
     if (misses) *misses = g_tmap_misses;
@@ -762,6 +775,9 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
             cuuint64_t str[1] = {(cuuint64_t)9 * C_in * 2};
             cuuint32_t box[2] = {64, 128};
             rc = make_tmap(&p.tmA, w_shared_prep, 2, dims, str, box);
+            if (rc) return rc;
+            cuuint32_t box_half[2] = {64, 64};
+            rc = make_tmap(&p.tmA_half, w_shared_prep, 2, dims, str, box_half);
             if (rc) return rc;
         }
         int tiles = 0;

@@ -81,6 +81,7 @@ struct LevelDesc {
 
 struct GemmLifParams {
     CUtensorMap tmA;
+    CUtensorMap tmA_half;          // kMC: the same weight tensor with a box of 64 rows (each CTA fetches half of its tile and multicasts it)
     CUtensorMap tmW[kMaxLevels];   // input spike-train words as byte tensors: conv [N][H][W][k_in*in_wb], fc [rows][k_in*in_wb]
     LevelDesc lv[kMaxLevels];
     int n_levels, conv, n_images;
@@ -182,8 +183,15 @@ __device__ __forceinline__ TilePos decode_tile(const GemmLifParams& p, int ut) {
 // them accumulate in TMEM buffer 0, the next Jh in buffer 1, and every weight tile feeds both MMAs -- half the
 // L2 -> SM weight stream and half the producer -> relay -> MMA hand-offs per FLOP; the (short) fc epilogue of a tile
 // then no longer overlaps the next tile's main loop.
-template <int kCG, int CW, bool kConv, bool kDual = false>
+// kMC (conv, cta_group 2): clusters of TWO CTA pairs.  Both pairs walk the same weight sequence (every tile does), so each
+// weight tile is read from L2 once per cluster: every CTA fetches half of its 128-row tile and multicasts it to its
+// counterpart in the other pair (`.multicast::cluster`), a ring stage is refilled when BOTH pairs' MMAs have retired it
+// (a_empty counts two commits, each multicast to the four CTAs), and the pair with one tile less runs a dummy tile with
+// its outputs suppressed so that the two stay in lock-step.  Everything else (spike tiles, accumulators, epilogue,
+// readout) stays per pair.
+template <int kCG, int CW, bool kConv, bool kDual = false, bool kMC = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const __grid_constant__ GemmLifParams p) {
+    static_assert(!kMC || (kCG == 2 && kConv && !kDual), "weight multicast: conv tiles on CTA pairs only");
     extern __shared__ uint8_t smem_raw[];
     const long long k_begin = clock64();          // profiling only (role_cycles)
     unsigned long long k_begin_ns = 0;
@@ -210,17 +218,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = (kCG == 2) ? cluster_ctarank() : 0u;
+    const uint32_t crank = (kCG == 2) ? cluster_ctarank() : 0u;      // rank in the cluster (0..3 with kMC)
+    const uint32_t rank = crank & 1u;                                // rank inside the CTA pair
+    const uint32_t leader_cta = crank & ~1u;                         // cluster rank of this pair's leader
+    const uint16_t pair_mask = static_cast<uint16_t>(0b11u << leader_cta);
     const int n_groups = gridDim.x / kCG;
     const int group = blockIdx.x / kCG;
     const int stages_b = p.stages_b;
     const int stages_w = p.stages_w;
 
-    if (warp == 0 && elect_one()) tma_prefetch_desc(&p.tmA);
+    if (warp == 0 && elect_one()) { tma_prefetch_desc(&p.tmA); if constexpr (kMC) tma_prefetch_desc(&p.tmA_half); }
     if (warp == 3 && elect_one())
         for (int l = 0; l < p.n_levels; ++l) tma_prefetch_desc(&p.tmW[l]);
     if (warp == 1 && elect_one()) {
-        for (int s = 0; s < kStagesA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < kStagesA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], kMC ? 2 : 1); }
         const uint32_t wpg = static_cast<uint32_t>(kProducerWarps / p.n_pg);      // warps per producer group
         for (int s = 0; s < kMaxStagesB; ++s) { mbar_init(&b_ready[s], wpg); mbar_init(&b_peer[s], 1); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < kMaxStagesW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], wpg); }
@@ -242,12 +253,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
     // 64-channel block, read by the 9 taps
     const int n_outer = kConv ? p.cblocks : p.kblocks;
     const int n_inner = kConv ? 9 : 1;
+    // tiles of this CTA pair: group, group + n_groups, ...; with kMC every pair runs the same number of iterations
+    // (the last one may be a dummy: tile >= total_tiles, computed on the last real tile's inputs, outputs suppressed)
+    const int my_iters = kMC ? (p.total_tiles + n_groups - 1) / n_groups
+                             : ((group < p.total_tiles) ? (p.total_tiles - group + n_groups - 1) / n_groups : 0);
 
     if (warp == 0) {
         // ===================================================== TMA producer (weight tiles)
         if (elect_one()) {
             uint32_t sa = 0, pa = 0;
-            for (int tile = group; tile < p.total_tiles; tile += n_groups) {
+            for (int k_it = 0; k_it < my_iters; ++k_it) {
+                const int tile = min(group + k_it * n_groups, p.total_tiles - 1);      // a dummy iteration repeats the last tile
                 const int ut = tile / p.m_tiles, mt = tile - ut * p.m_tiles;
                 const int m0 = mt * 128 * kCG + static_cast<int>(rank) * 128;
                 // k order: fc kb = 0..K/64; conv (64-channel block outer, tap inner) -- the order the MMA issuer uses
@@ -259,7 +275,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                             if (rank == 0) mbar_expect_tx(&a_full[sa], kTileBytesA * kCG);
                             uint8_t* adst = a_ring + sa * kTileBytesA;
                             if constexpr (kCG == 1) tma_load_2d(adst, &p.tmA, &a_full[sa], kcol, s * p.m_total + m0);
-                            else tma_load_2d_2sm(adst, &p.tmA, &a_full[sa], kcol, s * p.m_total + m0);
+                            else if constexpr (!kMC) tma_load_2d_2sm(adst, &p.tmA, &a_full[sa], kcol, s * p.m_total + m0);
+                            else {      // this CTA's half (64 rows, 8 KB) of the tile, to itself and its counterpart in the other pair
+                                const int half = static_cast<int>(crank >> 1);
+                                tma_load_2d_2sm_mcast(adst + half * (kTileBytesA / 2), &p.tmA_half, &a_full[sa], kcol,
+                                                      s * p.m_total + m0 + half * 64,
+                                                      static_cast<uint16_t>((1u << crank) | (1u << (crank ^ 2u))));
+                            }
                             if (++sa == static_cast<uint32_t>(stages_a)) { sa = 0; pa ^= 1u; }
                         }
                     }
@@ -273,7 +295,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             const bool timed = p.role_cycles != nullptr;
             long long c_acc = 0, c_b = 0, c_peer = 0, c_a = 0, c0 = 0;
             const long long c_begin = timed ? clock64() : 0;
-            for (int tile = group; tile < p.total_tiles; tile += n_groups, ++it) {
+            for (int k_it = 0; k_it < my_iters; ++k_it, ++it) {
                 const uint32_t buf = kDual ? 0u : (it & 1u);
                 if (timed) c0 = clock64();
                 if constexpr (kDual) {
@@ -323,19 +345,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                                                   (ko | s | k) != 0 ? 1u : 0u);
                             }
                             if constexpr (kCG == 1) umma_commit<1>(&a_empty[sa]);
-                            else umma_commit_2sm_mcast(&a_empty[sa], 0b11);
+                            else umma_commit_2sm_mcast(&a_empty[sa], kMC ? static_cast<uint16_t>(0b1111) : pair_mask);
                             if (++sa == static_cast<uint32_t>(stages_a)) { sa = 0; pa ^= 1u; }
                         }
                     }
                     if constexpr (kCG == 1) umma_commit<1>(&b_empty[sb]);
-                    else umma_commit_2sm_mcast(&b_empty[sb], 0b11);
+                    else umma_commit_2sm_mcast(&b_empty[sb], pair_mask);
                     if (++sb == static_cast<uint32_t>(stages_b)) { sb = 0; pb ^= 1u; }
                 }
                 if constexpr (kCG == 1) umma_commit<1>(&acc_full[buf]);
-                else umma_commit_2sm_mcast(&acc_full[buf], 0b11);
+                else umma_commit_2sm_mcast(&acc_full[buf], pair_mask);
                 if constexpr (kDual) {
                     if constexpr (kCG == 1) umma_commit<1>(&acc_full[1]);
-                    else umma_commit_2sm_mcast(&acc_full[1], 0b11);
+                    else umma_commit_2sm_mcast(&acc_full[1], pair_mask);
                 }
             }
             if (timed) {
@@ -350,12 +372,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             // relay (one lane per spike-tile ring stage): tell the leader's MMA thread that this CTA's half
             // of the stage is written.  The cluster-scope release costs about a microsecond; one lane per
             // stage keeps stages_b of them in flight, and none of them sits in a producer warp.
-            const int my_tiles = (group < p.total_tiles) ? (p.total_tiles - group + n_groups - 1) / n_groups : 0;
-            const long long total_kb = static_cast<long long>(my_tiles) * n_outer;
+            const long long total_kb = static_cast<long long>(my_iters) * n_outer;
             uint32_t pb = 0;
             for (long long i = lane; i < total_kb; i += stages_b, pb ^= 1u) {
                 mbar_wait_parked(&b_ready[lane], pb);
-                mbar_arrive_remote(&b_peer[lane], 0);
+                mbar_arrive_remote(&b_peer[lane], leader_cta);
             }
         }
     } else if (warp == 3) {
@@ -364,7 +385,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             uint32_t sw = 0, pw = 0;
             const uint32_t w_bytes = (kConv ? static_cast<uint32_t>(p.hrows) * 10u : static_cast<uint32_t>(p.Jh * (kDual ? 2 : 1))) *
                                      64u * static_cast<uint32_t>(p.in_wb);
-            for (int tile = group; tile < p.total_tiles; tile += n_groups) {
+            for (int k_it = 0; k_it < my_iters; ++k_it) {
+                const int tile = min(group + k_it * n_groups, p.total_tiles - 1);
                 const int ut = tile / p.m_tiles;
                 const TilePos tp = decode_tile(p, ut);
                 const int h0 = tp.h0 + static_cast<int>(rank) * p.sub_dh, w0 = tp.w0 + static_cast<int>(rank) * p.sub_dw;
@@ -402,11 +424,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 __syncwarp();
                 const int u = lane & 7, og0 = (lane >> 3) * 4;          // lane = (pixel u, outputs og0 .. og0 + 3)
                 const int chunks_per_sub = p.Jh / CW;
-                const int my_tiles = (group < p.total_tiles) ? (p.total_tiles - group + n_groups - 1) / n_groups : 0;
-                const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * kCG * chunks_per_sub;
+                const uint32_t total_chunks = static_cast<uint32_t>(my_iters) * kCG * chunks_per_sub;
                 const uint32_t w_a = smem_u32(ro_w) + static_cast<uint32_t>(og0 * kRoWStride) * 4u;
                 uint32_t ctr = 0;
-                for (int tile = group; tile < p.total_tiles; tile += n_groups) {
+                for (int k_it = 0; k_it < my_iters; ++k_it) {
+                    const bool tile_valid = group + k_it * n_groups < p.total_tiles;        // false: dummy iteration (kMC)
+                    const int tile = min(group + k_it * n_groups, p.total_tiles - 1);
                     const TilePos tp = decode_tile(p, tile / p.m_tiles);
                     const LevelDesc& L = p.lv[tp.lvl];
                     const size_t hw = static_cast<size_t>(L.H) * L.W;
@@ -434,7 +457,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                         // the buffer is free again (the epilogue only waits for it from its third chunk on, so the last two
                         // arrivals have no partner and are not made)
                         if (ctr + 2u < total_chunks) named_bar_arrive(kBarRoFree + static_cast<int>(buf), kRoBarThreads);
-                        if (hh < L.H && ww + u < L.W) {
+                        if (tile_valid && hh < L.H && ww + u < L.W) {
                             const size_t pix = static_cast<size_t>(hh) * L.W + ww + u;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -468,8 +491,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         const uint32_t pmask = tmask | (tmask << 16);
         const uint32_t one = p.spike_one;
         const bool packed = p.T_box <= 16;             // both neurons of a 32-bit output fit one register
-        const int my_tiles = (group < p.total_tiles) ? (p.total_tiles - group + n_groups - 1) / n_groups : 0;
-        const long long total_kb = static_cast<long long>(my_tiles) * n_outer;
+        const long long total_kb = static_cast<long long>(my_iters) * n_outer;
         const uint32_t b_base = smem_u32(b_ring), w_base = smem_u32(w_ring);
         // row of (unit j, step t): fc t * Jh + j; conv halo pixel (hh, ww): (hh * T_box + t) * 10 + ww
         const uint32_t row_step = (kConv ? 10u : static_cast<uint32_t>(p.Jh)) * 128u;
@@ -638,7 +660,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         const bool e_timed = p.role_cycles != nullptr && rank == 0 && warp == 4 && lane == 0;
         uint32_t e_wait = 0, e_t0 = 0;                 // 32-bit cycle counters: the role is short of registers
         const uint32_t e_begin = e_timed ? static_cast<uint32_t>(clock()) : 0u;
-        for (int tile = group; tile < p.total_tiles; tile += n_groups, ++it) {
+        for (int k_it = 0; k_it < my_iters; ++k_it, ++it) {
+            const bool tile_valid = group + k_it * n_groups < p.total_tiles;                // false: dummy iteration (kMC)
+            const int tile = min(group + k_it * n_groups, p.total_tiles - 1);
             const int ut = tile / p.m_tiles, mt = tile - ut * p.m_tiles;
             const int c = mt * 128 * kCG + static_cast<int>(rank) * 128 + te;
             int H = 1, W = 1, n = 0, h0 = 0, w0 = 0, lvl = 0;
@@ -679,12 +703,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                     if constexpr (kConv) {                     // a chunk lies inside one tile row (TWh == 8, CW <= 8)
                         hh = h0 + sub * p.sub_dh + (j0 >> 3);
                         ww = w0 + sub * p.sub_dw + (j0 & 7);
-                        row_ok = hh < H;
+                        row_ok = tile_valid && hh < H;
                         lim = W - ww;
                         r0 = (static_cast<size_t>(n) * H + hh) * W + ww;
                     } else {
                         const int rr = unit0 + sub * sub_units + j0;
-                        row_ok = true;
+                        row_ok = tile_valid;
                         lim = p.rows - rr;
                         r0 = static_cast<size_t>(rr);
                     }
@@ -803,7 +827,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 // CUTLASS's ClusterBarrier::arrive(cta_id) (the cluster-scope release compiled to an ERRBAR that was 6 %
                 // of the epilogue warps' samples, ncu r02c)
                 if constexpr (kCG == 1) mbar_arrive(&acc_empty[buf]);
-                else mbar_arrive_remote(&acc_empty[buf], 0);
+                else mbar_arrive_remote(&acc_empty[buf], leader_cta);
             }
             }   // bi
         }
