@@ -27,7 +27,7 @@ EXPORTS = [
     "snn_set_clock_probe", "snn_host_cache_stats", "snn_rpn_topk_keys", "snn_set_roi_kernel", "snn_li_readout_nhwc", "snn_li_readout_rows", "snn_rpn_topk_workspace_bytes", "snn_rpn_topk_select", "snn_set_conv_multicast",
 ]
 # the ABI the argtypes below describe (include/snn_heads.h SNN_ABI_VERSION); a library of another version is refused
-EXPECTED_ABI = 5
+EXPECTED_ABI = 6
 PHASES = ["rpn_encoder", "rpn_conv_lif_gemm", "rpn_readout", "box_encoder", "fc6_lif_gemm", "fc7_lif_gemm", "box_readout"]
 
 _lock = threading.Lock()

@@ -776,9 +776,11 @@ int snn_rpn_head_forward(const void* const* feat_ptrs, const int* H, const int* 
             cuuint32_t box[2] = {64, 128};
             rc = make_tmap(&p.tmA, w_shared_prep, 2, dims, str, box);
             if (rc) return rc;
-            cuuint32_t box_half[2] = {64, 64};
-            rc = make_tmap(&p.tmA_half, w_shared_prep, 2, dims, str, box_half);
-            if (rc) return rc;
+            if (g_conv_mc == 1) {          // experiment: half tiles for the multicast schedule
+                cuuint32_t box_half[2] = {64, 64};
+                rc = make_tmap(&p.tmA_half, w_shared_prep, 2, dims, str, box_half);
+                if (rc) return rc;
+            }
         }
         int tiles = 0;
         for (int l = 0; l < n_levels; ++l) {
