@@ -89,6 +89,22 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
         "r"(parity), "r"(20000u)
         : "memory");
 }
+// The same with an explicit sleep between polls.  ncu r02n: the suspend-time hint does not park a warp for long -- the
+// eight producer warps of the conv, which wait most of their life for the MMAs to free a spike-tile stage, came back
+// every ~50 cycles: 246 M of the kernel's 724 M warp instructions (34 %) were this poll loop.  For a waiter with
+// microseconds of slack a sleep of a few hundred nanoseconds removes them (and their share of the power budget).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITB_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONEB_%=;\n\t"
+        "nanosleep.u32 %3;\n\t"
+        "bra WAITB_%=;\n\t"
+        "DONEB_%=:\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(20000u), "r"(sleep_ns)
+        : "memory");
+}
 // wait observing arrivals made by other CTAs of the cluster (acquire at cluster scope)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     asm volatile(

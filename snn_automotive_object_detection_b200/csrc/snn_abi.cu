@@ -233,6 +233,8 @@ const float* scale_of(const void* w_prep, int rows, int cols, int mode) {
 }
 
 
+constexpr int kConvBackoffNs = 0;      // default sleep between polls of the conv producers (ptx.cuh mbar_wait_backoff); set after r02q
+
 // --------------------------------------------------------------------------- tile selection
 struct TileCfg { int cg, T_box, J, Jh, TW, TH, TWh, THh, dw, dh, CW, n_mma; };
 
@@ -390,6 +392,10 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
         const int phase = p.conv ? 0 : (p.kblocks >= 64 ? (p.dual ? 1 : 3) : 2);
         p.role_cycles = (g_role_cycles != nullptr && phase == g_role_phase) ? g_role_cycles : nullptr;
         p.clock_probe = (phase == 0) ? g_clock_probe : nullptr;
+    }
+    {   // conv producers: sleep between polls while the MMAs work through a spike tile (SNN_DBG_BACKOFF=ns overrides)
+        static const int backoff = [] { const char* e = getenv("SNN_DBG_BACKOFF"); return e ? atoi(e) : kConvBackoffNs; }();
+        p.wait_backoff_ns = p.conv ? backoff : 0;
     }
     p.m_tiles = p.m_total / (128 * tc.cg);
     p.total_tiles = p.unit_tiles * p.m_tiles;

@@ -122,6 +122,7 @@ struct GemmLifParams {
     // cycles ([0]) and in globaltimer nanoseconds ([1]) -> the SM clock the kernel really ran at, taken on the very
     // launches a bench times with CUDA events (two timer reads per CTA pair: no effect on the measurement)
     unsigned long long* clock_probe;
+    int wait_backoff_ns;      // conv producers: sleep between polls of the spike-tile stage they wait for (0 = none)
     int dbg_shift, dbg_sbo, dbg_boff;   // swizzle experiment (scratch/swizzle_experiment.py, fc only): row shift, group stride, base-offset field
     // fused leaky-integrator readout (conv, cta_group 2, m_total == 256): mem_{T-1} = W . sum_t kappa_{T-1-t} spk_t
     int fuse_readout, A;
@@ -578,7 +579,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
         uint32_t sb = static_cast<uint32_t>(grp), pb = 0u, sw = static_cast<uint32_t>(grp), pw = 0u;
         for (long long i_kb = grp; i_kb < total_kb; i_kb += n_pg) {
             mbar_wait_parked(&w_full[sw], pw);
-            mbar_wait_parked(&b_empty[sb], pb ^ 1u);
+            // the long wait of a conv producer: a halo'd spike tile serves 9 taps x the pieces (microseconds of MMAs)
+            if (kConv && p.wait_backoff_ns > 0) mbar_wait_backoff(&b_empty[sb], pb ^ 1u, static_cast<uint32_t>(p.wait_backoff_ns));
+            else mbar_wait_parked(&b_empty[sb], pb ^ 1u);
             const uint32_t wslot = w_base + sw * p.slot_w;
             const uint32_t slot = b_base + sb * p.slot_b;
 #pragma unroll
