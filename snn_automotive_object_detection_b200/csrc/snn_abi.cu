@@ -233,7 +233,9 @@ const float* scale_of(const void* w_prep, int rows, int cols, int mode) {
 }
 
 
-constexpr int kConvBackoffNs = 0;      // default sleep between polls of the conv producers (ptx.cuh mbar_wait_backoff); set after r02q
+// sleep between polls of the conv producers' long wait (ptx.cuh mbar_wait_backoff).  r02q A/B on one box, 400 steps each:
+// 0 ns 764.8 / 764.0 img/s, 100 ns 760.9, 300 ns 769.4 / 771.1, 1000 ns 763.2, 3000 ns 762.8 (profiles/r02/r02q_backoff.txt)
+constexpr int kConvBackoffNs = 300;
 
 // --------------------------------------------------------------------------- tile selection
 struct TileCfg { int cg, T_box, J, Jh, TW, TH, TWh, THh, dw, dh, CW, n_mma; };
