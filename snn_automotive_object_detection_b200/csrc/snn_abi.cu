@@ -398,6 +398,8 @@ int launch_gemm(GemmLifParams& p, const TileCfg& tc, const DeviceInfo& di, int m
     {   // conv producers: sleep between polls while the MMAs work through a spike tile (SNN_DBG_BACKOFF=ns overrides)
         static const int backoff = [] { const char* e = getenv("SNN_DBG_BACKOFF"); return e ? atoi(e) : kConvBackoffNs; }();
         p.wait_backoff_ns = p.conv ? backoff : 0;
+        static const int reuse = [] { const char* e = getenv("SNN_DBG_PROD_REUSE"); return e ? atoi(e) : 1; }();
+        p.prod_word_reuse = reuse;
     }
     p.m_tiles = p.m_total / (128 * tc.cg);
     p.total_tiles = p.unit_tiles * p.m_tiles;

@@ -125,6 +125,7 @@ struct GemmLifParams {
     // launches a bench times with CUDA events (two timer reads per CTA pair: no effect on the measurement)
     unsigned long long* clock_probe;
     int wait_backoff_ns;      // conv producers: sleep between polls of the spike-tile stage they wait for (0 = none)
+    int prod_word_reuse;      // fc producers: keep a pair's words in registers across its steps (1; 0 = reload per item, for A/B runs)
     int dbg_shift, dbg_sbo, dbg_boff;   // swizzle experiment (scratch/swizzle_experiment.py, fc only): row shift, group stride, base-offset field
     // fused leaky-integrator readout (conv, cta_group 2, m_total == 256): mem_{T-1} = W . sum_t kappa_{T-1-t} spk_t
     int fuse_readout, A;
@@ -515,6 +516,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             uint32_t it_src[kMaxItems], it_dst[kMaxItems], it_pre[kMaxItems], it_mask[kMaxItems], it_mul[kMaxItems];
             const uint32_t one_ctz = static_cast<uint32_t>(__ffs(static_cast<int>(one)) - 1);
             int n_my = 0;
+            // items of one thread are kProducerWarps * 32 apart: when that is a multiple of n_pairs (fc6: 64 pairs) they are
+            // the T_box steps of ONE pair and read the same 8 words, so the words are loaded once per run of equal sources
+            // (bit i of `reload`: item i's source differs from item i-1's) -- 2 instead of 6 LDS.128 per thread and stage
+            // in the dual fc6, where the producers' 32 KB of loads + 32 KB of stores per stage were most of the shared-memory
+            // wavefronts of a 768-cycle bf16 stage (r02w/r02x A/B on one box: bf16 fc6 0.946 -> 0.926 ms, fp16x2 unchanged)
+            uint32_t reload = 1u;
 #pragma unroll
             for (int i = 0; i < kMaxItems; ++i) {
                 const int item = ptid + i * (kProducerWarps * 32);
@@ -531,6 +538,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                         it_pre[i] = shift - low; it_mask[i] = 0x00010001u << low; it_mul[i] = one >> low;
                     }
                     n_my = i + 1;
+                    if (i > 0 && (it_src[i] != it_src[i - 1] || !p.prod_word_reuse)) reload |= 1u << i;
                 }
             }
             // The stage loop, specialised on the input word size (no per-item branch on it) and with a trip count that is
@@ -543,15 +551,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
                 uint32_t sb = 0u, pb = 0u, sw = 0u, pw = 0u;
                 for (long long i_kb = 0; i_kb < total_kb; ++i_kb) {
                     mbar_wait_parked(&w_full[sw], pw);
-                    mbar_wait_parked(&b_empty[sb], pb ^ 1u);
+                    mbar_wait_parked(&b_empty[sb], pb ^ 1u);   // (a sleep between polls, as in the conv, costs the bf16 fc6 3 % and gives fp16x2 nothing: r02x)
                     const uint32_t wslot = w_base + sw * p.slot_w;
                     const uint32_t slot = b_base + sb * p.slot_b;
+                    uint32_t P[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int i = 0; i < kMaxItems; ++i) {
                         if (i < n_max) {                       // uniform over the block
-                            uint32_t P[4];
                             const uint32_t src = wslot + it_src[i];
-                            if constexpr (WB == 1) {
+                            if (!((reload >> i) & 1u)) {
+                                // same words as the previous item: P is still in registers
+                            } else if constexpr (WB == 1) {
                                 const uint2 v = lds_v2(src);
                                 P[0] = __byte_perm(v.x, 0u, 0x4140); P[1] = __byte_perm(v.x, 0u, 0x4342);
                                 P[2] = __byte_perm(v.y, 0u, 0x4140); P[3] = __byte_perm(v.y, 0u, 0x4342);
