@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) spike_gemm_lif_kernel(const _
             for (int bi = 0; bi < (kDual ? 2 : 1); ++bi) {      // dual: both buffers belong to this tile
             const uint32_t buf = kDual ? static_cast<uint32_t>(bi) : (it & 1u);
             if (e_timed) e_t0 = static_cast<uint32_t>(clock());
-            mbar_wait(&acc_full[buf], kDual ? (it & 1u) : ((it >> 1) & 1u));
+            mbar_wait(&acc_full[buf], kDual ? (it & 1u) : ((it >> 1) & 1u));   // (a sleep between these polls changes nothing, sustained or burst: r02aa)
             if (e_timed) e_wait += static_cast<uint32_t>(clock()) - e_t0;
             tcgen05_fence_after();
             const uint32_t acc = tmem_base + lane_addr + buf * 256u;
