@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 6
+#define SNN_ABI_VERSION 7
 
 #define SNN_MODE_FP32_EXACT 0 /* 3 bf16 pieces per weight (24 mantissa bits): the parity mode          */
 #define SNN_MODE_BF16 1       /* 1 piece: weights rounded to bf16, the throughput mode                 */
@@ -191,6 +191,24 @@ int snn_li_readout_nhwc(const void* trains, int train_bytes, int N, int HW, int 
                         snn_stream_t stream);
 int snn_li_readout_rows(const void* trains, int train_bytes, int R, int Hd, const double* step_weights, const float* w_a,
                         int n_a, const float* w_b, int n_b, float* out_a, float* out_b, snn_stream_t stream);
+
+/* ---- "next" row 8f-4: the detector's post-processing, RoIHeadsSNN.postprocess_detections (roi_heads.py:1075-1176)
+ * after its softmax and box decode: clip (l.1105), score threshold on classes >= 1 (l.1127-1128), the background box of
+ * every RoI none of whose classes passed (l.1139-1150), remove_small_boxes (l.1153-1158), batched NMS of both sets
+ * (l.1161-1162), the detections_per_img best objects (l.1164), objects then background (l.1170-1172) -- one block per
+ * image, no host synchronisation.  The NMS repeats torchvision's CUDA path operation for operation (stable descending
+ * sort, devIoU as compiled for sm_100, the coordinate trick up to 5000 boxes and per-class NMS above), so the kept set
+ * and its order are the ones the reference gets on the same device.
+ * scores [R_total][C] (softmax), boxes [R_total][C][4] (decoded, NOT clipped), both fp32 device; rois_per_image, img_h,
+ * img_w: HOST arrays [N].  Outputs (device, caller-owned): all_boxes [R_total][C][4] clipped; out_boxes [N][cap][4],
+ * out_scores [N][cap], out_labels [N][cap] int64 -- image b's rows [0, counts[b][0]) are its objects, the next
+ * counts[b][1] rows its background boxes; out_counts [N][2] int32.  cap >= detections_per_img + max RoIs per image.
+ * Limits: C >= 2, RoIs per image * (C - 1) <= snn_det_postprocess_max_candidates() (8192). */
+int snn_det_postprocess_max_candidates(void);
+int snn_det_postprocess(const float* scores, const float* boxes, const int* rois_per_image, const int* img_h,
+                        const int* img_w, int N, int C, float score_thresh, float nms_thresh, float min_size,
+                        int detections_per_img, int cap, float* all_boxes, float* out_boxes, float* out_scores,
+                        long long* out_labels, int* out_counts, snn_stream_t stream);
 
 /* number of kernels the last forward call on this thread enqueued (for bench accounting) */
 int snn_last_launch_count(void);

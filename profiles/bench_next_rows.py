@@ -86,7 +86,31 @@ def main():
     coder2 = det_utils.BoxCoder((10.0, 10.0, 5.0, 5.0))
 
     def vectorised():
+        return DP.postprocess_detections(logits, reg, props, [IMG] * N, coder2, 0.4, 0.5, 100, use_kernel=False)
+
+    def kernel_path():         # softmax + decode in torch, everything after in one launch (snn_det_postprocess)
         return DP.postprocess_detections(logits, reg, props, [IMG] * N, coder2, 0.4, 0.5, 100)
+
+    def softmax_and_decode_only():
+        return coder2.decode(reg, props), torch.softmax(logits, -1)
+
+    import ctypes
+    from snn_automotive_object_detection_b200 import _lib
+    lib_ = _lib.load()
+    sc_, bx_ = torch.softmax(logits, -1).contiguous(), coder2.decode(reg, props).reshape(-1, C, 4).contiguous()
+    cap_ = 100 + R
+    bufs_ = [torch.empty_like(bx_), torch.empty(N, cap_, 4, device=dev), torch.empty(N, cap_, device=dev),
+             torch.empty(N, cap_, dtype=torch.int64, device=dev), torch.empty(N, 2, dtype=torch.int32, device=dev)]
+    IntArr = ctypes.c_int * N
+
+    def det_kernel_only():
+        rc = lib_.snn_det_postprocess(sc_.data_ptr(), bx_.data_ptr(), IntArr(*([R] * N)), IntArr(*([IMG[0]] * N)),
+                                     IntArr(*([IMG[1]] * N)), N, C, 0.4, 0.5, 1e-2, 100, cap_, *[t.data_ptr() for t in bufs_],
+                                     torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+
+    va, ka = vectorised(), kernel_path()
+    assert all(torch.equal(x, y) for k in range(5) for x, y in zip(va[k], ka[k])), "kernel path differs from the torch ops"
 
     def loop_mask_only():      # the part the reference does per detection in Python (roi_heads.py:1136-1147)
         scores = torch.softmax(logits, -1)
@@ -148,7 +172,10 @@ def main():
                                     "words_equal_between_kernels": same_words},
             "shapes": "cityscapes batch 2 (294 624 anchors/img, 1000 RoIs/img)",
             "rpn_select_ms": {"reference_path": timed(reference_path), "ours": timed(ours)},
-            "postprocess_ms": {"reference_python_mask_loop_only": timed(loop_mask_only, iters=3), "ours_whole_function": timed(vectorised)}}
+            "postprocess_ms": {"reference_python_mask_loop_only": timed(loop_mask_only, iters=3), "torch_ops_whole_function": timed(vectorised),
+                               "ours_whole_function": timed(kernel_path), "of_which_softmax_and_decode": timed(softmax_and_decode_only),
+                               "of_which_the_kernel": timed(det_kernel_only, iters=50),
+                               "detections_kept": [int(x.shape[0]) for x in ka[0]]}}
     print(json.dumps(line))
 
 

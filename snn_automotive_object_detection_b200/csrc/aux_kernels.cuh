@@ -930,4 +930,292 @@ __global__ void __launch_bounds__(256) encoder_selftest_kernel(int T_live, unsig
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, static_cast<unsigned long long>(bad));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Detector post-processing: RoIHeadsSNN.postprocess_detections, roi_heads.py:1075-1176, after the softmax
+// and the box decode (those stay torch: element-wise, no synchronisation).  One block per image does what the reference
+// does with ~40 small kernels and ~10 host synchronisations per image: clip the boxes to the image (l.1105), select the
+// (RoI, class >= 1) pairs with score > score_thresh (l.1127-1128), keep the background box of every RoI none of whose
+// classes passed (l.1139-1150), drop boxes below min_size (l.1153-1158), batched NMS of both sets (l.1161-1162), keep
+// the detections_per_img best objects (l.1164) and write objects, then background (l.1170-1172).
+// The NMS reproduces torchvision's CUDA path operation for operation, so the kept set and its order are the ones the
+// reference gets on the same device: a stable descending sort of the scores (ties: the lower index first); greedy
+// suppression inside a class; the IoU of torchvision's devIoU as its sm_100 SASS computes it (the keeper's area is an
+// FMUL, the sum of the two areas one FFMA with it as the addend, IEEE division, `> threshold`); and batched_nms's own
+// switch between the coordinate trick (boxes shifted by label * (max coordinate + 1), with the fp32 rounding that
+// implies) up to 5000 boxes and per-class NMS on the unshifted boxes above that.
+constexpr int kDetMaxCand = 8192;           // (RoI, class) pairs / RoIs per image the block sorts in shared memory
+constexpr int kDetThreads = 1024;
+constexpr int kDetMaxImages = 64;           // images per launch (the parameter block holds their geometry)
+constexpr int kDetWords = kDetMaxCand / 32;    // bitmap words (alive / kept)
+constexpr int kDetSmemBytes = kDetMaxCand * (8 + 16 + 2) + kDetWords * 12 + 32 * (16 + 4 + 4 + 4 + 4 + 4) + 32;
+constexpr unsigned short kDetDead = 0xFFFFu;
+
+struct DetParams {
+    const float* scores;            // [R_total][C] softmax scores
+    const float* boxes;             // [R_total][C][4] decoded boxes, not clipped
+    float* all_boxes;               // [R_total][C][4] clipped (the reference's `all_boxes`)
+    float* out_boxes;               // [N][cap][4]
+    float* out_scores;              // [N][cap]
+    long long* out_labels;          // [N][cap]
+    int* out_counts;                // [N][2] objects, background boxes written
+    int N, C, cap, det_per_img;
+    float score_thresh, nms_thresh, min_size;
+    int row0[kDetMaxImages], rows[kDetMaxImages];
+    float img_h[kDetMaxImages], img_w[kDetMaxImages];
+};
+
+// torch.clamp(min=0, max=hi): NaN stays NaN
+__device__ __forceinline__ float det_clamp(float v, float hi) { return v < 0.f ? 0.f : (v > hi ? hi : v); }
+__device__ __forceinline__ float4 det_clip(const float* b, float w, float h) {
+    const float4 v = *reinterpret_cast<const float4*>(b);
+    return make_float4(det_clamp(v.x, w), det_clamp(v.y, h), det_clamp(v.z, w), det_clamp(v.w, h));
+}
+// ascending sort key: higher score first (scores are softmax outputs, >= +0), then the lower index
+__device__ __forceinline__ unsigned long long det_key(float score, unsigned int idx) {
+    const int b = __float_as_int(score);
+    const unsigned int hi = static_cast<unsigned int>(b ^ ((b >> 31) & 0x7FFFFFFF)) ^ 0x80000000u;
+    return (static_cast<unsigned long long>(~hi) << 32) | idx;
+}
+
+// torchvision's devIoU(keeper a, candidate b) > threshold, as nvcc compiled it for sm_100 (see above)
+__device__ __forceinline__ bool det_suppresses(const float4 a, const float Sa, const float4 b, const float thr) {
+    const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z), top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+    const float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
+    const float inter = __fmul_rn(w, h);
+    const float sum = __fmaf_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y), Sa);
+    const float den = __fsub_rn(sum, inter);
+    // The correctly rounded quotient is only needed within 2^-20 of the threshold: with t = fl(thr * den) (relative error
+    // 2^-24), inter > t (1 + 2^-20) implies inter / den > thr (1 + 2^-21), whose rounding is still > thr, and likewise
+    // below -- the same boolean as the division for every input, without the division's ~40-instruction slow path on the
+    // (almost all) pairs that are nowhere near the threshold.
+    const float t = __fmul_rn(thr, den);
+    if (thr >= 0.f && t > 1.0e-30f && t < 1.0e38f) {
+        if (inter > __fmul_rn(t, 1.0f + 0x1p-20f)) return true;
+        if (inter < __fmul_rn(t, 1.0f - 0x1p-20f)) return false;
+    }
+    return __fdiv_rn(inter, den) > thr;
+}
+__device__ __forceinline__ float det_area(const float4 a) { return __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y)); }
+
+__global__ void __launch_bounds__(kDetThreads) det_postprocess_kernel(const __grid_constant__ DetParams p) {
+    extern __shared__ __align__(16) unsigned char det_smem[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(det_smem);                      // [kDetMaxCand]
+    float4* sbox = reinterpret_cast<float4*>(det_smem + static_cast<size_t>(kDetMaxCand) * 8);       // [kDetMaxCand]
+    unsigned short* lab = reinterpret_cast<unsigned short*>(det_smem + static_cast<size_t>(kDetMaxCand) * 24);
+    unsigned int* alive = reinterpret_cast<unsigned int*>(det_smem + static_cast<size_t>(kDetMaxCand) * 26);   // [kDetWords]
+    unsigned int* keptb = alive + kDetWords;                                                          // [kDetWords]
+    float4* kbox = reinterpret_cast<float4*>(keptb + kDetWords);                                      // [32] this round's keepers
+    float* karea = reinterpret_cast<float*>(kbox + 32);                                               // [32]
+    int* klab = reinterpret_cast<int*>(karea + 32);                                                   // [32]
+    int* bidx = klab + 32;                                                                            // [32] this round's candidates
+    int* s_scan = bidx + 32;                                                                          // [32] warp totals
+    unsigned int* s_supp = reinterpret_cast<unsigned int*>(s_scan + 32);                              // [32] pair tests of a round
+    int* s_pref = reinterpret_cast<int*>(s_supp + 32);                                                // [kDetWords] keepers before a word
+    int* s_misc = s_pref + kDetWords;                                     // [0] n, [1] max coordinate bits, [2] batch size, [3] keepers, [4] cursor
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = p.C, Cm1 = C - 1, R = p.rows[img];
+    const size_t r0 = static_cast<size_t>(p.row0[img]);
+    const float W = p.img_w[img], H = p.img_h[img];
+    const float* sc = p.scores + r0 * C;
+    const float* bx = p.boxes + r0 * C * 4;
+
+    // the reference's `all_boxes`: every class's box of every RoI, clipped
+    for (int e = tid; e < R * C; e += kDetThreads)
+        *reinterpret_cast<float4*>(p.all_boxes + (r0 * C + e) * 4) = det_clip(bx + static_cast<size_t>(e) * 4, W, H);
+
+    int n_written = 0;
+    for (int set = 0; set < 2; ++set) {                 // 0: objects (classes >= 1), 1: background (class 0)
+        const int n_src = set == 0 ? R * Cm1 : R;
+        if (tid < 5) s_misc[tid] = 0;
+        __syncthreads();
+        // ---- candidates (any order: the sort below fixes it; the key carries the reference's flat index
+        //      r * (C - 1) + (c - 1), or r)
+        float my_max = 0.f;
+        for (int f0 = 0; f0 < n_src; f0 += kDetThreads) {
+            const int f = f0 + tid;
+            bool pass = false;
+            float s = 0.f;
+            if (f < n_src) {
+                const int r = set == 0 ? f / Cm1 : f;
+                const int c = set == 0 ? 1 + (f - r * Cm1) : 0;
+                s = sc[static_cast<size_t>(r) * C + c];
+                if (set == 0) pass = s > p.score_thresh;
+                else {
+                    pass = s >= 0.f;                    // (keeps NaN rows out, as the reference's torch.where does)
+                    for (int k = 1; k < C; ++k) pass = pass && !(sc[static_cast<size_t>(r) * C + k] > p.score_thresh);
+                }
+                if (pass) {
+                    const float4 b = det_clip(bx + (static_cast<size_t>(r) * C + c) * 4, W, H);
+                    pass = (b.z - b.x >= p.min_size) && (b.w - b.y >= p.min_size);     // remove_small_boxes
+                    if (pass) my_max = fmaxf(my_max, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+                }
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, pass);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_misc[0], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) keys[base + __popc(m & ((1u << lane) - 1u))] = det_key(s, static_cast<unsigned int>(f));
+        }
+        for (int o = 16; o > 0; o >>= 1) my_max = fmaxf(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
+        if (lane == 0) atomicMax(&s_misc[1], __float_as_int(my_max));                  // clipped coordinates are >= 0
+        __syncthreads();
+        const int n = s_misc[0];
+        int P = 2;
+        while (P < n) P <<= 1;
+        for (int t = n + tid; t < P; t += kDetThreads) keys[t] = ~0ull;
+        __syncthreads();
+        // ---- stable descending sort of the scores (bitonic on unique keys)
+        for (int size = 2; size <= P; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = tid; t < (P >> 1); t += kDetThreads) {
+                    const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1)), hi = lo | stride;
+                    const unsigned long long a = keys[lo], b = keys[hi];
+                    const bool up = (lo & size) == 0;
+                    if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+                }
+                __syncthreads();
+            }
+        // ---- the boxes NMS sees: batched_nms shifts them by label * (max + 1) unless there are more than 5000
+        const bool trick = n * 4 <= 20000;
+        const float shift1 = __fadd_rn(__int_as_float(s_misc[1]), 1.0f);
+        for (int t = tid; t < n; t += kDetThreads) {
+            const unsigned int f = static_cast<unsigned int>(keys[t]);
+            const int r = set == 0 ? static_cast<int>(f) / Cm1 : static_cast<int>(f);
+            const int c = set == 0 ? 1 + (static_cast<int>(f) - r * Cm1) : 0;
+            float4 b = det_clip(bx + (static_cast<size_t>(r) * C + c) * 4, W, H);
+            if (trick) {
+                const float off = __fmul_rn(static_cast<float>(c), shift1);
+                b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off); b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
+            }
+            sbox[t] = b;
+            lab[t] = static_cast<unsigned short>(c);
+        }
+        const int n_words = (n + 31) >> 5;
+        for (int w = tid; w < n_words; w += kDetThreads) {
+            alive[w] = (w * 32 + 32 <= n) ? 0xFFFFFFFFu : ((1u << (n - w * 32)) - 1u);
+            keptb[w] = 0u;
+        }
+        __syncthreads();
+        // ---- greedy NMS in sorted order, 32 candidates a round:
+        //  A  warp 0 takes the next 32 boxes still alive;
+        //  B  the block tests every pair of them (thread (l, m): would m suppress l?);
+        //  C  warp 0 reads the keepers off in order (a box is kept iff no KEPT earlier box of the round suppresses it;
+        //     earlier rounds' keepers have been applied to it already) and publishes them;
+        //  D  the block tests every later box still alive against the round's keepers (one warp per box, one lane per
+        //     keeper).
+        const int max_keep = set == 0 ? p.det_per_img : 0x7FFFFFFF;
+        int nk = 0;
+        while (nk < max_keep) {
+            if (warp == 0) {                            // A
+                const int cursor = s_misc[4];
+                int cnt = 0;
+                for (int w0 = cursor >> 5; cnt < 32 && w0 < n_words; w0 += 32) {
+                    const int w = w0 + lane;
+                    unsigned int bits = w < n_words ? alive[w] : 0u;
+                    if (w == (cursor >> 5)) bits &= 0xFFFFFFFFu << (cursor & 31);
+                    const int c = __popc(bits);
+                    int incl = c;
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                    int pos = cnt + incl - c;
+                    while (bits && pos < 32) {
+                        bidx[pos++] = w * 32 + __ffs(static_cast<int>(bits)) - 1;
+                        bits &= bits - 1u;
+                    }
+                    cnt = min(32, cnt + __shfl_sync(0xffffffffu, incl, 31));
+                }
+                if (lane == 0) s_misc[2] = cnt;
+            }
+            __syncthreads();
+            const int cnt = s_misc[2];
+            if (cnt == 0) break;
+            {                                           // B: l = warp, m = lane
+                bool sup = false;
+                if (warp < cnt && lane < warp) {
+                    const int il = bidx[warp], im = bidx[lane];
+                    if (lab[il] == lab[im]) {
+                        const float4 a = sbox[im];
+                        sup = det_suppresses(a, det_area(a), sbox[il], p.nms_thresh);
+                    }
+                }
+                const unsigned int m = __ballot_sync(0xffffffffu, sup);
+                if (lane == 0) s_supp[warp] = m;
+            }
+            __syncthreads();
+            if (warp == 0) {                            // C
+                const unsigned int supp = s_supp[lane];
+                unsigned int kept_mask = 0u, seen = 0u;
+                int k_here = 0;
+                for (int m = 0; m < cnt; ++m) {
+                    const unsigned int sm = __shfl_sync(0xffffffffu, supp, m);
+                    if (nk + k_here >= max_keep) break;                 // the reference keeps the first detections_per_img
+                    seen |= 1u << m;
+                    if ((sm & kept_mask) == 0u) { kept_mask |= 1u << m; ++k_here; }
+                }
+                // every candidate looked at leaves the alive set; keepers are flagged and published for the block
+                if (lane < cnt && ((seen >> lane) & 1u)) {
+                    const int me = bidx[lane];
+                    atomicAnd(&alive[me >> 5], ~(1u << (me & 31)));
+                    if ((kept_mask >> lane) & 1u) {
+                        atomicOr(&keptb[me >> 5], 1u << (me & 31));
+                        const int q = __popc(kept_mask & ((1u << lane) - 1u));
+                        const float4 b = sbox[me];
+                        kbox[q] = b; karea[q] = det_area(b); klab[q] = lab[me];
+                    }
+                }
+                if (lane == 0) { s_misc[3] = k_here; s_misc[4] = bidx[cnt - 1] + 1; }
+            }
+            __syncthreads();
+            const int nkb = s_misc[3], from = s_misc[4];
+            nk += nkb;
+            if (nk >= max_keep) break;
+            {                                           // D
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                float Sa = 0.f;
+                int la = -1;
+                if (lane < nkb) { a = kbox[lane]; Sa = karea[lane]; la = klab[lane]; }
+                for (int jj = from + warp; jj < n; jj += kDetThreads / 32) {
+                    if (!((alive[jj >> 5] >> (jj & 31)) & 1u)) continue;        // uniform over the warp
+                    const bool sup = la == static_cast<int>(lab[jj]) && det_suppresses(a, Sa, sbox[jj], p.nms_thresh);
+                    if (__any_sync(0xffffffffu, sup) && lane == 0) atomicAnd(&alive[jj >> 5], ~(1u << (jj & 31)));
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        // ---- write the keepers in sorted order: rank = number of keepers before
+        {
+            const unsigned int bits = tid < n_words ? keptb[tid] : 0u;          // kDetWords <= kDetThreads
+            int incl = __popc(bits);
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                int v = s_scan[lane];
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+                s_scan[lane] = v;                       // inclusive totals of the warps
+            }
+            __syncthreads();
+            if (tid < n_words) s_pref[tid] = incl - __popc(bits) + (warp ? s_scan[warp - 1] : 0);
+            __syncthreads();
+            for (int t = tid; t < n; t += kDetThreads) {
+                const unsigned int wbits = keptb[t >> 5];
+                if (!((wbits >> (t & 31)) & 1u)) continue;
+                const int row = n_written + s_pref[t >> 5] + __popc(wbits & ((1u << (t & 31)) - 1u));
+                if (row >= p.cap) continue;
+                const unsigned int f = static_cast<unsigned int>(keys[t]);
+                const int r = set == 0 ? static_cast<int>(f) / Cm1 : static_cast<int>(f);
+                const int c = set == 0 ? 1 + (static_cast<int>(f) - r * Cm1) : 0;
+                const size_t o = static_cast<size_t>(img) * p.cap + row;
+                *reinterpret_cast<float4*>(p.out_boxes + o * 4) = det_clip(bx + (static_cast<size_t>(r) * C + c) * 4, W, H);
+                p.out_scores[o] = sc[static_cast<size_t>(r) * C + c];
+                p.out_labels[o] = c;
+            }
+            const int total = s_scan[31];
+            if (tid == 0) p.out_counts[img * 2 + set] = total;
+            n_written += total;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace snn

@@ -1080,6 +1080,54 @@ size_t snn_rpn_topk_workspace_bytes(int n_levels, int N) {
     return topk_ws_layout(n_levels, N).total;
 }
 
+int snn_det_postprocess_max_candidates(void) { return kDetMaxCand; }
+
+int snn_det_postprocess(const float* scores, const float* boxes, const int* rois_per_image, const int* img_h,
+                        const int* img_w, int N, int C, float score_thresh, float nms_thresh, float min_size,
+                        int detections_per_img, int cap, float* all_boxes, float* out_boxes, float* out_scores,
+                        long long* out_labels, int* out_counts, snn_stream_t stream) {
+    if (!rois_per_image || !img_h || !img_w || !out_counts) return fail(SNN_E_ARG, "det_postprocess: null argument");
+    if (N < 1 || C < 2 || detections_per_img < 0 || cap < 1) return fail(SNN_E_ARG, "det_postprocess: bad sizes (N %d, C %d, cap %d)", N, C, cap);
+    long long total = 0;
+    int max_rows = 0;
+    for (int b = 0; b < N; ++b) {
+        if (rois_per_image[b] < 0 || img_h[b] < 0 || img_w[b] < 0) return fail(SNN_E_ARG, "det_postprocess: image %d: bad argument", b);
+        if (static_cast<long long>(rois_per_image[b]) * (C - 1) > kDetMaxCand)
+            return fail(SNN_E_ARG, "det_postprocess: image %d has %d RoIs x %d classes > %d candidates", b, rois_per_image[b], C - 1, kDetMaxCand);
+        total += rois_per_image[b];
+        if (rois_per_image[b] > max_rows) max_rows = rois_per_image[b];
+    }
+    if (total > 0x7FFFFFFFll / (4ll * C)) return fail(SNN_E_ARG, "det_postprocess: too many RoIs");
+    if (cap < detections_per_img + max_rows) return fail(SNN_E_ARG, "det_postprocess: cap %d < detections_per_img + max RoIs per image (%d)", cap, detections_per_img + max_rows);
+    if (total > 0 && (!scores || !boxes || !all_boxes)) return fail(SNN_E_ARG, "det_postprocess: null tensor");
+    if (!out_boxes || !out_scores || !out_labels) return fail(SNN_E_ARG, "det_postprocess: null output");
+    if (((reinterpret_cast<uintptr_t>(boxes) | reinterpret_cast<uintptr_t>(all_boxes)) & 15) != 0)
+        return fail(SNN_E_ARG, "det_postprocess: boxes must be 16-byte aligned");
+    DeviceInfo di;
+    if (int rc = device_info(di)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(det_postprocess_kernel), kDetSmemBytes));
+    int row0 = 0;
+    for (int b0 = 0; b0 < N; b0 += kDetMaxImages) {
+        const int nb = N - b0 < kDetMaxImages ? N - b0 : kDetMaxImages;
+        DetParams p;
+        memset(&p, 0, sizeof(p));
+        p.scores = scores; p.boxes = boxes; p.all_boxes = all_boxes;
+        p.out_boxes = out_boxes + static_cast<size_t>(b0) * cap * 4; p.out_scores = out_scores + static_cast<size_t>(b0) * cap;
+        p.out_labels = out_labels + static_cast<size_t>(b0) * cap; p.out_counts = out_counts + static_cast<size_t>(b0) * 2;
+        p.N = nb; p.C = C; p.cap = cap; p.det_per_img = detections_per_img;
+        p.score_thresh = score_thresh; p.nms_thresh = nms_thresh; p.min_size = min_size;
+        for (int b = 0; b < nb; ++b) {
+            p.row0[b] = row0; p.rows[b] = rois_per_image[b0 + b];
+            p.img_h[b] = static_cast<float>(img_h[b0 + b]); p.img_w[b] = static_cast<float>(img_w[b0 + b]);
+            row0 += rois_per_image[b0 + b];
+        }
+        det_postprocess_kernel<<<nb, kDetThreads, kDetSmemBytes, st>>>(p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SNN_OK;
+}
+
 int snn_rpn_topk_select(const void* const* logits, const int* H, const int* W, int n_levels, int N, int A, int k,
                         long long* idx_out, void* workspace, size_t workspace_bytes, snn_stream_t stream) {
     if (!logits || !H || !W || !idx_out || !workspace) return fail(SNN_E_ARG, "rpn_topk_select: null argument");

@@ -29,14 +29,22 @@ from . import _lib
 # --------------------------------------------------------------------------- rank 4
 def postprocess_detections(class_logits: Tensor, box_regression: Tensor, proposals: List[Tensor],
                            image_shapes: List[Tuple[int, int]], box_coder, score_thresh: float, nms_thresh: float,
-                           detections_per_img: int):
+                           detections_per_img: int, use_kernel=None):
     """Vectorised RoIHeadsSNN.postprocess_detections (roi_heads.py:1075-1176); returns the same 5 lists:
-    boxes, scores, labels (objects first, then every surviving background box), all_scores, all_boxes."""
+    boxes, scores, labels (objects first, then every surviving background box), all_scores, all_boxes.
+    On CUDA tensors everything after the softmax and the box decode is one kernel launch and one read of the
+    per-image counts (`snn_det_postprocess`; `use_kernel=False` keeps the torch/torchvision ops below, which the
+    kernel reproduces bit for bit -- tests/test_detection_post.py)."""
     device = class_logits.device
     num_classes = class_logits.shape[-1]
     boxes_per_image = [b.shape[0] for b in proposals]
     pred_boxes = box_coder.decode(box_regression, proposals)
     pred_scores = F.softmax(class_logits, -1)
+    if use_kernel is None:
+        use_kernel = _det_kernel_eligible(pred_scores, pred_boxes, boxes_per_image, num_classes)
+    if use_kernel:
+        return _postprocess_detections_kernel(pred_scores, pred_boxes, boxes_per_image, image_shapes, score_thresh,
+                                              nms_thresh, detections_per_img)
     pred_boxes_list = pred_boxes.split(boxes_per_image, 0)
     pred_scores_list = pred_scores.split(boxes_per_image, 0)
 
@@ -83,6 +91,42 @@ def postprocess_detections(class_logits: Tensor, box_regression: Tensor, proposa
         all_scores_all_classes.append(scores_all_classes)
         all_pre_nms_boxes.append(boxes_all_classes)
     return all_boxes, all_scores, all_labels, all_scores_all_classes, all_pre_nms_boxes
+
+
+def _det_kernel_eligible(pred_scores, pred_boxes, boxes_per_image, num_classes) -> bool:
+    if not (pred_scores.is_cuda and pred_boxes.is_cuda and pred_scores.dtype == torch.float32
+            and pred_boxes.dtype == torch.float32 and num_classes >= 2 and len(boxes_per_image) >= 1):
+        return False
+    return max(boxes_per_image) * (num_classes - 1) <= _lib.load().snn_det_postprocess_max_candidates()
+
+
+def _postprocess_detections_kernel(pred_scores, pred_boxes, boxes_per_image, image_shapes, score_thresh, nms_thresh,
+                                   detections_per_img):
+    lib = _lib.load()
+    dev = pred_scores.device
+    n_img, C = len(boxes_per_image), pred_scores.shape[-1]
+    pred_scores = pred_scores.contiguous()
+    pred_boxes = pred_boxes.reshape(-1, C, 4).contiguous()
+    cap = int(detections_per_img) + max(boxes_per_image)
+    all_boxes = torch.empty_like(pred_boxes)
+    out_boxes = torch.empty((n_img, cap, 4), dtype=torch.float32, device=dev)
+    out_scores = torch.empty((n_img, cap), dtype=torch.float32, device=dev)
+    out_labels = torch.empty((n_img, cap), dtype=torch.int64, device=dev)
+    counts = torch.empty((n_img, 2), dtype=torch.int32, device=dev)
+    IntArr = ctypes.c_int * n_img
+    with torch.cuda.device(dev):
+        rc = lib.snn_det_postprocess(pred_scores.data_ptr(), pred_boxes.data_ptr(), IntArr(*boxes_per_image),
+                                     IntArr(*[int(s[0]) for s in image_shapes]), IntArr(*[int(s[1]) for s in image_shapes]),
+                                     n_img, C, float(score_thresh), float(nms_thresh), 1e-2, int(detections_per_img), cap,
+                                     all_boxes.data_ptr(), out_boxes.data_ptr(), out_scores.data_ptr(),
+                                     out_labels.data_ptr(), counts.data_ptr(),
+                                     torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "snn_det_postprocess")
+    kept = counts.sum(dim=1).tolist()                      # the one synchronisation of the call
+    boxes = [out_boxes[b, :kept[b]] for b in range(n_img)]
+    scores = [out_scores[b, :kept[b]] for b in range(n_img)]
+    labels = [out_labels[b, :kept[b]] for b in range(n_img)]
+    return (boxes, scores, labels, list(pred_scores.split(boxes_per_image, 0)), list(all_boxes.split(boxes_per_image, 0)))
 
 
 def patch_postprocess(roi_heads):

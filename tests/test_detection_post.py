@@ -218,3 +218,82 @@ def test_topk_ties_are_broken_in_the_references_order(k):
     allf = torch.cat([lg.permute(0, 2, 3, 1).reshape(N, -1) for lg in logits], dim=1)
     assert torch.allclose(probs.cpu(), torch.sigmoid(torch.gather(allf, 1, want)), atol=1e-6)
     assert levels.shape == want.shape and int(levels[0, -1]) == 1
+
+
+def _random_detector_outputs(seed, rois, C, logit_scale, device="cuda", duplicate_rows=0, image_hw=(768, 1536)):
+    """Class logits, box regression and proposals with the statistics of a trained detector's outputs: confident scores
+    (logit_scale), proposals spread over the image with heavy overlap, small regression deltas."""
+    g = torch.Generator().manual_seed(seed)
+    ih, iw = image_hw
+    logits, reg, props = [], [], []
+    for R in rois:
+        lg = torch.randn(R, C, generator=g) * logit_scale
+        ctr = torch.rand(R, 2, generator=g) * torch.tensor([iw * 1.0, ih * 1.0])
+        ctr = (ctr / 96).round() * 96 + torch.randn(R, 2, generator=g) * 12      # clusters of overlapping proposals
+        wh = (torch.rand(R, 2, generator=g) * 0.8 + 0.6) * torch.tensor([120.0, 90.0])
+        pr = torch.cat([ctr - wh / 2, ctr + wh / 2], dim=1)
+        rg = torch.randn(R, 4 * C, generator=g) * torch.tensor([1.0, 1.0, 0.5, 0.5]).repeat(C)
+        if duplicate_rows and R > 2 * duplicate_rows:           # exact ties: identical scores and boxes
+            lg[duplicate_rows:2 * duplicate_rows] = lg[:duplicate_rows]
+            pr[duplicate_rows:2 * duplicate_rows] = pr[:duplicate_rows]
+            rg[duplicate_rows:2 * duplicate_rows] = rg[:duplicate_rows]
+        logits.append(lg); reg.append(rg); props.append(pr.to(device))
+    return torch.cat(logits).to(device), torch.cat(reg).to(device), props, [image_hw] * len(rois)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,rois,C,scale,thresh,per_img,dups", [
+    ("bench_shape", [1000, 1000], 9, 3.0, 0.4, 100, 0),
+    ("low_threshold_many_candidates", [1000, 1000], 9, 1.0, 0.05, 100, 0),     # > 5000 boxes: per-class NMS, no shift
+    ("bdd_5_classes", [1000], 5, 3.0, 0.4, 100, 0),
+    ("ragged_and_empty", [0, 7, 513], 5, 3.0, 0.3, 100, 0),
+    ("two_classes", [300, 20], 2, 2.0, 0.5, 100, 0),
+    ("exact_ties", [400, 400], 9, 3.0, 0.4, 100, 37),
+    ("nothing_passes", [200], 9, 0.1, 0.9, 100, 0),
+    ("few_detections_kept", [1000], 9, 3.0, 0.2, 5, 0),
+    ("max_candidates", [1024], 9, 2.0, 0.01, 300, 0),                          # 8192 (RoI, class) pairs: the kernel's limit
+])
+def test_postprocess_kernel_equals_the_torchvision_path(name, rois, C, scale, thresh, per_img, dups):
+    """SURVEY 8f-4 on the device: `snn_det_postprocess` (one launch per batch) against the torch/torchvision ops of the
+    reference's own function on the same softmax scores and decoded boxes -- the same detections, in the same order,
+    bit for bit: boxes, scores, labels, all_scores, all_boxes."""
+    logits, reg, props, shapes = _random_detector_outputs(sum(map(ord, name)), rois, C, scale, duplicate_rows=dups)
+    coder = det_utils.BoxCoder((10.0, 10.0, 5.0, 5.0))
+    want = DP.postprocess_detections(logits, reg, props, shapes, coder, thresh, 0.5, per_img, use_kernel=False)
+    got = DP.postprocess_detections(logits, reg, props, shapes, coder, thresh, 0.5, per_img, use_kernel=True)
+    auto = DP.postprocess_detections(logits, reg, props, shapes, coder, thresh, 0.5, per_img)
+    n_obj = sum(int((l > 0).sum()) for l in want[2])
+    n_bg = sum(int((l == 0).sum()) for l in want[2])
+    if name == "nothing_passes":
+        assert n_obj == 0 and n_bg > 0
+    elif name in ("low_threshold_many_candidates", "max_candidates"):
+        assert n_obj > 0 and n_bg == 0, (n_obj, n_bg)         # every RoI has a class over the threshold
+    else:
+        assert n_obj > 0 and n_bg > 0, (n_obj, n_bg)
+    for out in (got, auto):
+        for k in range(5):
+            assert len(out[k]) == len(want[k]) == len(rois)
+            for i in range(len(rois)):
+                assert out[k][i].shape == want[k][i].shape, (name, k, i, out[k][i].shape, want[k][i].shape)
+                assert out[k][i].dtype == want[k][i].dtype
+                assert torch.equal(out[k][i], want[k][i]), (name, k, i)
+
+
+@pytest.mark.gpu
+def test_postprocess_kernel_on_the_reference_golden(golden_dir):
+    g = _load(golden_dir, "post_detections")
+    logits, reg, props, shapes = _post_inputs(g, "cuda")
+    coder = det_utils.BoxCoder((10.0, 10.0, 5.0, 5.0))
+    out = DP.postprocess_detections(logits, reg, props, shapes, coder, 0.4, 0.5, 100, use_kernel=True)
+    _check_post(g, out, exact=False)
+
+
+@pytest.mark.gpu
+def test_postprocess_kernel_limits_fall_back_or_fail_loudly():
+    logits, reg, props, shapes = _random_detector_outputs(5, [1200], 9, 2.0)     # 9600 pairs > 8192
+    coder = det_utils.BoxCoder((10.0, 10.0, 5.0, 5.0))
+    want = DP.postprocess_detections(logits, reg, props, shapes, coder, 0.4, 0.5, 100, use_kernel=False)
+    auto = DP.postprocess_detections(logits, reg, props, shapes, coder, 0.4, 0.5, 100)       # torch ops: over the limit
+    assert all(torch.equal(a, b) for a, b in zip(auto[0], want[0]))
+    with pytest.raises(RuntimeError, match="candidates"):
+        DP.postprocess_detections(logits, reg, props, shapes, coder, 0.4, 0.5, 100, use_kernel=True)
