@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SNN_ABI_VERSION 7
+#define SNN_ABI_VERSION 8
 
 #define SNN_MODE_FP32_EXACT 0 /* 3 bf16 pieces per weight (24 mantissa bits): the parity mode          */
 #define SNN_MODE_BF16 1       /* 1 piece: weights rounded to bf16, the throughput mode                 */
@@ -191,6 +191,22 @@ int snn_li_readout_nhwc(const void* trains, int train_bytes, int N, int HW, int 
                         snn_stream_t stream);
 int snn_li_readout_rows(const void* trains, int train_bytes, int R, int Hd, const double* step_weights, const float* w_a,
                         int n_a, const float* w_b, int n_b, float* out_a, float* out_b, snn_stream_t stream);
+
+/* ---- "next" row 8f-1, second half: the tail of RegionProposalNetwork.filter_proposals (rpn.py:493-525) on the entries
+ * snn_rpn_topk_select / snn_rpn_decode_selected produced -- clip to the image, remove_small_boxes(min_size), score >=
+ * score_thresh, batched NMS over the levels, the post_nms_top_n best -- in one launch of n_levels x N blocks (every
+ * (image, level) is its own NMS problem; the last block of an image merges the levels), no host synchronisation.  The
+ * NMS repeats torchvision's CUDA path operation for operation (see snn_det_postprocess), including batched_nms's shift
+ * of the boxes by level * (largest coordinate of the image + 1) up to 5000 candidates per image.
+ * proposals [N][K][4] (decoded, NOT clipped), probs [N][K], level-major with level_sizes[l] entries of level l per image
+ * (HOST array; K = their sum; each <= 2048; sum_l min(post_nms_top_n, level_sizes[l]) <= 8192); img_h, img_w HOST [N].
+ * Outputs (device): out_boxes [N][post_nms_top_n][4] clipped, out_scores [N][post_nms_top_n] -- score descending, ties by
+ * the lower position --, out_counts [N] int32 rows written per image. */
+size_t snn_rpn_nms_workspace_bytes(int n_levels, int N);
+int snn_rpn_nms(const float* proposals, const float* probs, const int* level_sizes, const int* img_h, const int* img_w,
+                int n_levels, int N, float min_size, float score_thresh, float nms_thresh, int post_nms_top_n,
+                float* out_boxes, float* out_scores, int* out_counts, void* workspace, size_t workspace_bytes,
+                snn_stream_t stream);
 
 /* ---- "next" row 8f-4: the detector's post-processing, RoIHeadsSNN.postprocess_detections (roi_heads.py:1075-1176)
  * after its softmax and box decode: clip (l.1105), score threshold on classes >= 1 (l.1127-1128), the background box of

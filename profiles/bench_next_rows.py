@@ -76,6 +76,25 @@ def main():
     ds, db = (sr - so).abs().max().item(), ((pr - po).abs() / (1.0 + pr.abs())).max().item()
     assert ds <= 1e-6 and db <= 1e-5, f"fast path differs from the reference path: scores {ds}, boxes (relative) {db}"
 
+    # ---- the tail of filter_proposals (rpn.py:493-525) on the selected entries: clip, small, threshold, NMS 0.7, top 1000
+    po_, so_, lv_, _ = ours()
+
+    def rpn_filter():
+        return DP.filter_selected(po_, so_, lv_, [IMG] * N, 1e-3, 0.0, 0.7, 1000)
+
+    LEVEL_SIZES = [min(1000, A * h * w) for (h, w) in LEVELS]
+
+    def rpn_filter_kernel():
+        return DP.filter_selected(po_, so_, lv_, [IMG] * N, 1e-3, 0.0, 0.7, 1000, level_sizes=LEVEL_SIZES)
+
+    def rpn_filter():
+        return DP.filter_selected(po_, so_, lv_, [IMG] * N, 1e-3, 0.0, 0.7, 1000, use_kernel=False)
+
+    fa, fb = rpn_filter(), rpn_filter_kernel()
+    assert all(torch.equal(x, y) for k in range(2) for x, y in zip(fa[k], fb[k])), "rpn filter kernel differs from the torch ops"
+    t_rpn_filter, t_rpn_filter_kernel = timed(rpn_filter), timed(rpn_filter_kernel)
+    n_after_nms = [int(b.shape[0]) for b in fb[0]]
+
     # ---- detection post-processing: 2 x 1000 RoIs, 9 classes, thresholds of model.py:98-99
     C, R = 9, 1000
     logits = torch.randn(N * R, C, device=dev) * 2.5
@@ -172,6 +191,7 @@ def main():
                                     "words_equal_between_kernels": same_words},
             "shapes": "cityscapes batch 2 (294 624 anchors/img, 1000 RoIs/img)",
             "rpn_select_ms": {"reference_path": timed(reference_path), "ours": timed(ours)},
+            "rpn_filter_tail_ms": {"torch_ops": t_rpn_filter, "ours": t_rpn_filter_kernel, "proposals_after_nms": n_after_nms},
             "postprocess_ms": {"reference_python_mask_loop_only": timed(loop_mask_only, iters=3), "torch_ops_whole_function": timed(vectorised),
                                "ours_whole_function": timed(kernel_path), "of_which_softmax_and_decode": timed(softmax_and_decode_only),
                                "of_which_the_kernel": timed(det_kernel_only, iters=50),

@@ -25,10 +25,10 @@ EXPORTS = [
     "snn_last_launch_count", "snn_set_cta_group", "snn_profile_enable", "snn_profile_read", "snn_rpn_decode_selected",
     "snn_roi_align_encode", "snn_box_head_forward_encoded", "snn_encoder_table", "snn_encoder_selftest", "snn_set_fc_tiling", "snn_set_role_timers",
     "snn_set_clock_probe", "snn_host_cache_stats", "snn_rpn_topk_keys", "snn_set_roi_kernel", "snn_li_readout_nhwc", "snn_li_readout_rows", "snn_rpn_topk_workspace_bytes", "snn_rpn_topk_select", "snn_set_conv_multicast",
-    "snn_det_postprocess_max_candidates", "snn_det_postprocess",
+    "snn_det_postprocess_max_candidates", "snn_det_postprocess", "snn_rpn_nms_workspace_bytes", "snn_rpn_nms",
 ]
 # the ABI the argtypes below describe (include/snn_heads.h SNN_ABI_VERSION); a library of another version is refused
-EXPECTED_ABI = 7
+EXPECTED_ABI = 8
 PHASES = ["rpn_encoder", "rpn_conv_lif_gemm", "rpn_readout", "box_encoder", "fc6_lif_gemm", "fc7_lif_gemm", "box_readout"]
 
 _lock = threading.Lock()
@@ -64,6 +64,8 @@ def _declare(lib):
     f = c.c_float
     lib.snn_det_postprocess.argtypes = [vp, vp, pi, pi, pi, i, i, f, f, f, i, i, vp, vp, vp, vp, vp, vp]
     lib.snn_det_postprocess.restype = i
+    lib.snn_rpn_nms_workspace_bytes.argtypes = [i, i]; lib.snn_rpn_nms_workspace_bytes.restype = sz
+    lib.snn_rpn_nms.argtypes = [vp, vp, pi, pi, pi, i, i, f, f, f, i, vp, vp, vp, vp, sz, vp]; lib.snn_rpn_nms.restype = i
     lib.snn_box_head_forward_encoded.argtypes = lib.snn_box_head_forward.argtypes
     lib.snn_box_head_forward_encoded.restype = i
     lib.snn_roi_align_encode.argtypes = [pvp, pi, pi, c.POINTER(c.c_float), i, i, vp, vp, i, i, i, i, vp, vp, vp]

@@ -947,8 +947,6 @@ constexpr int kDetMaxCand = 8192;           // (RoI, class) pairs / RoIs per ima
 constexpr int kDetThreads = 1024;
 constexpr int kDetMaxImages = 64;           // images per launch (the parameter block holds their geometry)
 constexpr int kDetWords = kDetMaxCand / 32;    // bitmap words (alive / kept)
-constexpr int kDetSmemBytes = kDetMaxCand * (8 + 16 + 2) + kDetWords * 12 + 32 * (16 + 4 + 4 + 4 + 4 + 4) + 32;
-constexpr unsigned short kDetDead = 0xFFFFu;
 
 struct DetParams {
     const float* scores;            // [R_total][C] softmax scores
@@ -997,22 +995,179 @@ __device__ __forceinline__ bool det_suppresses(const float4 a, const float Sa, c
 }
 __device__ __forceinline__ float det_area(const float4 a) { return __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y)); }
 
+// Working set of one NMS problem in shared memory (boxes in sorted order) -- shared by the detector post-processing and
+// the RPN proposal filter.
+struct NmsSmem {
+    float4* sbox;                   // [n] the boxes NMS sees (shifted by the coordinate trick or not)
+    unsigned short* lab;            // [n] class / level: boxes of different labels never suppress each other
+    unsigned int* alive;            // [words] not yet looked at and not suppressed
+    unsigned int* keptb;            // [words] kept
+    float4* kbox; float* karea; int* klab;      // [32] this round's keepers
+    int* bidx;                      // [32] this round's candidates
+    unsigned int* supp;             // [32] pair tests of a round
+    int* scan;                      // [32] warp totals
+    int* pref;                      // [words] keepers before a word
+    int* misc;                      // [2] batch size, [3] keepers of the round, [4] cursor
+};
+constexpr int kNmsFixedBytes = 32 * (16 + 4 + 4 + 4 + 4 + 4) + 32;     // kbox .. scan, misc
+__device__ __forceinline__ NmsSmem nms_carve(unsigned char* base, int max_n) {       // base 16-byte aligned, max_n % 32 == 0
+    NmsSmem m;
+    const int words = max_n / 32;
+    m.sbox = reinterpret_cast<float4*>(base);
+    m.lab = reinterpret_cast<unsigned short*>(base + static_cast<size_t>(max_n) * 16);
+    m.alive = reinterpret_cast<unsigned int*>(base + static_cast<size_t>(max_n) * 18);
+    m.keptb = m.alive + words;
+    m.pref = reinterpret_cast<int*>(m.keptb + words);
+    m.kbox = reinterpret_cast<float4*>(m.pref + words);
+    m.karea = reinterpret_cast<float*>(m.kbox + 32);
+    m.klab = reinterpret_cast<int*>(m.karea + 32);
+    m.bidx = m.klab + 32;
+    m.supp = reinterpret_cast<unsigned int*>(m.bidx + 32);
+    m.scan = reinterpret_cast<int*>(m.supp + 32);
+    m.misc = m.scan + 32;
+    return m;
+}
+__host__ __device__ constexpr int nms_smem_bytes(int max_n) { return max_n * 18 + (max_n / 32) * 12 + kNmsFixedBytes; }
+
+// ascending bitonic sort of P (a power of two) unique 64-bit keys in shared memory; all kDetThreads threads call it
+__device__ __forceinline__ void block_bitonic_sort(unsigned long long* keys, int P) {
+    for (int size = 2; size <= P; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += kDetThreads) {
+                const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1)), hi = lo | stride;
+                const unsigned long long a = keys[lo], b = keys[hi];
+                const bool up = (lo & size) == 0;
+                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+}
+
+// Greedy NMS over m.sbox[0, n) in order (all kDetThreads threads call it; m.sbox / m.lab filled and synchronised):
+// afterwards m.keptb flags the first max_keep boxes kept.  32 candidates a round:
+//  A  warp 0 takes the next 32 boxes still alive;
+//  B  the block tests every pair of them (thread (l, m): would m suppress l?);
+//  C  warp 0 reads the keepers off in order (a box is kept iff no KEPT earlier box of the round suppresses it; earlier
+//     rounds' keepers have been applied to it already) and publishes them;
+//  D  the block tests every later box still alive against the round's keepers (one warp per box, one lane per keeper).
+__device__ __forceinline__ void nms_rounds(const NmsSmem& m, const int n, const int max_keep, const float thr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_words = (n + 31) >> 5;
+    for (int w = tid; w < n_words; w += kDetThreads) {
+        m.alive[w] = (w * 32 + 32 <= n) ? 0xFFFFFFFFu : ((1u << (n - w * 32)) - 1u);
+        m.keptb[w] = 0u;
+    }
+    if (tid == 0) m.misc[4] = 0;
+    __syncthreads();
+    int nk = 0;
+    while (nk < max_keep) {
+        if (warp == 0) {                            // A
+            const int cursor = m.misc[4];
+            int cnt = 0;
+            for (int w0 = cursor >> 5; cnt < 32 && w0 < n_words; w0 += 32) {
+                const int w = w0 + lane;
+                unsigned int bits = w < n_words ? m.alive[w] : 0u;
+                if (w == (cursor >> 5)) bits &= 0xFFFFFFFFu << (cursor & 31);
+                const int c = __popc(bits);
+                int incl = c;
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                int pos = cnt + incl - c;
+                while (bits && pos < 32) {
+                    m.bidx[pos++] = w * 32 + __ffs(static_cast<int>(bits)) - 1;
+                    bits &= bits - 1u;
+                }
+                cnt = min(32, cnt + __shfl_sync(0xffffffffu, incl, 31));
+            }
+            if (lane == 0) m.misc[2] = cnt;
+        }
+        __syncthreads();
+        const int cnt = m.misc[2];
+        if (cnt == 0) break;
+        {                                           // B: l = warp, m = lane
+            bool sup = false;
+            if (warp < cnt && lane < warp) {
+                const int il = m.bidx[warp], im = m.bidx[lane];
+                if (m.lab[il] == m.lab[im]) {
+                    const float4 a = m.sbox[im];
+                    sup = det_suppresses(a, det_area(a), m.sbox[il], thr);
+                }
+            }
+            const unsigned int bal = __ballot_sync(0xffffffffu, sup);
+            if (lane == 0) m.supp[warp] = bal;
+        }
+        __syncthreads();
+        if (warp == 0) {                            // C
+            const unsigned int supp = m.supp[lane];
+            unsigned int kept_mask = 0u, seen = 0u;
+            int k_here = 0;
+            for (int q = 0; q < cnt; ++q) {
+                const unsigned int sq = __shfl_sync(0xffffffffu, supp, q);
+                if (nk + k_here >= max_keep) break;                 // only the first max_keep are wanted
+                seen |= 1u << q;
+                if ((sq & kept_mask) == 0u) { kept_mask |= 1u << q; ++k_here; }
+            }
+            // every candidate looked at leaves the alive set; keepers are flagged and published for the block
+            if (lane < cnt && ((seen >> lane) & 1u)) {
+                const int me = m.bidx[lane];
+                atomicAnd(&m.alive[me >> 5], ~(1u << (me & 31)));
+                if ((kept_mask >> lane) & 1u) {
+                    atomicOr(&m.keptb[me >> 5], 1u << (me & 31));
+                    const int q = __popc(kept_mask & ((1u << lane) - 1u));
+                    const float4 b = m.sbox[me];
+                    m.kbox[q] = b; m.karea[q] = det_area(b); m.klab[q] = m.lab[me];
+                }
+            }
+            if (lane == 0) { m.misc[3] = k_here; m.misc[4] = m.bidx[cnt - 1] + 1; }
+        }
+        __syncthreads();
+        const int nkb = m.misc[3], from = m.misc[4];
+        nk += nkb;
+        if (nk >= max_keep) break;
+        {                                           // D
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            float Sa = 0.f;
+            int la = -1;
+            if (lane < nkb) { a = m.kbox[lane]; Sa = m.karea[lane]; la = m.klab[lane]; }
+            for (int jj = from + warp; jj < n; jj += kDetThreads / 32) {
+                if (!((m.alive[jj >> 5] >> (jj & 31)) & 1u)) continue;          // uniform over the warp
+                const bool sup = la == static_cast<int>(m.lab[jj]) && det_suppresses(a, Sa, m.sbox[jj], thr);
+                if (__any_sync(0xffffffffu, sup) && lane == 0) atomicAnd(&m.alive[jj >> 5], ~(1u << (jj & 31)));
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+}
+
+// rank of every keeper among the keepers (m.pref[word] = keepers before the word); returns their number.  n <= 32 * kDetThreads
+__device__ __forceinline__ int nms_kept_ranks(const NmsSmem& m, const int n) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_words = (n + 31) >> 5;
+    const unsigned int bits = tid < n_words ? m.keptb[tid] : 0u;
+    int incl = __popc(bits);
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) m.scan[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = m.scan[lane];
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+        m.scan[lane] = v;                           // inclusive totals of the warps
+    }
+    __syncthreads();
+    if (tid < n_words) m.pref[tid] = incl - __popc(bits) + (warp ? m.scan[warp - 1] : 0);
+    const int total = m.scan[31];
+    __syncthreads();
+    return total;
+}
+
+constexpr int kDetSmemBytes = kDetMaxCand * 8 + nms_smem_bytes(kDetMaxCand);
+
 __global__ void __launch_bounds__(kDetThreads) det_postprocess_kernel(const __grid_constant__ DetParams p) {
     extern __shared__ __align__(16) unsigned char det_smem[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(det_smem);                      // [kDetMaxCand]
-    float4* sbox = reinterpret_cast<float4*>(det_smem + static_cast<size_t>(kDetMaxCand) * 8);       // [kDetMaxCand]
-    unsigned short* lab = reinterpret_cast<unsigned short*>(det_smem + static_cast<size_t>(kDetMaxCand) * 24);
-    unsigned int* alive = reinterpret_cast<unsigned int*>(det_smem + static_cast<size_t>(kDetMaxCand) * 26);   // [kDetWords]
-    unsigned int* keptb = alive + kDetWords;                                                          // [kDetWords]
-    float4* kbox = reinterpret_cast<float4*>(keptb + kDetWords);                                      // [32] this round's keepers
-    float* karea = reinterpret_cast<float*>(kbox + 32);                                               // [32]
-    int* klab = reinterpret_cast<int*>(karea + 32);                                                   // [32]
-    int* bidx = klab + 32;                                                                            // [32] this round's candidates
-    int* s_scan = bidx + 32;                                                                          // [32] warp totals
-    unsigned int* s_supp = reinterpret_cast<unsigned int*>(s_scan + 32);                              // [32] pair tests of a round
-    int* s_pref = reinterpret_cast<int*>(s_supp + 32);                                                // [kDetWords] keepers before a word
-    int* s_misc = s_pref + kDetWords;                                     // [0] n, [1] max coordinate bits, [2] batch size, [3] keepers, [4] cursor
-    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const NmsSmem m = nms_carve(det_smem + static_cast<size_t>(kDetMaxCand) * 8, kDetMaxCand);
+    int* s_cnt = m.misc;                                           // [0] candidates, [1] max coordinate bits
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int C = p.C, Cm1 = C - 1, R = p.rows[img];
     const size_t r0 = static_cast<size_t>(p.row0[img]);
     const float W = p.img_w[img], H = p.img_h[img];
@@ -1026,7 +1181,7 @@ __global__ void __launch_bounds__(kDetThreads) det_postprocess_kernel(const __gr
     int n_written = 0;
     for (int set = 0; set < 2; ++set) {                 // 0: objects (classes >= 1), 1: background (class 0)
         const int n_src = set == 0 ? R * Cm1 : R;
-        if (tid < 5) s_misc[tid] = 0;
+        if (tid < 2) s_cnt[tid] = 0;
         __syncthreads();
         // ---- candidates (any order: the sort below fixes it; the key carries the reference's flat index
         //      r * (C - 1) + (c - 1), or r)
@@ -1050,34 +1205,24 @@ __global__ void __launch_bounds__(kDetThreads) det_postprocess_kernel(const __gr
                     if (pass) my_max = fmaxf(my_max, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
                 }
             }
-            const unsigned int m = __ballot_sync(0xffffffffu, pass);
+            const unsigned int bal = __ballot_sync(0xffffffffu, pass);
             int base = 0;
-            if (lane == 0 && m) base = atomicAdd(&s_misc[0], __popc(m));
+            if (lane == 0 && bal) base = atomicAdd(&s_cnt[0], __popc(bal));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (pass) keys[base + __popc(m & ((1u << lane) - 1u))] = det_key(s, static_cast<unsigned int>(f));
+            if (pass) keys[base + __popc(bal & ((1u << lane) - 1u))] = det_key(s, static_cast<unsigned int>(f));
         }
         for (int o = 16; o > 0; o >>= 1) my_max = fmaxf(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
-        if (lane == 0) atomicMax(&s_misc[1], __float_as_int(my_max));                  // clipped coordinates are >= 0
+        if (lane == 0) atomicMax(&s_cnt[1], __float_as_int(my_max));                   // clipped coordinates are >= 0
         __syncthreads();
-        const int n = s_misc[0];
+        const int n = s_cnt[0];
+        const float shift1 = __fadd_rn(__int_as_float(s_cnt[1]), 1.0f);
         int P = 2;
         while (P < n) P <<= 1;
         for (int t = n + tid; t < P; t += kDetThreads) keys[t] = ~0ull;
         __syncthreads();
-        // ---- stable descending sort of the scores (bitonic on unique keys)
-        for (int size = 2; size <= P; size <<= 1)
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int t = tid; t < (P >> 1); t += kDetThreads) {
-                    const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1)), hi = lo | stride;
-                    const unsigned long long a = keys[lo], b = keys[hi];
-                    const bool up = (lo & size) == 0;
-                    if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
-                }
-                __syncthreads();
-            }
+        block_bitonic_sort(keys, P);                    // stable descending sort of the scores (unique keys)
         // ---- the boxes NMS sees: batched_nms shifts them by label * (max + 1) unless there are more than 5000
         const bool trick = n * 4 <= 20000;
-        const float shift1 = __fadd_rn(__int_as_float(s_misc[1]), 1.0f);
         for (int t = tid; t < n; t += kDetThreads) {
             const unsigned int f = static_cast<unsigned int>(keys[t]);
             const int r = set == 0 ? static_cast<int>(f) / Cm1 : static_cast<int>(f);
@@ -1087,135 +1232,173 @@ __global__ void __launch_bounds__(kDetThreads) det_postprocess_kernel(const __gr
                 const float off = __fmul_rn(static_cast<float>(c), shift1);
                 b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off); b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
             }
-            sbox[t] = b;
-            lab[t] = static_cast<unsigned short>(c);
-        }
-        const int n_words = (n + 31) >> 5;
-        for (int w = tid; w < n_words; w += kDetThreads) {
-            alive[w] = (w * 32 + 32 <= n) ? 0xFFFFFFFFu : ((1u << (n - w * 32)) - 1u);
-            keptb[w] = 0u;
+            m.sbox[t] = b;
+            m.lab[t] = static_cast<unsigned short>(c);
         }
         __syncthreads();
-        // ---- greedy NMS in sorted order, 32 candidates a round:
-        //  A  warp 0 takes the next 32 boxes still alive;
-        //  B  the block tests every pair of them (thread (l, m): would m suppress l?);
-        //  C  warp 0 reads the keepers off in order (a box is kept iff no KEPT earlier box of the round suppresses it;
-        //     earlier rounds' keepers have been applied to it already) and publishes them;
-        //  D  the block tests every later box still alive against the round's keepers (one warp per box, one lane per
-        //     keeper).
-        const int max_keep = set == 0 ? p.det_per_img : 0x7FFFFFFF;
-        int nk = 0;
-        while (nk < max_keep) {
-            if (warp == 0) {                            // A
-                const int cursor = s_misc[4];
-                int cnt = 0;
-                for (int w0 = cursor >> 5; cnt < 32 && w0 < n_words; w0 += 32) {
-                    const int w = w0 + lane;
-                    unsigned int bits = w < n_words ? alive[w] : 0u;
-                    if (w == (cursor >> 5)) bits &= 0xFFFFFFFFu << (cursor & 31);
-                    const int c = __popc(bits);
-                    int incl = c;
-                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                    int pos = cnt + incl - c;
-                    while (bits && pos < 32) {
-                        bidx[pos++] = w * 32 + __ffs(static_cast<int>(bits)) - 1;
-                        bits &= bits - 1u;
-                    }
-                    cnt = min(32, cnt + __shfl_sync(0xffffffffu, incl, 31));
-                }
-                if (lane == 0) s_misc[2] = cnt;
-            }
-            __syncthreads();
-            const int cnt = s_misc[2];
-            if (cnt == 0) break;
-            {                                           // B: l = warp, m = lane
-                bool sup = false;
-                if (warp < cnt && lane < warp) {
-                    const int il = bidx[warp], im = bidx[lane];
-                    if (lab[il] == lab[im]) {
-                        const float4 a = sbox[im];
-                        sup = det_suppresses(a, det_area(a), sbox[il], p.nms_thresh);
-                    }
-                }
-                const unsigned int m = __ballot_sync(0xffffffffu, sup);
-                if (lane == 0) s_supp[warp] = m;
-            }
-            __syncthreads();
-            if (warp == 0) {                            // C
-                const unsigned int supp = s_supp[lane];
-                unsigned int kept_mask = 0u, seen = 0u;
-                int k_here = 0;
-                for (int m = 0; m < cnt; ++m) {
-                    const unsigned int sm = __shfl_sync(0xffffffffu, supp, m);
-                    if (nk + k_here >= max_keep) break;                 // the reference keeps the first detections_per_img
-                    seen |= 1u << m;
-                    if ((sm & kept_mask) == 0u) { kept_mask |= 1u << m; ++k_here; }
-                }
-                // every candidate looked at leaves the alive set; keepers are flagged and published for the block
-                if (lane < cnt && ((seen >> lane) & 1u)) {
-                    const int me = bidx[lane];
-                    atomicAnd(&alive[me >> 5], ~(1u << (me & 31)));
-                    if ((kept_mask >> lane) & 1u) {
-                        atomicOr(&keptb[me >> 5], 1u << (me & 31));
-                        const int q = __popc(kept_mask & ((1u << lane) - 1u));
-                        const float4 b = sbox[me];
-                        kbox[q] = b; karea[q] = det_area(b); klab[q] = lab[me];
-                    }
-                }
-                if (lane == 0) { s_misc[3] = k_here; s_misc[4] = bidx[cnt - 1] + 1; }
-            }
-            __syncthreads();
-            const int nkb = s_misc[3], from = s_misc[4];
-            nk += nkb;
-            if (nk >= max_keep) break;
-            {                                           // D
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                float Sa = 0.f;
-                int la = -1;
-                if (lane < nkb) { a = kbox[lane]; Sa = karea[lane]; la = klab[lane]; }
-                for (int jj = from + warp; jj < n; jj += kDetThreads / 32) {
-                    if (!((alive[jj >> 5] >> (jj & 31)) & 1u)) continue;        // uniform over the warp
-                    const bool sup = la == static_cast<int>(lab[jj]) && det_suppresses(a, Sa, sbox[jj], p.nms_thresh);
-                    if (__any_sync(0xffffffffu, sup) && lane == 0) atomicAnd(&alive[jj >> 5], ~(1u << (jj & 31)));
-                }
-            }
-            __syncthreads();
+        nms_rounds(m, n, set == 0 ? p.det_per_img : 0x7FFFFFFF, p.nms_thresh);
+        // ---- write the keepers in sorted order
+        const int total = nms_kept_ranks(m, n);
+        for (int t = tid; t < n; t += kDetThreads) {
+            const unsigned int wbits = m.keptb[t >> 5];
+            if (!((wbits >> (t & 31)) & 1u)) continue;
+            const int row = n_written + m.pref[t >> 5] + __popc(wbits & ((1u << (t & 31)) - 1u));
+            if (row >= p.cap) continue;
+            const unsigned int f = static_cast<unsigned int>(keys[t]);
+            const int r = set == 0 ? static_cast<int>(f) / Cm1 : static_cast<int>(f);
+            const int c = set == 0 ? 1 + (static_cast<int>(f) - r * Cm1) : 0;
+            const size_t o = static_cast<size_t>(img) * p.cap + row;
+            *reinterpret_cast<float4*>(p.out_boxes + o * 4) = det_clip(bx + (static_cast<size_t>(r) * C + c) * 4, W, H);
+            p.out_scores[o] = sc[static_cast<size_t>(r) * C + c];
+            p.out_labels[o] = c;
         }
-        __syncthreads();
-        // ---- write the keepers in sorted order: rank = number of keepers before
-        {
-            const unsigned int bits = tid < n_words ? keptb[tid] : 0u;          // kDetWords <= kDetThreads
-            int incl = __popc(bits);
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            if (lane == 31) s_scan[warp] = incl;
-            __syncthreads();
-            if (warp == 0) {
-                int v = s_scan[lane];
-                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-                s_scan[lane] = v;                       // inclusive totals of the warps
-            }
-            __syncthreads();
-            if (tid < n_words) s_pref[tid] = incl - __popc(bits) + (warp ? s_scan[warp - 1] : 0);
-            __syncthreads();
-            for (int t = tid; t < n; t += kDetThreads) {
-                const unsigned int wbits = keptb[t >> 5];
-                if (!((wbits >> (t & 31)) & 1u)) continue;
-                const int row = n_written + s_pref[t >> 5] + __popc(wbits & ((1u << (t & 31)) - 1u));
-                if (row >= p.cap) continue;
-                const unsigned int f = static_cast<unsigned int>(keys[t]);
-                const int r = set == 0 ? static_cast<int>(f) / Cm1 : static_cast<int>(f);
-                const int c = set == 0 ? 1 + (static_cast<int>(f) - r * Cm1) : 0;
-                const size_t o = static_cast<size_t>(img) * p.cap + row;
-                *reinterpret_cast<float4*>(p.out_boxes + o * 4) = det_clip(bx + (static_cast<size_t>(r) * C + c) * 4, W, H);
-                p.out_scores[o] = sc[static_cast<size_t>(r) * C + c];
-                p.out_labels[o] = c;
-            }
-            const int total = s_scan[31];
-            if (tid == 0) p.out_counts[img * 2 + set] = total;
-            n_written += total;
-        }
+        if (tid == 0) p.out_counts[img * 2 + set] = total;
+        n_written += total;
         __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The tail of RegionProposalNetwork.filter_proposals (rpn.py:493-525) on the selected and decoded entries of
+// snn_rpn_topk_select / snn_rpn_decode_selected: clip to the image, remove_small_boxes, score threshold, batched NMS over
+// the levels, the post_nms_top_n best.  torchvision's NMS spends milliseconds here (its keeper scan is one serial pass
+// over all 4864 boxes of an image).  batched NMS never lets boxes of different levels interact, so every (image, level)
+// is its own NMS problem: one block each sorts its <= 2048 candidates and runs the rounds above -- on the boxes as
+// batched_nms shifts them (level * (max coordinate of the IMAGE + 1), fp32 rounding included; no shift above 5000
+// candidates per image), so the kept set is torchvision's -- and writes its keepers' (score, index) keys; the last
+// block of an image to finish (ticket) merges the levels by one more sort and writes the post_nms_top_n best, score
+// descending, ties by the lower index, as the stable sort inside torchvision's nms orders them.
+constexpr int kRpnNmsMaxLevel = 2048;       // candidates per (image, level) = kTopkMaxK
+constexpr int kRpnNmsMaxKept = 8192;        // keepers per image the merging block sorts
+constexpr int kRpnNmsSmemBytes = kRpnNmsMaxKept * 8 + nms_smem_bytes(kRpnNmsMaxLevel);
+
+struct RpnNmsParams {
+    const float* props;             // [N][K][4] decoded boxes, not clipped
+    const float* probs;             // [N][K]
+    float* out_boxes;               // [N][post_n][4]
+    float* out_scores;              // [N][post_n]
+    int* out_counts;                // [N]
+    unsigned long long* kept_keys;  // workspace [N][L][kRpnNmsMaxLevel]
+    int* kept_cnt;                  // workspace [N][L]
+    unsigned int* done;             // workspace [N], zero before the launch
+    int N, L, K, post_n;
+    float min_size, score_thresh, nms_thresh;
+    int k_begin[kPropMaxLevels + 1];
+    float img_h[kDetMaxImages], img_w[kDetMaxImages];
+};
+
+__global__ void __launch_bounds__(kDetThreads) rpn_nms_kernel(const __grid_constant__ RpnNmsParams p) {
+    extern __shared__ __align__(16) unsigned char det_smem[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(det_smem);                      // [kRpnNmsMaxKept]
+    const NmsSmem m = nms_carve(det_smem + static_cast<size_t>(kRpnNmsMaxKept) * 8, kRpnNmsMaxLevel);
+    int* s_cnt = m.misc;                                // [0] candidates of the level, [1] max coordinate bits, [5] of the image, [6] ticket
+    const int l = blockIdx.x, img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const float W = p.img_w[img], H = p.img_h[img];
+    const float* bx = p.props + static_cast<size_t>(img) * p.K * 4;
+    const float* sc = p.probs + static_cast<size_t>(img) * p.K;
+    const int kb = p.k_begin[l], ke = p.k_begin[l + 1];
+    if (tid < 8) s_cnt[tid] = 0;
+    __syncthreads();
+    // ---- the image's candidates (all levels): their number picks batched_nms's variant, their largest coordinate its shift
+    {
+        int cnt = 0;
+        float my_max = 0.f;
+        for (int k = tid; k < p.K; k += kDetThreads) {
+            const float4 b = det_clip(bx + static_cast<size_t>(k) * 4, W, H);
+            if ((b.z - b.x >= p.min_size) && (b.w - b.y >= p.min_size) && sc[k] >= p.score_thresh) {
+                ++cnt;
+                my_max = fmaxf(my_max, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            my_max = fmaxf(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
+        }
+        if (lane == 0) { atomicAdd(&s_cnt[5], cnt); atomicMax(&s_cnt[1], __float_as_int(my_max)); }
+    }
+    // ---- this level's candidates; the key carries the entry's position in the image's level-major list
+    for (int k0 = kb; k0 < ke; k0 += kDetThreads) {
+        const int k = k0 + tid;
+        bool pass = false;
+        float s = 0.f;
+        if (k < ke) {
+            const float4 b = det_clip(bx + static_cast<size_t>(k) * 4, W, H);
+            s = sc[k];
+            pass = (b.z - b.x >= p.min_size) && (b.w - b.y >= p.min_size) && s >= p.score_thresh;
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, pass);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_cnt[0], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) keys[base + __popc(bal & ((1u << lane) - 1u))] = det_key(s, static_cast<unsigned int>(k));
+    }
+    __syncthreads();
+    const int n = s_cnt[0];
+    const bool trick = s_cnt[5] * 4 <= 20000;
+    const float off = trick ? __fmul_rn(static_cast<float>(l), __fadd_rn(__int_as_float(s_cnt[1]), 1.0f)) : 0.f;
+    int P = 2;
+    while (P < n) P <<= 1;
+    for (int t = n + tid; t < P; t += kDetThreads) keys[t] = ~0ull;
+    __syncthreads();
+    block_bitonic_sort(keys, P);
+    for (int t = tid; t < n; t += kDetThreads) {
+        float4 b = det_clip(bx + static_cast<size_t>(static_cast<unsigned int>(keys[t])) * 4, W, H);
+        if (trick) { b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off); b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off); }
+        m.sbox[t] = b;
+        m.lab[t] = 0;
+    }
+    __syncthreads();
+    nms_rounds(m, n, p.post_n, p.nms_thresh);
+    const int total = nms_kept_ranks(m, n);
+    unsigned long long* mine = p.kept_keys + (static_cast<size_t>(img) * p.L + l) * kRpnNmsMaxLevel;
+    for (int t = tid; t < n; t += kDetThreads) {
+        const unsigned int wbits = m.keptb[t >> 5];
+        if ((wbits >> (t & 31)) & 1u) mine[m.pref[t >> 5] + __popc(wbits & ((1u << (t & 31)) - 1u))] = keys[t];
+    }
+    if (tid == 0) p.kept_cnt[img * p.L + l] = total;
+    // ---- the last block of the image merges the levels
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_cnt[6] = static_cast<int>(atomicAdd(&p.done[img], 1u));
+    __syncthreads();
+    if (s_cnt[6] != p.L - 1) return;
+    __threadfence();
+    // every level's keepers are sorted (score descending, then position): a keeper's place in the merged order is its
+    // place in its own list plus, for every other list, the number of keys below it (binary search; keys are unique)
+    int* s_off = m.pref;                                // [L + 1] starts of the levels' lists in keys[]
+    if (tid == 0) {
+        int acc = 0;
+        for (int ll = 0; ll < p.L; ++ll) { s_off[ll] = acc; acc += __ldcg(&p.kept_cnt[img * p.L + ll]); }
+        s_off[p.L] = acc;
+    }
+    __syncthreads();
+    const int n_all = s_off[p.L];
+    for (int ll = 0; ll < p.L; ++ll) {
+        const unsigned long long* src = p.kept_keys + (static_cast<size_t>(img) * p.L + ll) * kRpnNmsMaxLevel;
+        for (int t = s_off[ll] + tid; t < s_off[ll + 1]; t += kDetThreads) keys[t] = __ldcg(&src[t - s_off[ll]]);
+    }
+    __syncthreads();
+    const int n_out = min(n_all, p.post_n);
+    for (int t = tid; t < n_all; t += kDetThreads) {
+        const unsigned long long key = keys[t];
+        int rank = 0;
+        for (int ll = 0; ll < p.L; ++ll) {
+            int lo = s_off[ll], hi = s_off[ll + 1];
+            if (t >= lo && t < hi) { rank += t - lo; continue; }
+            while (lo < hi) {                           // first position of the list whose key is not below `key`
+                const int mid = (lo + hi) >> 1;
+                if (keys[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            rank += lo - s_off[ll];
+        }
+        if (rank < n_out) {
+            const unsigned int k = static_cast<unsigned int>(key);
+            const size_t o = static_cast<size_t>(img) * p.post_n + rank;
+            *reinterpret_cast<float4*>(p.out_boxes + o * 4) = det_clip(bx + static_cast<size_t>(k) * 4, W, H);
+            p.out_scores[o] = sc[k];
+        }
+    }
+    if (tid == 0) p.out_counts[img] = n_out;
 }
 
 }  // namespace snn

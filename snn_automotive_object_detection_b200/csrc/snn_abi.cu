@@ -1080,6 +1080,76 @@ size_t snn_rpn_topk_workspace_bytes(int n_levels, int N) {
     return topk_ws_layout(n_levels, N).total;
 }
 
+namespace {
+struct RpnNmsWs { size_t keys, cnt, done, total; };
+RpnNmsWs rpn_nms_ws_layout(int n_levels, int N) {
+    RpnNmsWs w;
+    size_t off = 0;
+    w.keys = off; off = align_up(off + static_cast<size_t>(N) * n_levels * kRpnNmsMaxLevel * sizeof(unsigned long long), 256);
+    w.cnt = off; off = align_up(off + static_cast<size_t>(N) * n_levels * sizeof(int), 256);
+    w.done = off; off = align_up(off + static_cast<size_t>(N) * sizeof(unsigned int), 256);
+    w.total = off;
+    return w;
+}
+}  // namespace
+
+size_t snn_rpn_nms_workspace_bytes(int n_levels, int N) {
+    if (n_levels < 1 || n_levels > kPropMaxLevels || N < 1) return 0;
+    return rpn_nms_ws_layout(n_levels, N).total;
+}
+
+int snn_rpn_nms(const float* proposals, const float* probs, const int* level_sizes, const int* img_h, const int* img_w,
+                int n_levels, int N, float min_size, float score_thresh, float nms_thresh, int post_nms_top_n,
+                float* out_boxes, float* out_scores, int* out_counts, void* workspace, size_t workspace_bytes,
+                snn_stream_t stream) {
+    if (!proposals || !probs || !level_sizes || !img_h || !img_w || !out_boxes || !out_scores || !out_counts || !workspace)
+        return fail(SNN_E_ARG, "rpn_nms: null argument");
+    if (n_levels < 1 || n_levels > kPropMaxLevels || N < 1 || post_nms_top_n < 1)
+        return fail(SNN_E_ARG, "rpn_nms: bad sizes (levels %d, N %d, post_nms_top_n %d)", n_levels, N, post_nms_top_n);
+    RpnNmsParams p;
+    memset(&p, 0, sizeof(p));
+    long long K = 0, kept_max = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        if (level_sizes[l] < 0 || level_sizes[l] > kRpnNmsMaxLevel)
+            return fail(SNN_E_ARG, "rpn_nms: level %d has %d entries per image (limit %d)", l, level_sizes[l], kRpnNmsMaxLevel);
+        p.k_begin[l] = static_cast<int>(K);
+        K += level_sizes[l];
+        kept_max += level_sizes[l] < post_nms_top_n ? level_sizes[l] : post_nms_top_n;
+    }
+    p.k_begin[n_levels] = static_cast<int>(K);
+    if (kept_max > kRpnNmsMaxKept) return fail(SNN_E_ARG, "rpn_nms: up to %lld keepers per image (limit %d)", kept_max, kRpnNmsMaxKept);
+    if (((reinterpret_cast<uintptr_t>(proposals) | reinterpret_cast<uintptr_t>(out_boxes)) & 15) != 0)
+        return fail(SNN_E_ARG, "rpn_nms: boxes must be 16-byte aligned");
+    const RpnNmsWs w = rpn_nms_ws_layout(n_levels, N);
+    if (workspace_bytes < w.total) return fail(SNN_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, w.total);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(SNN_E_ARG, "workspace must be 256-B aligned");
+    DeviceInfo di;
+    if (int rc = device_info(di)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(ensure_dyn_smem(reinterpret_cast<const void*>(rpn_nms_kernel), kRpnNmsSmemBytes));
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    CUDA_TRY(cudaMemsetAsync(ws + w.done, 0, static_cast<size_t>(N) * sizeof(unsigned int), st));
+    p.L = n_levels; p.K = static_cast<int>(K); p.post_n = post_nms_top_n;
+    p.min_size = min_size; p.score_thresh = score_thresh; p.nms_thresh = nms_thresh;
+    for (int b0 = 0; b0 < N; b0 += kDetMaxImages) {
+        const int nb = N - b0 < kDetMaxImages ? N - b0 : kDetMaxImages;
+        p.N = nb;
+        p.props = proposals + static_cast<size_t>(b0) * K * 4; p.probs = probs + static_cast<size_t>(b0) * K;
+        p.out_boxes = out_boxes + static_cast<size_t>(b0) * post_nms_top_n * 4;
+        p.out_scores = out_scores + static_cast<size_t>(b0) * post_nms_top_n; p.out_counts = out_counts + b0;
+        p.kept_keys = reinterpret_cast<unsigned long long*>(ws + w.keys) + static_cast<size_t>(b0) * n_levels * kRpnNmsMaxLevel;
+        p.kept_cnt = reinterpret_cast<int*>(ws + w.cnt) + static_cast<size_t>(b0) * n_levels;
+        p.done = reinterpret_cast<unsigned int*>(ws + w.done) + b0;
+        for (int b = 0; b < nb; ++b) {
+            if (img_h[b0 + b] < 0 || img_w[b0 + b] < 0) return fail(SNN_E_ARG, "rpn_nms: image %d: bad size", b0 + b);
+            p.img_h[b] = static_cast<float>(img_h[b0 + b]); p.img_w[b] = static_cast<float>(img_w[b0 + b]);
+        }
+        rpn_nms_kernel<<<dim3(n_levels, nb), kDetThreads, kRpnNmsSmemBytes, st>>>(p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SNN_OK;
+}
+
 int snn_det_postprocess_max_candidates(void) { return kDetMaxCand; }
 
 int snn_det_postprocess(const float* scores, const float* boxes, const int* rois_per_image, const int* img_h,

@@ -216,10 +216,48 @@ def rpn_select_proposals(objectness: Sequence[Tensor], pred_bbox_deltas: Sequenc
     return boxes, scores, levels, ref_index
 
 
+_RPN_NMS_WS = {}                  # (device, levels, images) -> workspace of the proposal-filter kernel
+RPN_NMS_MAX_LEVEL = 2048          # entries per (image, level) snn_rpn_nms sorts in shared memory
+RPN_NMS_MAX_KEPT = 8192           # keepers per image its merging block sorts
+
+
 def filter_selected(proposals: Tensor, objectness_prob: Tensor, levels: Tensor, image_shapes: List[Tuple[int, int]],
-                    min_size: float, score_thresh: float, nms_thresh: float, post_nms_top_n: int):
-    """The tail of RegionProposalNetwork.filter_proposals (rpn.py:493-525) on the already selected / decoded entries."""
+                    min_size: float, score_thresh: float, nms_thresh: float, post_nms_top_n: int,
+                    level_sizes: Sequence[int] = None, use_kernel=None):
+    """The tail of RegionProposalNetwork.filter_proposals (rpn.py:493-525) on the already selected / decoded entries.
+    With `level_sizes` (entries per level and image of the level-major lists, as rpn_select_proposals lays them out) and
+    CUDA tensors it is one launch of `snn_rpn_nms` and one read of the per-image counts; `use_kernel=False` keeps the
+    torchvision ops below, whose result the kernel reproduces bit for bit (tests/test_detection_post.py)."""
     pre_nms = [{"proposals": prop, "objectness": objectness_prob[i]} for i, prop in enumerate(proposals)]
+    if use_kernel is None:
+        use_kernel = (level_sizes is not None and proposals.is_cuda and proposals.dtype == torch.float32
+                      and objectness_prob.dtype == torch.float32 and proposals.shape[0] >= 1
+                      and max(level_sizes) <= RPN_NMS_MAX_LEVEL
+                      and sum(min(int(post_nms_top_n), int(k)) for k in level_sizes) <= RPN_NMS_MAX_KEPT)
+    if use_kernel:
+        if level_sizes is None or sum(level_sizes) != proposals.shape[1]:
+            raise RuntimeError("filter_selected: level_sizes must add up to the entries per image")
+        lib = _lib.load()
+        dev = proposals.device
+        N, L, post_n = proposals.shape[0], len(level_sizes), int(post_nms_top_n)
+        props = proposals.contiguous()
+        probs = objectness_prob.contiguous()
+        out_boxes = torch.empty((N, post_n, 4), dtype=torch.float32, device=dev)
+        out_scores = torch.empty((N, post_n), dtype=torch.float32, device=dev)
+        counts = torch.empty((N,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _RPN_NMS_WS.get((str(dev), L, N))
+            if ws is None:
+                ws = _RPN_NMS_WS[(str(dev), L, N)] = torch.empty(lib.snn_rpn_nms_workspace_bytes(L, N), dtype=torch.uint8, device=dev)
+            IntL, IntN = ctypes.c_int * L, ctypes.c_int * N
+            rc = lib.snn_rpn_nms(props.data_ptr(), probs.data_ptr(), IntL(*[int(k) for k in level_sizes]),
+                                 IntN(*[int(s[0]) for s in image_shapes]), IntN(*[int(s[1]) for s in image_shapes]),
+                                 L, N, float(min_size), float(score_thresh), float(nms_thresh), post_n,
+                                 out_boxes.data_ptr(), out_scores.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                                 torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "snn_rpn_nms")
+        kept = counts.tolist()                             # the one synchronisation of the call
+        return [out_boxes[i, :kept[i]] for i in range(N)], [out_scores[i, :kept[i]] for i in range(N)], pre_nms
     final_boxes, final_scores = [], []
     for boxes, scores, lvl, img_shape in zip(proposals, objectness_prob, levels, image_shapes):
         boxes = box_ops.clip_boxes_to_image(boxes, img_shape)
@@ -242,8 +280,9 @@ def fast_rpn_forward(rpn, images, features: Dict[str, Tensor]):
     strides = [(image_size[0] // f.shape[-2], image_size[1] // f.shape[-1]) for f in feats]
     props, probs, levels, _ = rpn_select_proposals(objectness, pred_bbox_deltas, rpn.anchor_generator.cell_anchors,
                                                    strides, rpn.pre_nms_top_n())
+    level_sizes = [min(int(rpn.pre_nms_top_n()), int(o.shape[1] * o.shape[2] * o.shape[3])) for o in objectness]
     boxes, _scores, pre_nms = filter_selected(props, probs, levels, images.image_sizes, rpn.min_size, rpn.score_thresh,
-                                              rpn.nms_thresh, rpn.post_nms_top_n())
+                                              rpn.nms_thresh, rpn.post_nms_top_n(), level_sizes=level_sizes)
     return boxes, pre_nms
 
 

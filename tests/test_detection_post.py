@@ -297,3 +297,55 @@ def test_postprocess_kernel_limits_fall_back_or_fail_loudly():
     assert all(torch.equal(a, b) for a, b in zip(auto[0], want[0]))
     with pytest.raises(RuntimeError, match="candidates"):
         DP.postprocess_detections(logits, reg, props, shapes, coder, 0.4, 0.5, 100, use_kernel=True)
+
+
+def _random_selected_proposals(seed, N, level_sizes, image_hw, saturated=0, device="cuda"):
+    """Level-major selected proposals as rpn_select_proposals returns them: per level, objectness descending; boxes
+    clustered so that NMS at 0.7 has work to do; some boxes outside the image or degenerate."""
+    g = torch.Generator().manual_seed(seed)
+    ih, iw = image_hw
+    props, probs, levels = [], [], []
+    for l, k in enumerate(level_sizes):
+        size = 32.0 * 2 ** l
+        ctr = torch.rand(N, k, 2, generator=g) * torch.tensor([iw * 1.1, ih * 1.1]) - torch.tensor([iw * 0.05, ih * 0.05])
+        ctr = (ctr / (size / 2)).round() * (size / 2) + torch.randn(N, k, 2, generator=g) * size * 0.08
+        wh = (torch.rand(N, k, 2, generator=g) * 0.6 + 0.7) * size
+        wh[:, : max(1, k // 50)] *= 1e-5                                   # a few boxes below min_size
+        props.append(torch.cat([ctr - wh / 2, ctr + wh / 2], dim=2))
+        pr = torch.sigmoid(torch.randn(N, k, generator=g) * 3).sort(dim=1, descending=True)[0]
+        if saturated:
+            pr[:, :saturated] = 1.0                                       # exact ties at the top (a saturated sigmoid)
+        probs.append(pr)
+        levels.append(torch.full((N, k), l, dtype=torch.int64))
+    return torch.cat(props, 1).to(device), torch.cat(probs, 1).to(device), torch.cat(levels, 1).to(device)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,N,level_sizes,post_n,score_thresh,saturated", [
+    ("bench_shape", 2, [1000, 1000, 1000, 1000, 864], 1000, 0.0, 0),
+    ("training_sizes_over_5000_boxes", 2, [2000, 2000, 2000, 1152, 288], 2000, 0.0, 0),     # per-class NMS, no shift
+    ("score_threshold", 3, [1000, 1000, 500, 100, 7], 300, 0.3, 0),
+    ("saturated_scores_tie", 2, [600, 600, 600], 1000, 0.0, 25),
+    ("one_level", 1, [1500], 100, 0.0, 0),
+    ("nothing_left", 2, [50, 50], 100, 1.5, 0),
+])
+def test_rpn_filter_kernel_equals_the_torchvision_path(name, N, level_sizes, post_n, score_thresh, saturated):
+    """SURVEY 8f-1, the tail of filter_proposals (rpn.py:493-525): `snn_rpn_nms` (one launch, one block per (image,
+    level), the last block of an image merges) against clip / remove_small_boxes / threshold / torchvision batched_nms /
+    top-n on the same inputs -- the same proposals in the same order, bit for bit."""
+    shapes = [(768, 1536), (700, 1400), (768, 1365)][:N]
+    props, probs, levels = _random_selected_proposals(sum(map(ord, name)), N, level_sizes, (768, 1536), saturated)
+    want = DP.filter_selected(props, probs, levels, shapes, 1e-3, score_thresh, 0.7, post_n, use_kernel=False)
+    got = DP.filter_selected(props, probs, levels, shapes, 1e-3, score_thresh, 0.7, post_n, level_sizes=level_sizes,
+                             use_kernel=True)
+    auto = DP.filter_selected(props, probs, levels, shapes, 1e-3, score_thresh, 0.7, post_n, level_sizes=level_sizes)
+    n_kept = [int(b.shape[0]) for b in want[0]]
+    if name == "nothing_left":
+        assert n_kept == [0] * N
+    else:
+        assert min(n_kept) > 0 and (name != "bench_shape" or min(n_kept) > 100), n_kept
+    for out in (got, auto):
+        for i in range(N):
+            assert out[0][i].shape == want[0][i].shape, (name, i, out[0][i].shape, want[0][i].shape)
+            assert torch.equal(out[1][i], want[1][i]), (name, i, "scores")
+            assert torch.equal(out[0][i], want[0][i]), (name, i, "boxes")
