@@ -101,7 +101,7 @@ def _det_kernel_eligible(pred_scores, pred_boxes, boxes_per_image, num_classes) 
 
 
 def _postprocess_detections_kernel(pred_scores, pred_boxes, boxes_per_image, image_shapes, score_thresh, nms_thresh,
-                                   detections_per_img):
+                                   detections_per_img, objects_only=False):
     lib = _lib.load()
     dev = pred_scores.device
     n_img, C = len(boxes_per_image), pred_scores.shape[-1]
@@ -122,7 +122,7 @@ def _postprocess_detections_kernel(pred_scores, pred_boxes, boxes_per_image, ima
                                      out_labels.data_ptr(), counts.data_ptr(),
                                      torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "snn_det_postprocess")
-    kept = counts.sum(dim=1).tolist()                      # the one synchronisation of the call
+    kept = (counts[:, 0] if objects_only else counts.sum(dim=1)).tolist()      # the one synchronisation of the call
     boxes = [out_boxes[b, :kept[b]] for b in range(n_img)]
     scores = [out_scores[b, :kept[b]] for b in range(n_img)]
     labels = [out_labels[b, :kept[b]] for b in range(n_img)]
@@ -134,6 +134,29 @@ def patch_postprocess(roi_heads):
     def _pp(self, class_logits, box_regression, proposals, image_shapes):
         return postprocess_detections(class_logits, box_regression, proposals, image_shapes, self.box_coder,
                                       self.score_thresh, self.nms_thresh, self.detections_per_img)
+    roi_heads.postprocess_detections = types.MethodType(_pp, roi_heads)
+    return roi_heads
+
+
+def patch_postprocess_torchvision(roi_heads):
+    """The same for a stock torchvision RoIHeads, whose postprocess_detections returns (boxes, scores, labels) without
+    the reference's background boxes and `all_*` lists -- the objects part of the reference's function, which is where
+    the reference took it from (roi_heads.py:1075-1134 = torchvision's).  CUDA tensors within the kernel's limits run
+    `snn_det_postprocess` and return its object rows; anything else goes to torchvision's own method."""
+    original = roi_heads.postprocess_detections
+
+    def _pp(self, class_logits, box_regression, proposals, image_shapes):
+        boxes_per_image = [b.shape[0] for b in proposals]
+        if not (class_logits.is_cuda and class_logits.dtype == torch.float32 and len(boxes_per_image) >= 1
+                and class_logits.shape[-1] >= 2 and max(boxes_per_image) * (class_logits.shape[-1] - 1)
+                <= _lib.load().snn_det_postprocess_max_candidates()):
+            return original(class_logits, box_regression, proposals, image_shapes)
+        pred_boxes = self.box_coder.decode(box_regression, proposals)
+        pred_scores = F.softmax(class_logits, -1)
+        boxes, scores, labels, _, _ = _postprocess_detections_kernel(pred_scores, pred_boxes, boxes_per_image, image_shapes,
+                                                                    self.score_thresh, self.nms_thresh,
+                                                                    self.detections_per_img, objects_only=True)
+        return boxes, scores, labels
     roi_heads.postprocess_detections = types.MethodType(_pp, roi_heads)
     return roi_heads
 
@@ -304,6 +327,8 @@ def attach_fast_postprocessing(model):
     rpn.forward = types.MethodType(_forward, rpn)
     if reference_style:                                              # the reference's RoIHeadsSNN
         patch_postprocess(model.roi_heads)
+    else:
+        patch_postprocess_torchvision(model.roi_heads)
     return model
 
 
@@ -372,7 +397,10 @@ def attach_fused_roi_pool(model):
     forward hands the pooler's output straight to `box_head_and_predictor`, roi_heads.py:1217-1230)."""
     rh = model.roi_heads
     head = getattr(rh, "box_head_and_predictor", None)
-    if head is None:
-        raise RuntimeError("attach_fused_roi_pool: needs the reference's RoIHeadsSNN (box_head_and_predictor)")
+    if head is None and isinstance(getattr(rh, "box_head", None), torch.nn.Identity):
+        head = getattr(rh, "box_predictor", None)        # stock torchvision RoIHeads as attach_snn_heads leaves them
+    if head is None or not hasattr(head, "num_steps"):
+        raise RuntimeError("attach_fused_roi_pool: needs the reference's RoIHeadsSNN (box_head_and_predictor) or a "
+                           "torchvision RoIHeads prepared by attach_snn_heads")
     rh.box_roi_pool = FusedRoIAlignEncoder.from_pooler(rh.box_roi_pool, int(head.num_steps))
     return model

@@ -349,3 +349,24 @@ def test_rpn_filter_kernel_equals_the_torchvision_path(name, N, level_sizes, pos
             assert out[0][i].shape == want[0][i].shape, (name, i, out[0][i].shape, want[0][i].shape)
             assert torch.equal(out[1][i], want[1][i]), (name, i, "scores")
             assert torch.equal(out[0][i], want[0][i]), (name, i, "boxes")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("thresh,per_img", [(0.05, 100), (0.4, 100), (0.2, 7)])
+def test_torchvision_roi_heads_postprocess_patched_equals_the_stock_method(thresh, per_img):
+    """A stock torchvision RoIHeads (what attach_snn_heads leaves on a torchvision Faster R-CNN): its own
+    postprocess_detections against the patched one (snn_det_postprocess, object rows) -- same detections, same order."""
+    from torchvision.models.detection import fasterrcnn_resnet50_fpn
+    model = fasterrcnn_resnet50_fpn(weights=None, weights_backbone=None, num_classes=9, box_score_thresh=thresh,
+                                    box_detections_per_img=per_img)
+    rh = model.roi_heads
+    logits, reg, props, shapes = _random_detector_outputs(77, [1000, 640], 9, 2.0)
+    want = rh.postprocess_detections(logits, reg, props, shapes)
+    DP.patch_postprocess_torchvision(rh)
+    got = rh.postprocess_detections(logits, reg, props, shapes)
+    assert sum(int(b.shape[0]) for b in want[0]) > 0
+    for k in range(3):
+        for a, b in zip(want[k], got[k]):
+            assert a.shape == b.shape and a.dtype == b.dtype and torch.equal(a, b), (k, a.shape, b.shape)
+    cpu = rh.postprocess_detections(logits.cpu(), reg.cpu(), [p.cpu() for p in props], shapes)     # torchvision's method
+    assert all(a.shape == b.shape for a, b in zip(cpu[2], want[2]))
