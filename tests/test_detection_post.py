@@ -370,3 +370,23 @@ def test_torchvision_roi_heads_postprocess_patched_equals_the_stock_method(thres
             assert a.shape == b.shape and a.dtype == b.dtype and torch.equal(a, b), (k, a.shape, b.shape)
     cpu = rh.postprocess_detections(logits.cpu(), reg.cpu(), [p.cpu() for p in props], shapes)     # torchvision's method
     assert all(a.shape == b.shape for a, b in zip(cpu[2], want[2]))
+
+
+@pytest.mark.gpu
+def test_post_kernels_with_more_images_than_one_launch_holds():
+    """Both kernels keep the images' geometry in their parameter block, 64 images a launch: 70 images take two."""
+    N = 70
+    rois = [12 + (i * 7) % 30 for i in range(N)]
+    logits, reg, props, shapes = _random_detector_outputs(3, rois, 5, 2.0)
+    coder = det_utils.BoxCoder((10.0, 10.0, 5.0, 5.0))
+    want = DP.postprocess_detections(logits, reg, props, shapes, coder, 0.3, 0.5, 10, use_kernel=False)
+    got = DP.postprocess_detections(logits, reg, props, shapes, coder, 0.3, 0.5, 10, use_kernel=True)
+    for k in range(5):
+        assert all(torch.equal(a, b) for a, b in zip(want[k], got[k])), k
+    level_sizes = [40, 0, 25]                                               # and a level without entries
+    p, s, lv = _random_selected_proposals(9, N, level_sizes, (256, 320))
+    shapes = [(256, 320)] * N
+    want = DP.filter_selected(p, s, lv, shapes, 1e-3, 0.0, 0.7, 30, use_kernel=False)
+    got = DP.filter_selected(p, s, lv, shapes, 1e-3, 0.0, 0.7, 30, level_sizes=level_sizes, use_kernel=True)
+    for k in range(2):
+        assert all(a.shape == b.shape and torch.equal(a, b) for a, b in zip(want[k], got[k])), k
