@@ -978,6 +978,8 @@ __device__ __forceinline__ unsigned long long det_key(float score, unsigned int 
 // torchvision's devIoU(keeper a, candidate b) > threshold, as nvcc compiled it for sm_100 (see above)
 __device__ __forceinline__ bool det_suppresses(const float4 a, const float Sa, const float4 b, const float thr) {
     const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z), top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+    // disjoint boxes (most pairs): the intersection is 0 (or NaN), the quotient 0, -0 or NaN, never > a threshold >= 0
+    if (thr >= 0.f && (right <= left || bottom <= top)) return false;
     const float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
     const float inter = __fmul_rn(w, h);
     const float sum = __fmaf_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y), Sa);
