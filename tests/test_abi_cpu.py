@@ -133,3 +133,30 @@ def test_workspace_sizes_are_host_only_and_cover_the_carried_state(lib):
     assert R * K * 4 + 2 * R * Hd * 4 + R * Hd * 16 <= b32 <= R * K * 4 + 2 * R * Hd * 4 + R * Hd * 16 + 16384
     assert lib.snn_box_head_workspace_bytes(R, K, Hd, 2, 3) > 0          # T < 3 runs (zero membranes, as the reference)
     assert lib.snn_box_head_workspace_bytes(R, K, Hd, 0, 3) == 0 and lib.snn_box_head_workspace_bytes(R, K, Hd, 33, 3) == 0
+
+
+def test_post_processing_entry_points_validate_on_the_host(lib):
+    """snn_det_postprocess / snn_rpn_nms: sizes and limits are checked before any CUDA call; the workspace query is
+    host-only."""
+    c = ctypes
+    assert lib.snn_det_postprocess_max_candidates() == 8192
+    assert lib.snn_rpn_nms_workspace_bytes(5, 2) >= 5 * 2 * 2048 * 8 and lib.snn_rpn_nms_workspace_bytes(0, 2) == 0
+    one, big = (c.c_int * 1)(1000), (c.c_int * 1)(1025)
+    hw = (c.c_int * 1)(768)
+    rc = lib.snn_det_postprocess(None, None, one, hw, hw, 0, 9, 0.4, 0.5, 0.01, 100, 1100, None, None, None, None, None, None)
+    assert rc != 0 and b"null" in lib.snn_last_error()
+    cnt = (c.c_int * 2)()
+    rc = lib.snn_det_postprocess(None, None, big, hw, hw, 1, 9, 0.4, 0.5, 0.01, 100, 1200, None, None, None, None,
+                                 c.cast(cnt, c.c_void_p), None)
+    assert rc != 0 and b"candidates" in lib.snn_last_error()           # 1025 RoIs x 8 classes > 8192
+    rc = lib.snn_det_postprocess(None, None, one, hw, hw, 1, 9, 0.4, 0.5, 0.01, 100, 500, None, None, None, None,
+                                 c.cast(cnt, c.c_void_p), None)
+    assert rc != 0 and b"cap" in lib.snn_last_error()
+    buf = c.create_string_buffer(64)
+    p = c.cast(buf, c.c_void_p)
+    sizes = (c.c_int * 2)(3000, 10)
+    rc = lib.snn_rpn_nms(p, p, sizes, hw, hw, 2, 1, 1e-3, 0.0, 0.7, 1000, p, p, p, p, 64, None)
+    assert rc != 0 and b"limit" in lib.snn_last_error()                # 3000 entries in a level > 2048
+    sizes = (c.c_int * 5)(2000, 2000, 2000, 2000, 2000)
+    rc = lib.snn_rpn_nms(p, p, sizes, hw, hw, 5, 1, 1e-3, 0.0, 0.7, 2000, p, p, p, p, 64, None)
+    assert rc != 0 and b"keepers" in lib.snn_last_error()              # 10000 possible keepers > 8192
