@@ -390,3 +390,45 @@ def test_post_kernels_with_more_images_than_one_launch_holds():
     got = DP.filter_selected(p, s, lv, shapes, 1e-3, 0.0, 0.7, 30, level_sizes=level_sizes, use_kernel=True)
     for k in range(2):
         assert all(a.shape == b.shape and torch.equal(a, b) for a, b in zip(want[k], got[k])), k
+
+
+def _threshold_pairs(seed, n_pairs, ratio, image_hw, device="cuda"):
+    """Pairs of boxes whose IoU is `ratio` in exact arithmetic (one box is the other cut to `ratio` of its height), at
+    random scales and translations: in fp32 every pair lands within a few ulps of the NMS threshold, on either side,
+    so the kept set depends on every rounding of the IoU (the FMUL / FFMA / division sequence torchvision compiles to)."""
+    g = torch.Generator().manual_seed(seed)
+    ih, iw = image_hw
+    s = torch.rand(n_pairs, 1, generator=g) * 40 + 3
+    t = torch.rand(n_pairs, 2, generator=g) * torch.tensor([iw - 60.0, ih - 60.0])
+    a = torch.cat([t, t + s], dim=1)
+    b = torch.cat([t, t[:, :1] + s, t[:, 1:] + s * ratio], dim=1)
+    return torch.stack([a, b], dim=1).reshape(-1, 4).to(device)             # a0, b0, a1, b1, ...
+
+
+@pytest.mark.gpu
+def test_nms_decisions_on_the_threshold_follow_torchvisions_rounding():
+    # detector post-processing, NMS 0.5: 600 pairs with IoU 0.5 +- ulps, one object class, distinct scores
+    boxes = _threshold_pairs(1, 600, 0.5, (768, 1536))
+    R = boxes.shape[0]
+    g = torch.Generator().manual_seed(2)
+    logits = torch.stack([torch.zeros(R), torch.rand(R, generator=g) * 4 + 1], dim=1).cuda()
+    reg = torch.zeros(R, 8, device="cuda")
+    coder = det_utils.BoxCoder((10.0, 10.0, 5.0, 5.0))
+    want = DP.postprocess_detections(logits, reg, [boxes], [(768, 1536)], coder, 0.4, 0.5, 2000, use_kernel=False)
+    got = DP.postprocess_detections(logits, reg, [boxes], [(768, 1536)], coder, 0.4, 0.5, 2000, use_kernel=True)
+    kept = int(want[0][0].shape[0])
+    assert R * 0.55 < kept < R * 0.95, kept                 # a good share of the pairs falls on each side
+    for k in range(5):
+        assert torch.equal(want[k][0], got[k][0]), k
+    # proposal filter, NMS 0.7, two levels (the second one shifted by the coordinate trick, which rounds the boxes)
+    props = _threshold_pairs(3, 500, 0.7, (768, 1536)).reshape(1, -1, 4)
+    K = props.shape[1]
+    probs = torch.rand(1, K, generator=g).sort(dim=1, descending=True)[0].cuda()
+    sizes = [K // 2, K - K // 2]
+    probs = torch.cat([probs[:, 0::2], probs[:, 1::2]], dim=1).contiguous()         # descending inside each level
+    levels = torch.cat([torch.zeros(1, sizes[0]), torch.ones(1, sizes[1])], dim=1).long().cuda()
+    want = DP.filter_selected(props, probs, levels, [(768, 1536)], 1e-3, 0.0, 0.7, 2000, use_kernel=False)
+    got = DP.filter_selected(props, probs, levels, [(768, 1536)], 1e-3, 0.0, 0.7, 2000, level_sizes=sizes, use_kernel=True)
+    kept = int(want[0][0].shape[0])
+    assert K * 0.55 < kept < K * 0.95, kept
+    assert torch.equal(want[0][0], got[0][0]) and torch.equal(want[1][0], got[1][0])
